@@ -1,0 +1,109 @@
+/*
+ * csx_b200.h — thin C-ABI of the B200 CSX SpMV engine.
+ *
+ * This is the boundary between host code (C, C++, ctypes, cgo, JNI ...) and the
+ * CUDA kernels: plain pointers and sizes, no C++ or torch types.  The SparseX
+ * public API (include/sparsex/sparsex.h, spx_* functions) is implemented on top
+ * of these entry points in sparsex_b200/csrc/api.cpp; each entry point below
+ * names the reference interface it stands in for (file:line into the SparseX
+ * tree).
+ *
+ * Threading: like the reference (global RtConfig/ThreadPool singletons,
+ * Runtime.hpp:74-78), one caller thread per matrix handle.
+ */
+#ifndef CSX_B200_H
+#define CSX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct csxb_matrix csxb_matrix_t;
+
+/* ---- tuning (host) ------------------------------------------------------
+ * Replaces TuneCSR / TuneMMF -> SparseMatrix::CreateCsx()
+ * (src/internals/Facade.cpp:86-122, SparseMatrix.hpp:123-255) and everything
+ * below it (BuildPartitions, EncodingManager, CsxManager).
+ *
+ * `options` is a ';'-separated list of "mnemonic=value" pairs using the
+ * reference's property names (src/internals/Runtime.cpp:65-95), e.g.
+ * "spx.preproc.xform=all;spx.rt.nr_threads=8".  spx.rt.nr_threads is the number
+ * of row partitions.  Partitions [part_lo, part_hi) are encoded by this call
+ * (one process per GPU encodes only its own partition); pass 0, -1 for all.
+ * CSR arrays are zero-based and are only read during the call.
+ * Returns NULL and fills `err` on failure (the reference calls exit(1)).
+ */
+csxb_matrix_t *csxb_tune_csr(const int32_t *rowptr, const int32_t *colind, const double *values,
+                             int64_t nrows, int64_t ncols, const char *options,
+                             int part_lo, int part_hi, char *err, size_t errlen);
+csxb_matrix_t *csxb_tune_mmf(const char *path, const char *options, int part_lo, int part_hi,
+                             char *err, size_t errlen);
+void csxb_destroy(csxb_matrix_t *m);
+
+/* Matrix-level queries (spx_mat_get_nrows/ncols/nnz, src/api/matvec.c:447-476). */
+enum { CSXB_NROWS = 0, CSXB_NCOLS = 1, CSXB_NNZ = 2, CSXB_SYMMETRIC = 3, CSXB_NPARTS = 4,
+       CSXB_NPARTS_TOTAL = 5, CSXB_PART_LO = 6, CSXB_FULL_COLIND = 7 };
+int64_t csxb_info(const csxb_matrix_t *m, int what);
+
+/* Per-partition CSX arrays == csx_matrix_t / csx_sym_matrix_t / map_t
+ * (include/sparsex/internals/Csx.hpp:29-53, Map.hpp:23-27).  `part` is local
+ * (0 .. CSXB_NPARTS-1).  Used by spx_mat_get_partition and by the parity tests. */
+enum { CSXB_P_NNZ = 0, CSXB_P_NROWS = 1, CSXB_P_NCOLS = 2, CSXB_P_ROW_START = 3, CSXB_P_CTL_SIZE = 4,
+       CSXB_P_ROW_JUMPS = 5, CSXB_P_ID_MAP_LEN = 6, CSXB_P_MAP_LEN = 7, CSXB_P_DVALUES_LEN = 8,
+       CSXB_P_ROWS_INFO_LEN = 9, CSXB_P_SAMPLING_UNDEFINED = 10 };
+int64_t csxb_part_info(const csxb_matrix_t *m, int part, int what);
+/* what: values f64[nnz] | ctl u8[ctl_size] | id_map i64[len] | rows_info {i64 rowptr,i64 valptr,i32 span,i32 pad}[nrows]
+ *       | dvalues f64 | map_cpus u32 | map_pos u32 */
+enum { CSXB_A_VALUES = 0, CSXB_A_CTL = 1, CSXB_A_ID_MAP = 2, CSXB_A_ROWS_INFO = 3, CSXB_A_DVALUES = 4,
+       CSXB_A_MAP_CPUS = 5, CSXB_A_MAP_POS = 6 };
+int csxb_part_copy(const csxb_matrix_t *m, int part, int what, void *dst);
+/* Human-readable encoding sequence chosen for a partition, e.g. "d{1} h{1} ". */
+const char *csxb_part_log(const csxb_matrix_t *m, int part);
+
+/* ---- device ---------------------------------------------------------------
+ * Replaces the per-partition JIT (CsxJit::GenCode, CsxJit.hpp:675-732) and
+ * CreatePool (Facade.cpp:207-212): derives the GPU side tables from the ctl
+ * stream and copies values/ctl/tables to `device`.  `free_host` != 0 drops the
+ * host copies of values afterwards (ctl/id_map stay for introspection).
+ * Returns 0 or a negative error (message via csxb_last_error). */
+int csxb_upload(csxb_matrix_t *m, int device, int free_host);
+const char *csxb_last_error(void);
+
+/* Device footprint and algorithmic traffic of one SpMV over the local
+ * partitions, in bytes: */
+enum { CSXB_B_VALUES = 0, CSXB_B_CTL = 1, CSXB_B_TABLES = 2, CSXB_B_X = 3, CSXB_B_Y = 4, CSXB_B_TOTAL = 5,
+       CSXB_B_LAUNCHES = 6 /* kernels launched per SpMV */ };
+int64_t csxb_traffic(const csxb_matrix_t *m, int what);
+
+/* y[rows of the local partitions] = alpha * A_local * x (+ beta * y).
+ * Replaces MatVecMult / MatVecKernel and their _sym variants
+ * (src/internals/CsxKernels.cpp:35-129) plus the generated
+ * spm_csx_multiply / spm_csx_sym_multiply (src/templates/csx_spmv_tmpl.c:66-101,
+ * csx_sym_spmv_tmpl.c:60-106).
+ *   d_x : device pointer, ncols doubles (the whole x vector)
+ *   d_y : device pointer, nrows doubles (the whole y vector; only local rows are written)
+ *   overwrite != 0 : spx_matvec_mult semantics (y := alpha*A*x, beta ignored, CsxKernels.cpp:93)
+ *   overwrite == 0 : spx_matvec_kernel semantics (y := alpha*A*x + beta*y, CsxSpmv.cpp:52-65)
+ *   stream : cudaStream_t (NULL = default stream).  Asynchronous.
+ * CSX-Sym matrices need every partition local (single GPU) in this version. */
+int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, double *d_y,
+              int overwrite, void *stream);
+
+/* Host-buffer convenience used by spx_matvec_* for vectors the library does
+ * not own: H2D x (and y when beta matters), SpMV, D2H of the local y rows.
+ * Synchronous. */
+int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double beta, double *h_y,
+                   int overwrite);
+
+/* Debug/parity aid: decode the device-side tables back into (row, col) pairs
+ * in values order for partition `part` (0-based global coordinates), running
+ * the same ctl walk the kernels use but on the host copy of the tables. */
+int csxb_decode_coords(const csxb_matrix_t *m, int part, int32_t *rows, int32_t *cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSX_B200_H */

@@ -1,0 +1,576 @@
+// SparseX C API (spx_*) on top of the csxb_* engine ABI — the drop-in surface.
+// Mirrors src/api/matvec.c, src/api/common.c and src/api/error.c of SparseX:
+// same names, argument checks, return values and error-handler calls.  The
+// runtime behind it is different: no thread pool, no JIT; spx_mat_tune encodes
+// CSX on the host and uploads it to the GPU, spx_matvec_* launch CUDA kernels.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unistd.h>
+
+#include <csx_b200.h>
+#include <sparsex/sparsex.h>
+
+#include "csx_host.hpp"
+
+// defined in engine.cu (C++ linkage): tune from an in-memory COO input
+csxb_matrix_t *csxb_tune_coo_internal(const spxb::CooHost &coo, const char *options, char *err, size_t errlen);
+
+namespace {
+
+// ---- global runtime configuration (RtConfig singleton, Runtime.hpp:74-134) ----
+std::map<std::string, std::string> &props() {
+  static std::map<std::string, std::string> p;
+  return p;
+}
+int g_device = 0;
+bool g_async = false;
+int g_log_level = 2;  // 0 none, 1 error, 2 warning, 3 info, 4 verbose, 5 debug
+FILE *g_log_file = nullptr;
+
+enum { ALLOC_STD = 0, ALLOC_OTHER = 3, ALLOC_MANAGED = 5 };   // Vector.cpp:35-41 + engine addition
+enum { VEC_MODE_AS_IS = 43, VEC_MODE_TUNED = 44, VEC_MODE_INVALID = 45 };
+
+spx_errhandler_t g_handler = err_handle;
+
+std::string options_string() {
+  std::string s;
+  for (auto &kv : props()) {
+    if (kv.first == "spx.b200.device" || kv.first == "spx.b200.async") continue;
+    s += kv.first + "=" + kv.second + ";";
+  }
+  return s;
+}
+
+bool is_managed(const spx_vector_t *v) { return v->alloc_type == ALLOC_MANAGED; }
+
+}  // namespace
+
+struct matrix {   // src/api/matvec.c:30-38
+  spx_index_t nrows, ncols, nnz;
+  int symmetric;
+  spx_perm_t *permutation;
+  csxb_matrix_t *csx;
+  double *stage_x, *stage_y;   // device staging for vectors that live in plain host memory
+};
+struct input {    // src/api/matvec.c:43-48
+  spx_index_t nrows, ncols, nnz;
+  char type;      // 'C' CSR wrapper, 'M' MatrixMarket
+  const spx_index_t *rowptr, *colind;
+  const spx_value_t *values;
+  spxb::CooHost *coo;
+};
+struct partition {  // src/api/matvec.c:53-60
+  size_t nr_partitions;
+  size_t *parts;
+  int *nodes;
+  int *affinity;
+  spx_index_t *row_start;
+  spx_index_t *row_end;
+};
+
+extern "C" {
+
+// ---------------------------------------------------------------- errors --
+static const char *err_text(spx_error_t c) {  // src/api/error.c message tables
+  switch (c) {
+    case SPX_ERR_ARG_INVALID: return "invalid argument";
+    case SPX_ERR_FILE: return "file doesn't exist or can't be read";
+    case SPX_ERR_INPUT_MAT: return "input matrix wasn't properly created";
+    case SPX_ERR_TUNED_MAT: return "tuned matrix wasn't properly created";
+    case SPX_ERR_VEC: return "vector creation failed";
+    case SPX_ERR_PART: return "partitioning object wasn't properly created";
+    case SPX_ERR_PERM: return "error in permutation";
+    case SPX_ERR_DIM: return "incompatible matrix and vector dimensions";
+    case SPX_ERR_VEC_DIM: return "incompatible vector dimension";
+    case SPX_ERR_ENTRY_NOT_FOUND: return "matrix entry doesn't exist";
+    case SPX_OUT_OF_BOUNDS: return "index out of bounds";
+    case SPX_ERR_FILE_OPEN: return "unable to open file";
+    case SPX_ERR_FILE_READ: return "unable to read from file";
+    case SPX_ERR_FILE_WRITE: return "unable to write to file";
+    case SPX_ERR_MEM_ALLOC: return "memory allocation failed";
+    case SPX_ERR_MEM_FREE: return "memory deallocation failed";
+    case SPX_WARN_CSXFILE: return "no specific file given to save CSX, using default: \"csx_file\"";
+    case SPX_WARN_TUNING_OPT: return "invalid tuning option";
+    case SPX_WARN_RUNTIME_OPT: return "invalid runtime option";
+    case SPX_WARN_REORDER: return "reordering failed";
+    case SPX_WARN_ENTRY_NOT_SET: return "entry not set";
+  }
+  return "unknown error";
+}
+
+void err_handle(spx_error_t code, const char *sourcefile, unsigned long lineno, const char *function, const char *fmt, ...) {
+  (void)sourcefile; (void)lineno;
+  bool warning = code > SPX_ERR_MAX_VALUE && code < SPX_WARN_MAX_VALUE;
+  bool valid = (code > SPX_ERR_MIN_VALUE && code < SPX_ERR_MAX_VALUE) || warning;
+  if (g_log_level >= (warning ? 2 : 1)) {
+    FILE *out = g_log_file ? g_log_file : stderr;
+    char msg[512] = "";
+    if (fmt) { va_list ap; va_start(ap, fmt); vsnprintf(msg, sizeof(msg), fmt, ap); va_end(ap); }
+    fprintf(out, "[%s]: %s() -> %s%s%s\n", warning ? "WARNING" : "ERROR", function ? function : "?",
+            valid ? err_text(code) : "unknown error code", fmt ? ": " : "", msg);
+    fflush(out);
+  }
+  if (code > SPX_ERR_SYSTEM && code < SPX_ERR_MAX_VALUE) exit(1);  // src/api/error.c:86
+}
+spx_errhandler_t spx_err_get_handler(void) { return g_handler; }
+void spx_err_set_handler(spx_errhandler_t h) { g_handler = h ? h : err_handle; }
+
+// --------------------------------------------------------------- logging --
+void spx_log_disable_all(void) { g_log_level = 0; }
+void spx_log_error_console(void) { g_log_level = 1; g_log_file = nullptr; }
+void spx_log_warning_console(void) { g_log_level = 2; g_log_file = nullptr; }
+void spx_log_info_console(void) { g_log_level = 3; g_log_file = nullptr; }
+void spx_log_verbose_console(void) { g_log_level = 4; g_log_file = nullptr; }
+void spx_log_debug_console(void) { g_log_level = 5; g_log_file = nullptr; }
+void spx_log_set_file(const char *file) {
+  if (g_log_file) fclose(g_log_file);
+  g_log_file = file ? fopen(file, "a") : nullptr;
+}
+static void ensure_log_file() { if (!g_log_file) spx_log_set_file("sparsex.log"); }
+void spx_log_error_file(void) { g_log_level = 1; ensure_log_file(); }
+void spx_log_warning_file(void) { g_log_level = 2; ensure_log_file(); }
+void spx_log_info_file(void) { g_log_level = 3; ensure_log_file(); }
+void spx_log_verbose_file(void) { g_log_level = 4; ensure_log_file(); }
+void spx_log_debug_file(void) { g_log_level = 5; ensure_log_file(); }
+void spx_log_all_console(void) { g_log_level = 5; g_log_file = nullptr; }
+void spx_log_all_file(const char *file) { g_log_level = 5; spx_log_set_file(file); }
+
+void spx_init(void) { spx_log_warning_console(); }
+void spx_finalize(void) {}
+
+void *malloc_internal(size_t x, const char *sourcefile, unsigned long lineno, const char *function) {
+  void *ret = malloc(x);
+  if (!ret) { err_handle(SPX_ERR_MEM_ALLOC, sourcefile, lineno, function, NULL); exit(1); }
+  return ret;
+}
+void free_internal(void *ptr, const char *sourcefile, unsigned long lineno, const char *function) {
+  if (!ptr) { err_handle(SPX_ERR_MEM_FREE, sourcefile, lineno, function, NULL); exit(1); }
+  free(ptr);
+}
+
+// --------------------------------------------------------------- options --
+void spx_option_set(const char *option, const char *value) {  // matvec.c:753-756
+  if (!option || !value) { SETWARNING(SPX_WARN_TUNING_OPT); return; }
+  std::string k(option), v(value);
+  if (k == "spx.b200.device") { g_device = atoi(value); return; }
+  if (k == "spx.b200.async") { g_async = (v == "true" || v == "1"); return; }
+  spxb::TuneOptions probe;
+  std::string e = probe.set(k, v);
+  if (!e.empty()) {
+    spx_err_get_handler()(k.rfind("spx.rt.", 0) == 0 ? SPX_WARN_RUNTIME_OPT : SPX_WARN_TUNING_OPT, __FILE__, __LINE__,
+                          __func__, "%s", e.c_str());
+    return;
+  }
+  props()[k] = v;
+}
+void spx_options_set_from_env(void) {  // Runtime.cpp:97-149
+  const char *s;
+  if ((s = getenv("SYMMETRIC"))) spx_option_set("spx.matrix.symmetric", s);
+  if ((s = getenv("CPU_AFFINITY"))) spx_option_set("spx.rt.cpu_affinity", s);
+  if ((s = getenv("NUM_THREADS"))) spx_option_set("spx.rt.nr_threads", s);
+  if ((s = getenv("XFORM_CONF"))) spx_option_set("spx.preproc.xform", s);
+  if ((s = getenv("WINDOW_SIZE"))) { spx_option_set("spx.preproc.sampling", "window"); spx_option_set("spx.preproc.sampling.window_size", s); }
+  if ((s = getenv("SAMPLES"))) spx_option_set("spx.preproc.sampling.nr_samples", s);
+  if ((s = getenv("SAMPLING_PORTION"))) { spx_option_set("spx.preproc.sampling", "portion"); spx_option_set("spx.preproc.sampling.portion", s); }
+  if ((s = getenv("SAMPLING"))) spx_option_set("spx.preproc.sampling", s);
+}
+
+// ----------------------------------------------------------------- input --
+spx_input_t *spx_input_load_csr(const spx_index_t *rowptr, const spx_index_t *colind, const spx_value_t *values,
+                                spx_index_t nrows, spx_index_t ncols, ...) {
+  // the optional indexing argument is read and discarded: the reference's check
+  // (matvec.c:171-177) always falls back to zero-based
+  if (!check_mat_dim(nrows) || !check_mat_dim(ncols)) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix dimensions"); return SPX_INVALID_INPUT; }
+  if (!rowptr) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid rowptr argument"); return SPX_INVALID_INPUT; }
+  if (!colind) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid colind argument"); return SPX_INVALID_INPUT; }
+  if (!values) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid values argument"); return SPX_INVALID_INPUT; }
+  spx_input_t *A = spx_malloc(spx_input_t, sizeof(spx_input_t));
+  A->type = 'C';
+  A->nrows = nrows; A->ncols = ncols; A->nnz = rowptr[nrows];
+  A->rowptr = rowptr; A->colind = colind; A->values = values;
+  A->coo = nullptr;
+  return A;
+}
+
+spx_input_t *spx_input_load_mmf(const char *filename) {
+  if (!filename) { SETERROR_0(SPX_ERR_FILE); return SPX_INVALID_INPUT; }
+  if (access(filename, F_OK | R_OK) == -1) { SETERROR_0(SPX_ERR_FILE); return SPX_INVALID_INPUT; }
+  spxb::CooHost *coo = new spxb::CooHost;
+  std::string e = spxb::read_mmf(filename, *coo);
+  if (!e.empty()) {
+    delete coo;
+    spx_err_get_handler()(SPX_ERR_INPUT_MAT, __FILE__, __LINE__, __func__, "%s", e.c_str());
+    return SPX_INVALID_INPUT;
+  }
+  spx_input_t *A = spx_malloc(spx_input_t, sizeof(spx_input_t));
+  A->type = 'M';
+  A->nrows = (spx_index_t)coo->nrows; A->ncols = (spx_index_t)coo->ncols; A->nnz = (spx_index_t)coo->row.size();
+  A->rowptr = A->colind = nullptr; A->values = nullptr;
+  A->coo = coo;
+  return A;
+}
+
+spx_error_t spx_input_destroy(spx_input_t *A) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid input handle"); return SPX_FAILURE; }
+  delete A->coo;
+  spx_free(A);
+  return SPX_SUCCESS;
+}
+
+// ---------------------------------------------------------------- tuning --
+spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
+  if (!in) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid input matrix"); return SPX_INVALID_MAT; }
+  // Optional SPX_MAT_REORDER (RCM, Rcm.hpp) is outside this engine's scope; the
+  // variadic slot cannot be read portably when the caller passed nothing, so it
+  // is left untouched and the matrix is tuned in its given ordering.
+  char err[512] = "";
+  std::string opts = options_string();
+  csxb_matrix_t *m = nullptr;
+  if (in->type == 'C')
+    m = csxb_tune_csr(in->rowptr, in->colind, in->values, in->nrows, in->ncols, opts.c_str(), 0, -1, err, sizeof(err));
+  else if (in->type == 'M')
+    m = csxb_tune_coo_internal(*in->coo, opts.c_str(), err, sizeof(err));
+  if (!m) { spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
+  if (csxb_upload(m, g_device, 0) != 0) {
+    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+    csxb_destroy(m);
+    return SPX_INVALID_MAT;
+  }
+  spx_matrix_t *A = spx_malloc(spx_matrix_t, sizeof(spx_matrix_t));
+  A->nrows = in->nrows; A->ncols = in->ncols; A->nnz = in->nnz;
+  A->symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
+  A->permutation = SPX_INVALID_PERM;
+  A->csx = m;
+  A->stage_x = A->stage_y = nullptr;
+  return A;
+}
+
+spx_error_t spx_mat_destroy(spx_matrix_t *A) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  cudaDeviceSynchronize();
+  if (A->stage_x) cudaFree(A->stage_x);
+  if (A->stage_y) cudaFree(A->stage_y);
+  csxb_destroy(A->csx);
+  spx_free(A);
+  return SPX_SUCCESS;
+}
+
+struct csxb_matrix *spx_mat_get_engine(const spx_matrix_t *A) { return A ? A->csx : nullptr; }
+void spx_device_synchronize(void) { cudaDeviceSynchronize(); }
+
+spx_index_t spx_mat_get_nrows(const spx_matrix_t *A) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  return A->nrows;
+}
+spx_index_t spx_mat_get_ncols(const spx_matrix_t *A) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  return A->ncols;
+}
+spx_index_t spx_mat_get_nnz(const spx_matrix_t *A) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  return A->nnz;
+}
+
+// Out of scope for this engine (SURVEY.md section 8b "may stub"): fail through the handler.
+spx_error_t spx_mat_get_entry(const spx_matrix_t *A, spx_index_t, spx_index_t, spx_value_t *, ...) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  SETERROR_1(SPX_ERR_ENTRY_NOT_FOUND, "spx_mat_get_entry is not provided by the B200 engine");
+  return SPX_FAILURE;
+}
+spx_error_t spx_mat_set_entry(spx_matrix_t *A, spx_index_t, spx_index_t, spx_value_t, ...) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  SETERROR_1(SPX_ERR_ENTRY_NOT_FOUND, "spx_mat_set_entry is not provided by the B200 engine");
+  SETWARNING(SPX_WARN_ENTRY_NOT_SET);
+  return SPX_FAILURE;
+}
+spx_error_t spx_mat_save(const spx_matrix_t *A, const char *) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  SETERROR_1(SPX_ERR_FILE, "spx_mat_save is not provided by the B200 engine");
+  return SPX_FAILURE;
+}
+spx_matrix_t *spx_mat_restore(const char *) {
+  SETERROR_1(SPX_ERR_TUNED_MAT, "spx_mat_restore is not provided by the B200 engine");
+  return SPX_INVALID_MAT;
+}
+spx_perm_t *spx_mat_get_perm(const spx_matrix_t *A) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_INVALID_PERM; }
+  SETERROR_1(SPX_ERR_ARG_INVALID, "a permutation is not available");
+  return SPX_INVALID_PERM;
+}
+
+// ------------------------------------------------------------- partitions --
+static spx_partition_t *part_alloc(size_t n) {
+  spx_partition_t *p = spx_malloc(spx_partition_t, sizeof(spx_partition_t));
+  p->nr_partitions = n;
+  p->parts = nullptr; p->nodes = nullptr; p->affinity = nullptr;
+  p->row_start = (spx_index_t *)malloc(sizeof(spx_index_t) * (n ? n : 1));
+  p->row_end = (spx_index_t *)malloc(sizeof(spx_index_t) * (n ? n : 1));
+  return p;
+}
+spx_partition_t *spx_mat_get_partition(const spx_matrix_t *A) {  // matvec.c:485-514: a new object, caller destroys
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_INVALID_PART; }
+  int np = (int)csxb_info(A->csx, CSXB_NPARTS);
+  spx_partition_t *p = part_alloc(np);
+  for (int i = 0; i < np; i++) {
+    p->row_start[i] = (spx_index_t)csxb_part_info(A->csx, i, CSXB_P_ROW_START);
+    p->row_end[i] = p->row_start[i] + (spx_index_t)csxb_part_info(A->csx, i, CSXB_P_NROWS);
+  }
+  return p;
+}
+spx_partition_t *spx_partition_csr(const spx_index_t *rowptr, spx_index_t nr_rows, size_t nr_threads) {  // matvec.c:687-735
+  if (!rowptr || nr_threads == 0) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition arguments"); return SPX_INVALID_PART; }
+  spx_partition_t *ret = part_alloc(nr_threads);
+  size_t per = (size_t)(rowptr[nr_rows] - 1) / nr_threads, cur = 0, start = 0, cnt = 0;
+  for (size_t k = 0; k < nr_threads; k++) { ret->row_start[k] = 0; ret->row_end[k] = 0; }
+  ret->row_start[0] = 0;
+  spx_index_t i;
+  for (i = 0; i < nr_rows; i++) {
+    cur += (size_t)(rowptr[i + 1] - rowptr[i]);
+    if (cur >= per && cnt < nr_threads) {
+      ret->row_end[cnt] = i + 1;
+      start = (size_t)i + 1; cur = 0; ++cnt;
+      if (cnt < nr_threads) ret->row_start[cnt] = (spx_index_t)start;
+    }
+  }
+  if (cur < per && cnt < nr_threads) ret->row_end[cnt] = i + 1;
+  return ret;
+}
+spx_index_t *spx_partition_get_rs(const spx_partition_t *p) {
+  if (!p) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition handle"); return NULL; }
+  return p->row_start;
+}
+spx_index_t *spx_partition_get_re(const spx_partition_t *p) {
+  if (!p) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition handle"); return NULL; }
+  return p->row_end;
+}
+spx_error_t spx_partition_destroy(spx_partition_t *p) {
+  if (!p) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition handle"); return SPX_FAILURE; }
+  free(p->parts); free(p->nodes); free(p->affinity); free(p->row_start); free(p->row_end);
+  spx_free(p);
+  return SPX_SUCCESS;
+}
+
+// ------------------------------------------------------------------ SpMV --
+// x and y may live in managed memory (library vectors: used in place, resident
+// in HBM) or in plain host memory (spx_vec_create_from_buff: staged through
+// device buffers, copies inside the call).
+static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx_vector_t *x, spx_value_t beta,
+                            spx_vector_t *y, int overwrite) {
+  spx_matrix_t *A = const_cast<spx_matrix_t *>(Ac);
+  cudaSetDevice(g_device);
+  const double *dx = x->elements;
+  double *dy = y->elements;
+  bool x_host = !is_managed(x), y_host = !is_managed(y);
+  if (x_host) {
+    if (!A->stage_x && cudaMalloc((void **)&A->stage_x, (size_t)(A->ncols ? A->ncols : 1) * 8) != cudaSuccess) {
+      SETERROR_1(SPX_ERR_VEC, "device allocation failed");
+      return SPX_FAILURE;
+    }
+    if (cudaMemcpyAsync(A->stage_x, x->elements, (size_t)A->ncols * 8, cudaMemcpyHostToDevice, 0) != cudaSuccess) {
+      SETERROR_1(SPX_ERR_VEC, "host to device copy of x failed (no usable GPU?)");
+      return SPX_FAILURE;
+    }
+    dx = A->stage_x;
+  } else {
+    cudaMemPrefetchAsync(x->elements, x->size * 8, g_device, 0);
+  }
+  if (y_host) {
+    if (!A->stage_y && cudaMalloc((void **)&A->stage_y, (size_t)(A->nrows ? A->nrows : 1) * 8) != cudaSuccess) {
+      SETERROR_1(SPX_ERR_VEC, "device allocation failed");
+      return SPX_FAILURE;
+    }
+    if (!overwrite) cudaMemcpyAsync(A->stage_y, y->elements, (size_t)A->nrows * 8, cudaMemcpyHostToDevice, 0);
+    dy = A->stage_y;
+  } else {
+    cudaMemPrefetchAsync(y->elements, y->size * 8, g_device, 0);
+  }
+  if (csxb_spmv(A->csx, alpha, dx, beta, dy, overwrite, nullptr) != 0) {
+    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+    return SPX_FAILURE;
+  }
+  if (y_host) cudaMemcpyAsync(y->elements, A->stage_y, (size_t)A->nrows * 8, cudaMemcpyDeviceToHost, 0);
+  if (y_host || !g_async) {
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) {
+      spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", cudaGetErrorString(e));
+      return SPX_FAILURE;
+    }
+  }
+  return SPX_SUCCESS;
+}
+
+static spx_error_t check_spmv_args(const spx_matrix_t *A, const spx_vector_t *x, const spx_vector_t *y) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  if (!x) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid vector x"); return SPX_FAILURE; }
+  if (!y) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid vector y"); return SPX_FAILURE; }
+  // The reference rejects only when BOTH sizes mismatch (matvec.c:571); a single
+  // mismatch would make the kernels read or write out of bounds, so either one
+  // is an error here.
+  if (!check_vec_dim(x, (unsigned long)A->ncols) || !check_vec_dim(y, (unsigned long)A->nrows)) { SETERROR_0(SPX_ERR_DIM); return SPX_FAILURE; }
+  return SPX_SUCCESS;
+}
+
+spx_error_t spx_matvec_mult(spx_value_t alpha, const spx_matrix_t *A, const spx_vector_t *x, spx_vector_t *y) {
+  if (check_spmv_args(A, x, y) != SPX_SUCCESS) return SPX_FAILURE;
+  return run_spmv(A, alpha, x, 0.0, y, 1);   // VecInit(y, 0) semantics, CsxKernels.cpp:93
+}
+spx_error_t spx_matvec_kernel(spx_value_t alpha, const spx_matrix_t *A, const spx_vector_t *x, spx_value_t beta,
+                              spx_vector_t *y) {
+  if (check_spmv_args(A, x, y) != SPX_SUCCESS) return SPX_FAILURE;
+  return run_spmv(A, alpha, x, beta, y, 0);
+}
+spx_error_t spx_matvec_kernel_csr(spx_matrix_t **A, spx_index_t nrows, spx_index_t ncols, const spx_index_t *rowptr,
+                                  const spx_index_t *colind, const spx_value_t *values, spx_value_t alpha,
+                                  const spx_vector_t *x, spx_value_t beta, spx_vector_t *y) {  // matvec.c:622-673
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  if (!x) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid vector x"); return SPX_FAILURE; }
+  if (!y) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid vector y"); return SPX_FAILURE; }
+  if (!*A) {
+    spx_input_t *in = spx_input_load_csr(rowptr, colind, values, nrows, ncols, SPX_INDEX_ZERO_BASED);
+    if (!in) return SPX_FAILURE;
+    *A = spx_mat_tune(in);
+    spx_input_destroy(in);
+    if (!*A) return SPX_FAILURE;
+  }
+  return spx_matvec_kernel(alpha, *A, x, beta, y);
+}
+
+// --------------------------------------------------------------- vectors --
+static spx_vector_t *vec_alloc(size_t size, bool zero) {
+  spx_vector_t *v = (spx_vector_t *)malloc(sizeof(spx_vector_t));
+  if (!v) { SETERROR_0(SPX_ERR_MEM_ALLOC); return SPX_INVALID_VEC; }
+  void *p = nullptr;
+  size_t bytes = (size ? size : 1) * sizeof(spx_value_t);
+  if (cudaMallocManaged(&p, bytes, cudaMemAttachGlobal) == cudaSuccess) {
+    v->alloc_type = ALLOC_MANAGED;
+    if (zero) memset(p, 0, bytes);
+  } else {
+    cudaGetLastError();  // no usable GPU: a plain host vector still works for the BLAS-1 helpers
+    p = zero ? calloc(size ? size : 1, sizeof(spx_value_t)) : malloc(bytes);
+    if (!p) { free(v); SETERROR_0(SPX_ERR_MEM_ALLOC); return SPX_INVALID_VEC; }
+    v->alloc_type = ALLOC_STD;
+  }
+  v->elements = (spx_value_t *)p;
+  v->size = size;
+  v->vec_mode = VEC_MODE_INVALID;
+  return v;
+}
+spx_vector_t *spx_vec_create(size_t size, const spx_partition_t *p) {  // matvec.c:763-779
+  if (p == SPX_INVALID_PART) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition handle"); return SPX_INVALID_VEC; }
+  return vec_alloc(size, true);
+}
+spx_vector_t *spx_vec_create_from_buff(spx_value_t *buff, spx_value_t **tuned, size_t size, const spx_partition_t *p,
+                                       spx_vecmode_t mode) {  // matvec.c:781-818, Vector.cpp:113-159 (non-NUMA)
+  if (!buff) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid buffer"); return SPX_INVALID_VEC; }
+  if (!check_vecmode(mode)) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid vector mode"); return SPX_INVALID_VEC; }
+  if (p == SPX_INVALID_PART && mode == SPX_VEC_TUNE) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition handle"); return SPX_INVALID_VEC; }
+  spx_vector_t *v = (spx_vector_t *)malloc(sizeof(spx_vector_t));
+  if (!v) { SETERROR_0(SPX_ERR_MEM_ALLOC); return SPX_INVALID_VEC; }
+  v->elements = buff;
+  v->size = size;
+  v->alloc_type = ALLOC_OTHER;
+  v->vec_mode = (int)mode;
+  if (tuned) *tuned = buff;
+  return v;
+}
+void spx_vec_init_rand_range(spx_vector_t *v, spx_value_t max, spx_value_t min) {  // Vector.cpp:228-236
+  for (size_t i = 0; i < v->size; i++) {
+    spx_value_t val = ((spx_value_t)(rand() + i) / ((spx_value_t)RAND_MAX + 1));
+    v->elements[i] = min + val * (max - min);
+  }
+}
+spx_vector_t *spx_vec_create_random(size_t size, const spx_partition_t *p) {  // Vector.cpp:161-167
+  if (p == SPX_INVALID_PART) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid partition handle"); return SPX_INVALID_VEC; }
+  spx_vector_t *v = vec_alloc(size, true);
+  if (v) spx_vec_init_rand_range(v, (spx_value_t)-0.1, (spx_value_t)0.1);
+  return v;
+}
+void spx_vec_destroy(spx_vector_t *v) {  // Vector.cpp:187-204
+  if (!v) return;
+  if (v->alloc_type == ALLOC_MANAGED) { cudaDeviceSynchronize(); cudaFree(v->elements); }
+  else if (v->alloc_type == ALLOC_STD) free(v->elements);
+  free(v);
+}
+void spx_vec_init(spx_vector_t *v, spx_value_t val) { for (size_t i = 0; i < v->size; i++) v->elements[i] = val; }
+void spx_vec_init_part(spx_vector_t *v, spx_value_t val, spx_index_t start, spx_index_t end) {
+  for (spx_index_t i = start; i < end; i++) v->elements[i] = val;
+}
+spx_error_t spx_vec_set_entry(spx_vector_t *v, spx_index_t idx, spx_value_t val, ...) {  // matvec.c:838-862
+  // one-based like the reference (its indexing argument always degrades to one-based + !0)
+  if (idx <= 0 || (size_t)idx > v->size) { SETERROR_0(SPX_OUT_OF_BOUNDS); SETWARNING(SPX_WARN_ENTRY_NOT_SET); return SPX_FAILURE; }
+  v->elements[idx - 1] = val;
+  return SPX_SUCCESS;
+}
+void spx_vec_scale(spx_vector_t *v1, spx_vector_t *v2, spx_value_t num) {
+  for (size_t i = 0; i < v1->size; i++) v2->elements[i] = num * v1->elements[i];
+}
+void spx_vec_scale_add(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_value_t num) {
+  for (size_t i = 0; i < v1->size; i++) v3->elements[i] = v1->elements[i] + num * v2->elements[i];
+}
+void spx_vec_scale_add_part(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_value_t num, spx_index_t start,
+                            spx_index_t end) {
+  for (spx_index_t i = start; i < end; i++) v3->elements[i] = v1->elements[i] + num * v2->elements[i];
+}
+void spx_vec_add(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3) {
+  for (size_t i = 0; i < v1->size; i++) v3->elements[i] = v1->elements[i] + v2->elements[i];
+}
+void spx_vec_add_part(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_index_t start, spx_index_t end) {
+  for (spx_index_t i = start; i < end; i++) v3->elements[i] = v1->elements[i] + v2->elements[i];
+}
+void spx_vec_sub(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3) {
+  for (size_t i = 0; i < v1->size; i++) v3->elements[i] = v1->elements[i] - v2->elements[i];
+}
+void spx_vec_sub_part(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_index_t start, spx_index_t end) {
+  for (spx_index_t i = start; i < end; i++) v3->elements[i] = v1->elements[i] - v2->elements[i];
+}
+spx_value_t spx_vec_mul(const spx_vector_t *v1, const spx_vector_t *v2) {
+  spx_value_t r = 0;
+  for (size_t i = 0; i < v1->size; i++) r += v1->elements[i] * v2->elements[i];
+  return r;
+}
+spx_value_t spx_vec_mul_part(const spx_vector_t *v1, const spx_vector_t *v2, spx_index_t start, spx_index_t end) {
+  spx_value_t r = 0;
+  for (spx_index_t i = start; i < end; i++) r += v1->elements[i] * v2->elements[i];
+  return r;
+}
+spx_error_t spx_vec_reorder(spx_vector_t *v, spx_perm_t *p) {  // matvec.c:934-958
+  if (p == SPX_INVALID_PERM) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid permutation"); return SPX_FAILURE; }
+  spx_value_t *tmp = (spx_value_t *)malloc(v->size * sizeof(spx_value_t));
+  for (size_t i = 0; i < v->size; i++) tmp[p[i]] = v->elements[i];
+  memcpy(v->elements, tmp, v->size * sizeof(spx_value_t));
+  free(tmp);
+  return SPX_SUCCESS;
+}
+spx_error_t spx_vec_inv_reorder(spx_vector_t *v, spx_perm_t *p) {
+  if (p == SPX_INVALID_PERM) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid permutation"); return SPX_FAILURE; }
+  spx_value_t *tmp = (spx_value_t *)malloc(v->size * sizeof(spx_value_t));
+  for (size_t i = 0; i < v->size; i++) tmp[i] = v->elements[p[i]];
+  memcpy(v->elements, tmp, v->size * sizeof(spx_value_t));
+  free(tmp);
+  return SPX_SUCCESS;
+}
+void spx_vec_copy(const spx_vector_t *v1, spx_vector_t *v2) { memcpy(v2->elements, v1->elements, v1->size * sizeof(spx_value_t)); }
+int spx_vec_compare(const spx_vector_t *v1, const spx_vector_t *v2) {  // Vector.cpp:51-57, 396-413
+  if (v1->size != v2->size) { fprintf(stderr, "v1->size=%lu v2->size=%lu differ\n", v1->size, v2->size); return -2; }
+  for (size_t i = 0; i < v1->size; i++) {
+    if (fabs((v1->elements[i] - v2->elements[i]) / v1->elements[i]) > 1.e-6) {
+      fprintf(stderr, "element %ld differs: %10.20f != %10.20f\n", (long)i, v1->elements[i], v2->elements[i]);
+      return -1;
+    }
+  }
+  return 0;
+}
+void spx_vec_print(const spx_vector_t *v) {
+  printf("[ ");
+  for (size_t i = 0; i < v->size; i++) printf("%g ", v->elements[i]);
+  printf("]\n");
+}
+
+}  // extern "C"

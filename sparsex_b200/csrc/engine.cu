@@ -1,0 +1,664 @@
+// CUDA kernels (sm_100a) and the csxb_* C-ABI of the B200 CSX SpMV engine.
+//
+// Execution model (see gpu_layout.hpp for the tables):
+//   grid  = one CTA per 256-row tile of a partition, 8 warps, no CTA-wide sync;
+//   warp  = one 32-row segment, lane L owns row 32*seg + L for the whole kernel:
+//     phase A  walk the ctl bytes of the units that start in the segment; unit
+//              heads and varints are decoded redundantly by all lanes from an
+//              8-byte register window, delta bodies are loaded one element per
+//              lane and turned into columns with a warp prefix sum; row-local
+//              units (delta8/16/32/64, horizontal) are multiplied here and
+//              folded into the owning lane with a shuffle reduction per row;
+//     phase B  every lane gathers the contributions of the cross-row units
+//              (vertical, diagonal, anti-diagonal, block) listed for its tile;
+//     epilogue y = alpha*acc + beta*y, one coalesced 256-byte store per warp.
+// SpMV is HBM-bound fp64 work: no tensor cores, no atomics on the main path,
+// every value and ctl byte is read once, y is written once.
+//
+// Reference semantics reproduced: src/templates/csx_spmv_tmpl.c:66-101 and the
+// nine unit templates (delta/horiz/vert/diag/rdiag/block_row/block_col), the
+// symmetric variants (csx_sym_spmv_tmpl.c:60-106, *_sym_tmpl.c) and the
+// y handling of CsxKernels.cpp:35-129 / CsxSpmv.cpp:28-86.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/csx_b200.h"
+#include "csx_host.hpp"
+#include "gpu_layout.hpp"
+
+using namespace spxb;
+
+// ------------------------------------------------------------ device side --
+struct PartDev {
+  const uint8_t *ctl;          // this partition's ctl bytes (16-byte aligned, CTL_PAD readable bytes behind)
+  const double *values;        // device-wide values array
+  const uint64_t *seg_ctl;
+  const uint32_t *seg_val;
+  const uint32_t *tile_xoff;
+  const uint4 *xdesc;
+  const KindEntry *ktab;
+  const double *dvalues;       // CSX-Sym: diagonal of the owned rows
+  double *tbuf;                // CSX-Sym: transposed contributions of row-local units, zero between calls
+  long long nrows, row_start;  // owned rows
+  uint32_t val_base;
+  int full_colind;
+  KindEntry idtab[64];
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// 8-byte register window over the ctl stream; every lane of the warp holds the
+// same state (uniform control flow), loads are warp-broadcast.
+struct CtlReader {
+  const uint8_t *base;
+  uint64_t pos;
+  uint64_t w;
+  int avail;
+  __device__ __forceinline__ CtlReader(const uint8_t *b, uint64_t p) : base(b), pos(p), w(0), avail(0) {}
+  __device__ __forceinline__ uint32_t byte() {
+    if (avail == 0) {
+      uint64_t a = __ldg(reinterpret_cast<const unsigned long long *>(base + (pos & ~7ull)));
+      unsigned sh = (unsigned)(pos & 7);
+      w = a >> (8 * sh);
+      avail = 8 - (int)sh;
+    }
+    uint32_t b = (uint32_t)(w & 0xff);
+    w >>= 8; avail--; pos++;
+    return b;
+  }
+  __device__ __forceinline__ uint64_t varint() {  // CtlUtil.hpp:110-133
+    uint64_t v = 0;
+    unsigned shift = 0;
+    for (;;) {
+      uint32_t b = byte();
+      v |= (uint64_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) break;
+      shift += 7;
+    }
+    return v;
+  }
+  __device__ __forceinline__ uint32_t u32() { uint32_t v = byte(); v |= byte() << 8; v |= byte() << 16; v |= byte() << 24; return v; }
+  __device__ __forceinline__ void skip(uint64_t n) { pos += n; avail = 0; }
+};
+
+// low 32 bits of the little-endian fixed-width delta at byte address a
+__device__ __forceinline__ uint32_t load_delta(const uint8_t *ctl, uint64_t a, uint32_t w, bool aligned) {
+  if (w == 1) return __ldg(ctl + a);
+  if (aligned) {
+    if (w == 2) return __ldg(reinterpret_cast<const unsigned short *>(ctl + a));
+    return __ldg(reinterpret_cast<const unsigned int *>(ctl + a));  // w == 4 or low half of w == 8
+  }
+  uint32_t v = __ldg(ctl + a) | ((uint32_t)__ldg(ctl + a + 1) << 8);
+  if (w > 2) v |= ((uint32_t)__ldg(ctl + a + 2) << 16) | ((uint32_t)__ldg(ctl + a + 3) << 24);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// Phase A.  Op::elem(value index within the partition, row within the segment, column)
+// is called by the lane that owns the element, Op::row_done(row) by all lanes.
+template <class Op>
+__device__ __forceinline__ void walk_segment(const PartDev &P, long long seg, int lane, Op &op) {
+  uint64_t e0 = __ldg(reinterpret_cast<const unsigned long long *>(P.seg_ctl + seg));
+  uint64_t e1 = __ldg(reinterpret_cast<const unsigned long long *>(P.seg_ctl + seg + 1));
+  const uint64_t OFF = (1ull << 56) - 1;
+  uint64_t pend = e1 & OFF;
+  if ((e0 & OFF) >= pend) return;
+  int row = (int)(e0 >> 56);
+  uint32_t v = __ldg(P.seg_val + seg);
+  uint32_t col = 0;
+  bool first = true;
+  CtlReader rd(P.ctl, e0 & OFF);
+  while (rd.pos < pend) {
+    uint32_t flags = rd.byte(), size = rd.byte();
+    if (flags & 0x80) {  // new row (csx_spmv_tmpl.c:86-91); the entry unit's row comes from the table
+      uint32_t jmp = 1;
+      if (flags & 0x40) jmp = (uint32_t)rd.varint();
+      if (!first) { op.row_done(row); row += (int)jmp; }
+      col = 0;
+    }
+    first = false;
+    if (P.full_colind) col = rd.u32(); else col += (uint32_t)rd.varint();  // modulo 2^32 == modulo 2^64 truncated
+    KindEntry ke = P.idtab[flags & 0x3f];
+    uint32_t kind = ke.kind_align & 0xff, delta = ke.delta;
+    if (kind <= K_DELTA64) {  // delta_tmpl.c:20-37
+      uint64_t pb = rd.pos;
+      uint32_t wl = delta > 4 ? 4 : delta;
+      bool aligned = ((reinterpret_cast<uintptr_t>(P.ctl) + pb) & (wl - 1)) == 0;
+      for (uint32_t base = 0; base < size; base += 32) {
+        uint32_t j = base + lane;
+        uint32_t d = 0;
+        if (j < size && j > 0) d = load_delta(P.ctl, pb + (uint64_t)(j - 1) * delta, delta, aligned);
+        uint32_t mycol = col + warp_scan_incl(d, lane);
+        if (j < size) op.elem(v + j, row, mycol);
+        col = __shfl_sync(FULL, mycol, 31);
+      }
+      rd.skip((uint64_t)(size - 1) * delta);
+    } else if (kind == K_HORIZ) {  // horiz_tmpl.c:20-37
+      for (uint32_t j = lane; j < size; j += 32) op.elem(v + j, row, col + j * delta);
+      col += (size - 1) * delta;
+    }
+    // cross-row units leave the cursor on their first element (Element.hpp:657-666)
+    v += size;
+  }
+  op.row_done(row);
+}
+
+// Phase B.  Op::add(device-wide value index, x index) for every element of
+// descriptor d that contributes to `myrow` (global row).
+template <bool SYM, class Op>
+__device__ __forceinline__ void gather_desc(const uint4 d, const KindEntry *__restrict__ ktab, int myrow, Op &op) {
+  const uint32_t meta = d.w, kind = (meta >> 24) & 0xf, size = (meta >> 16) & 0xff;
+  const int r = (int)d.y, c = (int)d.z;
+  const uint32_t voff = d.x;
+  if (!SYM || !(meta & XD_TRANSPOSED)) {
+    int t = myrow - r;
+    if (t < 0) return;
+    if (kind <= K_ADIAG) {  // vert_tmpl.c, diag_tmpl.c, rdiag_tmpl.c
+      uint32_t k = (uint32_t)t;
+      if (!(meta & XD_DELTA1)) {
+        uint32_t delta = __ldg(&ktab[meta & 0xffff].delta);
+        k = (uint32_t)t / delta;
+        if (k * delta != (uint32_t)t) return;
+      }
+      if (k >= size) return;
+      int col = kind == K_VERT ? c : (kind == K_DIAG ? c + t : c - t);
+      op.add(voff + k, col);
+    } else if (kind == K_BROW) {  // block_row_tmpl.c: R rows x C cols, column-major values
+      uint32_t R = (meta >> 29) + 1;
+      if ((uint32_t)t >= R) return;
+      uint32_t C = size / R;
+      for (uint32_t m = 0; m < C; m++) op.add(voff + t + R * m, c + (int)m);
+    } else {  // block_col_tmpl.c: rr rows x C cols, row-major values
+      uint32_t C = (meta >> 29) + 1, rr = size / C;
+      if ((uint32_t)t >= rr) return;
+      for (uint32_t m = 0; m < C; m++) op.add(voff + t * C + m, c + (int)m);
+    }
+  } else {
+    // transposed image (CSX-Sym): element (r+a, c+b, v) adds v * x[r+a] to y[c+b]
+    if (kind == K_VERT) {  // vert_sym_tmpl.c: cur[x_indx] += sum v_k x[y_indx + k*delta]
+      if (myrow != c) return;
+      uint32_t delta = (meta & XD_DELTA1) ? 1u : __ldg(&ktab[meta & 0xffff].delta);
+      for (uint32_t k = 0; k < size; k++) op.add(voff + k, r + (int)(k * delta));
+    } else if (kind == K_DIAG || kind == K_ADIAG) {  // diag_sym_tmpl.c, rdiag_sym_tmpl.c
+      int u = kind == K_DIAG ? myrow - c : c - myrow;
+      if (u < 0) return;
+      uint32_t k = (uint32_t)u;
+      if (!(meta & XD_DELTA1)) {
+        uint32_t delta = __ldg(&ktab[meta & 0xffff].delta);
+        k = (uint32_t)u / delta;
+        if (k * delta != (uint32_t)u) return;
+      }
+      if (k >= size) return;
+      op.add(voff + k, r + u);
+    } else if (kind == K_BROW) {  // block_row_sym_tmpl.c
+      uint32_t R = (meta >> 29) + 1, C = size / R;
+      int u = myrow - c;
+      if (u < 0 || (uint32_t)u >= C) return;
+      for (uint32_t j = 0; j < R; j++) op.add(voff + j + R * u, r + (int)j);
+    } else {  // block_col_sym_tmpl.c
+      uint32_t C = (meta >> 29) + 1, rr = size / C;
+      int u = myrow - c;
+      if (u < 0 || (uint32_t)u >= C) return;
+      for (uint32_t j = 0; j < rr; j++) op.add(voff + j * C + u, r + (int)j);
+    }
+  }
+}
+
+struct SpmvWalkOp {
+  const double *__restrict__ values;  // partition base applied
+  const double *__restrict__ x;
+  double part, acc;
+  int lane;
+  __device__ __forceinline__ void elem(uint32_t vi, int, uint32_t col) { part += __ldg(values + vi) * __ldg(x + col); }
+  __device__ __forceinline__ void row_done(int row) {
+    double s = warp_sum(part);
+    if (lane == row) acc += s;
+    part = 0;
+  }
+};
+struct SpmvGatherOp {
+  const double *__restrict__ values;  // device-wide
+  const double *__restrict__ x;
+  double acc;
+  __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * __ldg(x + xi); }
+};
+
+template <bool WALK, bool XD, bool SYM>
+__global__ void __launch_bounds__(TILE_ROWS) csx_spmv_kernel(const __grid_constant__ PartDev P, const double *__restrict__ x,
+                                                             double *__restrict__ y, double alpha, double beta,
+                                                             int overwrite) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x;
+  const long long seg = tile * (TILE_ROWS / SEG_ROWS) + warp;
+  const long long lrow = seg * SEG_ROWS + lane;
+  if (seg * SEG_ROWS >= P.nrows) return;
+  const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
+  double acc = 0;
+  if (WALK && (tx0 & 0x80000000u)) {
+    SpmvWalkOp op{P.values + P.val_base, x, 0.0, 0.0, lane};
+    walk_segment(P, seg, lane, op);
+    acc = op.acc;
+  }
+  if (XD) {
+    SpmvGatherOp op{P.values, x, 0.0};
+    const int myrow = (int)(P.row_start + lrow);
+    const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
+    for (uint32_t j = b; j < e; j++) gather_desc<SYM>(__ldg(P.xdesc + j), P.ktab, myrow, op);
+    acc += op.acc;
+  }
+  if (lrow < P.nrows) {
+    const long long g = P.row_start + lrow;
+    if (SYM) {  // diagonal (CsxJit.hpp:373-394 new-row hook) + reduce of the local vector
+      acc += __ldg(P.dvalues + lrow) * __ldg(x + g);
+      acc += P.tbuf[g];
+      P.tbuf[g] = 0.0;
+    }
+    y[g] = overwrite ? alpha * acc : alpha * acc + beta * y[g];
+  }
+}
+
+// CSX-Sym, first phase: transposed contributions of the row-local units
+// (delta_sym_tmpl.c / horiz_sym_tmpl.c: cur[col] += x[row] * v) go to the local
+// vector tbuf with fp64 reductions; the main kernel folds tbuf into y.
+struct SymScatterOp {
+  const double *__restrict__ values;
+  const double *__restrict__ x;
+  double *tbuf;
+  long long row0;  // global row of the segment's first row
+  __device__ __forceinline__ void elem(uint32_t vi, int row, uint32_t col) {
+    atomicAdd(tbuf + col, __ldg(values + vi) * __ldg(x + row0 + row));
+  }
+  __device__ __forceinline__ void row_done(int) {}
+};
+__global__ void __launch_bounds__(TILE_ROWS) csx_sym_scatter_kernel(const __grid_constant__ PartDev P, const double *__restrict__ x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x;
+  const long long seg = tile * (TILE_ROWS / SEG_ROWS) + warp;
+  if (seg * SEG_ROWS >= P.nrows) return;
+  if (!(__ldg(P.tile_xoff + tile) & 0x80000000u)) return;
+  SymScatterOp op{P.values + P.val_base, x, P.tbuf, P.row_start + seg * SEG_ROWS};
+  walk_segment(P, seg, lane, op);
+}
+
+// Parity aid: the same traversal, storing the decoded coordinates per value.
+struct DecodeWalkOp {
+  int *rows, *cols;   // partition base applied
+  long long row0;
+  __device__ __forceinline__ void elem(uint32_t vi, int row, uint32_t col) { rows[vi] = (int)(row0 + row); cols[vi] = (int)col; }
+  __device__ __forceinline__ void row_done(int) {}
+};
+struct DecodeGatherOp {
+  int *rows, *cols;   // device-wide
+  int myrow;
+  __device__ __forceinline__ void add(uint32_t vi, int col) { rows[vi] = myrow; cols[vi] = col; }
+};
+__global__ void __launch_bounds__(TILE_ROWS) csx_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x;
+  const long long seg = tile * (TILE_ROWS / SEG_ROWS) + warp;
+  if (seg * SEG_ROWS >= P.nrows) return;
+  const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
+  if (tx0 & 0x80000000u) {
+    DecodeWalkOp op{rows + P.val_base, cols + P.val_base, P.row_start + seg * SEG_ROWS};
+    walk_segment(P, seg, lane, op);
+  }
+  DecodeGatherOp op{rows, cols, (int)(P.row_start + seg * SEG_ROWS + lane)};
+  for (uint32_t j = tx0 & 0x7fffffffu; j < (tx1 & 0x7fffffffu); j++) {
+    uint4 d = __ldg(P.xdesc + j);
+    if (d.w & XD_TRANSPOSED) continue;
+    gather_desc<false>(d, P.ktab, op.myrow, op);
+  }
+}
+
+// --------------------------------------------------------------- host side --
+static thread_local std::string g_last_error;
+static int fail(const std::string &m) { g_last_error = m; return -1; }
+#define CUDA_TRY(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+  } while (0)
+
+struct csxb_matrix {
+  CsxMatrix host;
+  DeviceLayout layout;
+  bool uploaded = false;
+  int device = -1;
+  std::vector<void *> allocs;
+  std::vector<PartDev> pdev;
+  double *d_values = nullptr, *d_tbuf = nullptr;
+  double *d_x = nullptr, *d_y = nullptr;   // staging for csxb_spmv_host
+  int64_t covered_rows_end = 0;
+  int64_t bytes[7] = {0, 0, 0, 0, 0, 0, 0};
+  std::vector<std::string> logs;
+  ~csxb_matrix() {
+    if (!allocs.empty() || d_x || d_y) {
+      int cur = -1;
+      cudaGetDevice(&cur);
+      if (device >= 0) cudaSetDevice(device);
+      for (void *p : allocs) cudaFree(p);
+      if (d_x) cudaFree(d_x);
+      if (d_y) cudaFree(d_y);
+      if (cur >= 0) cudaSetDevice(cur);
+    }
+  }
+};
+
+static std::string parse_options(const char *options, TuneOptions &o) {
+  if (!options) return "";
+  std::stringstream ss(options);
+  std::string kv;
+  while (std::getline(ss, kv, ';')) {
+    if (kv.empty()) continue;
+    size_t eq = kv.find('=');
+    if (eq == std::string::npos) return "malformed option \"" + kv + "\"";
+    std::string e = o.set(kv.substr(0, eq), kv.substr(eq + 1));
+    if (!e.empty()) return e;
+  }
+  return "";
+}
+static void put_err(char *err, size_t n, const std::string &m) {
+  g_last_error = m;
+  if (err && n) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
+}
+
+// C++ entry used by api.cpp for inputs already parsed into memory (spx_input_load_mmf)
+csxb_matrix_t *csxb_tune_coo_internal(const CooHost &coo, const char *options, char *err, size_t errlen) {
+  TuneOptions o;
+  std::string e = parse_options(options, o);
+  if (!e.empty()) { put_err(err, errlen, e); return nullptr; }
+  csxb_matrix *m = new csxb_matrix;
+  e = tune_coo(coo, o, 0, o.nr_threads, m->host);
+  if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
+  return m;
+}
+
+extern "C" {
+
+csxb_matrix_t *csxb_tune_csr(const int32_t *rowptr, const int32_t *colind, const double *values, int64_t nrows,
+                             int64_t ncols, const char *options, int part_lo, int part_hi, char *err, size_t errlen) {
+  TuneOptions o;
+  std::string e = parse_options(options, o);
+  if (e.empty() && (!rowptr || !colind || !values || nrows < 0 || ncols < 0)) e = "invalid CSR arguments";
+  if (e.empty() && rowptr[0] != 0) e = "CSR arrays must be zero-based";
+  if (!e.empty()) { put_err(err, errlen, e); return nullptr; }
+  if (part_hi < 0) { part_lo = 0; part_hi = o.nr_threads; }
+  csxb_matrix *m = new csxb_matrix;
+  CsrView v{rowptr, colind, values, nrows, ncols};
+  e = tune_csr(v, o, part_lo, part_hi, m->host);
+  if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
+  return m;
+}
+
+csxb_matrix_t *csxb_tune_mmf(const char *path, const char *options, int part_lo, int part_hi, char *err, size_t errlen) {
+  TuneOptions o;
+  std::string e = parse_options(options, o);
+  CooHost coo;
+  if (e.empty()) e = path ? read_mmf(path, coo) : "invalid file name";
+  if (!e.empty()) { put_err(err, errlen, e); return nullptr; }
+  if (part_hi < 0) { part_lo = 0; part_hi = o.nr_threads; }
+  csxb_matrix *m = new csxb_matrix;
+  e = tune_coo(coo, o, part_lo, part_hi, m->host);
+  if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
+  return m;
+}
+
+void csxb_destroy(csxb_matrix_t *m) { delete m; }
+
+int64_t csxb_info(const csxb_matrix_t *m, int what) {
+  switch (what) {
+    case CSXB_NROWS: return m->host.nrows;
+    case CSXB_NCOLS: return m->host.ncols;
+    case CSXB_NNZ: return m->host.nnz;
+    case CSXB_SYMMETRIC: return m->host.symmetric;
+    case CSXB_NPARTS: return (int64_t)m->host.parts.size();
+    case CSXB_NPARTS_TOTAL: return m->host.nparts_total;
+    case CSXB_PART_LO: return m->host.part_lo;
+    case CSXB_FULL_COLIND: return m->host.full_colind;
+  }
+  return -1;
+}
+
+int64_t csxb_part_info(const csxb_matrix_t *m, int part, int what) {
+  if (part < 0 || (size_t)part >= m->host.parts.size()) return -1;
+  const CsxPartition &p = m->host.parts[part];
+  switch (what) {
+    case CSXB_P_NNZ: return p.nnz;
+    case CSXB_P_NROWS: return p.nrows;
+    case CSXB_P_NCOLS: return p.ncols;
+    case CSXB_P_ROW_START: return p.row_start;
+    case CSXB_P_CTL_SIZE: return (int64_t)p.ctl.size();
+    case CSXB_P_ROW_JUMPS: return p.row_jumps;
+    case CSXB_P_ID_MAP_LEN: return (int64_t)p.id_map.size();
+    case CSXB_P_MAP_LEN: return (int64_t)p.map_cpus.size();
+    case CSXB_P_DVALUES_LEN: return (int64_t)p.dvalues.size();
+    case CSXB_P_ROWS_INFO_LEN: return (int64_t)p.rows_info.size();
+    case CSXB_P_SAMPLING_UNDEFINED: return p.sampling_undefined;
+  }
+  return -1;
+}
+
+int csxb_part_copy(const csxb_matrix_t *m, int part, int what, void *dst) {
+  if (part < 0 || (size_t)part >= m->host.parts.size() || !dst) return fail("invalid argument");
+  const CsxPartition &p = m->host.parts[part];
+  switch (what) {
+    case CSXB_A_VALUES:
+      if (p.values.size() != (size_t)p.nnz) return fail("host values were released at upload");
+      memcpy(dst, p.values.data(), p.values.size() * 8); break;
+    case CSXB_A_CTL: memcpy(dst, p.ctl.data(), p.ctl.size()); break;
+    case CSXB_A_ID_MAP: { int64_t *d = (int64_t *)dst; for (size_t i = 0; i < p.id_map.size(); i++) d[i] = p.id_map[i]; break; }
+    case CSXB_A_ROWS_INFO: {
+      struct R { int64_t rowptr, valptr; int32_t span, pad; } *d = (R *)dst;
+      for (size_t i = 0; i < p.rows_info.size(); i++) d[i] = R{p.rows_info[i].rowptr, p.rows_info[i].valptr, p.rows_info[i].span, 0};
+      break;
+    }
+    case CSXB_A_DVALUES: memcpy(dst, p.dvalues.data(), p.dvalues.size() * 8); break;
+    case CSXB_A_MAP_CPUS: memcpy(dst, p.map_cpus.data(), p.map_cpus.size() * 4); break;
+    case CSXB_A_MAP_POS: memcpy(dst, p.map_pos.data(), p.map_pos.size() * 4); break;
+    default: return fail("unknown array");
+  }
+  return 0;
+}
+
+const char *csxb_part_log(const csxb_matrix_t *m, int part) {
+  if (part < 0 || (size_t)part >= m->host.parts.size()) return "";
+  return m->host.parts[part].encoding_log.c_str();
+}
+
+const char *csxb_last_error(void) { return g_last_error.c_str(); }
+
+}  // extern "C"
+
+template <class T>
+static int dev_copy(csxb_matrix *m, const T *src, size_t n, T **dst, size_t extra_zero = 0) {
+  void *p = nullptr;
+  size_t bytes = (n + extra_zero) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16));
+  m->allocs.push_back(p);
+  if (n) CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  if (extra_zero) CUDA_TRY(cudaMemset((char *)p + n * sizeof(T), 0, extra_zero * sizeof(T)));
+  *dst = (T *)p;
+  return 0;
+}
+
+extern "C" {
+
+int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
+  if (m->uploaded) return fail("matrix already uploaded");
+  if (m->host.symmetric && (int)m->host.parts.size() != m->host.nparts_total)
+    return fail("CSX-Sym needs all partitions on one device in this version");
+  // CSX-Sym: a partition owns dvalues.size() rows (SparsePartitionSym::GetNrRows, SparsePartition.hpp:420-423)
+  CsxMatrix &H = m->host;
+  std::vector<int64_t> saved_nrows;
+  for (auto &p : H.parts) { saved_nrows.push_back(p.nrows); if (H.symmetric) p.nrows = (int64_t)p.dvalues.size(); }
+  std::string e = build_layout(H, m->layout);
+  for (size_t i = 0; i < H.parts.size(); i++) H.parts[i].nrows = saved_nrows[i];
+  if (!e.empty()) return fail("layout: " + e);
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("invalid device");
+  CUDA_TRY(cudaSetDevice(device));
+  m->device = device;
+  DeviceLayout &L = m->layout;
+  // device-wide arrays
+  void *dv = nullptr, *dc = nullptr;
+  CUDA_TRY(cudaMalloc(&dv, std::max<uint64_t>(L.total_values, 1) * 8));
+  m->allocs.push_back(dv);
+  CUDA_TRY(cudaMalloc(&dc, std::max<uint64_t>(L.total_ctl, 16)));
+  m->allocs.push_back(dc);
+  CUDA_TRY(cudaMemset(dc, 0, std::max<uint64_t>(L.total_ctl, 16)));
+  m->d_values = (double *)dv;
+  KindEntry *d_ktab = nullptr;
+  if (dev_copy(m, L.ktab.data(), L.ktab.size(), &d_ktab)) return -1;
+  if (H.symmetric) {
+    void *t = nullptr;
+    CUDA_TRY(cudaMalloc(&t, std::max<int64_t>(H.nrows, 1) * 8));
+    m->allocs.push_back(t);
+    CUDA_TRY(cudaMemset(t, 0, std::max<int64_t>(H.nrows, 1) * 8));
+    m->d_tbuf = (double *)t;
+  }
+  int64_t tables = (int64_t)L.ktab.size() * 8, nnz_stored = 0, ctl_bytes = 0, rows_owned = 0, launches = 0;
+  m->pdev.resize(L.parts.size());
+  for (size_t i = 0; i < L.parts.size(); i++) {
+    PartLayout &pl = L.parts[i];
+    CsxPartition &hp = H.parts[i];
+    PartDev &P = m->pdev[i];
+    memset(&P, 0, sizeof(P));
+    if (hp.nnz) CUDA_TRY(cudaMemcpy(m->d_values + pl.val_base, hp.values.data(), (size_t)hp.nnz * 8, cudaMemcpyHostToDevice));
+    if (!hp.ctl.empty()) CUDA_TRY(cudaMemcpy((uint8_t *)dc + pl.ctl_base, hp.ctl.data(), hp.ctl.size(), cudaMemcpyHostToDevice));
+    P.ctl = (const uint8_t *)dc + pl.ctl_base;
+    P.values = m->d_values;
+    uint64_t *sc = nullptr; uint32_t *sv = nullptr, *tx = nullptr; XDesc *xd = nullptr;
+    if (dev_copy(m, pl.seg_ctl.data(), pl.seg_ctl.size(), &sc)) return -1;
+    if (dev_copy(m, pl.seg_val.data(), pl.seg_val.size(), &sv)) return -1;
+    if (dev_copy(m, pl.tile_xoff.data(), pl.tile_xoff.size(), &tx)) return -1;
+    if (dev_copy(m, pl.xdesc.data(), pl.xdesc.size(), &xd)) return -1;
+    P.seg_ctl = sc; P.seg_val = sv; P.tile_xoff = tx; P.xdesc = (const uint4 *)xd; P.ktab = d_ktab;
+    if (H.symmetric) {
+      double *dd = nullptr;
+      if (dev_copy(m, hp.dvalues.data(), hp.dvalues.size(), &dd)) return -1;
+      P.dvalues = dd; P.tbuf = m->d_tbuf;
+      tables += (int64_t)hp.dvalues.size() * 8;
+    }
+    P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
+    P.full_colind = L.full_colind;
+    memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
+    nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;
+    tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
+    if (pl.has_row_local) tables += (int64_t)pl.seg_ctl.size() * 8 + (int64_t)pl.seg_val.size() * 4;
+    if (pl.nrows) launches += 1 + (H.symmetric && pl.has_row_local ? 1 : 0);
+    m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
+    if (free_host) std::vector<double>().swap(hp.values);
+  }
+  m->bytes[CSXB_B_VALUES] = nnz_stored * 8;
+  m->bytes[CSXB_B_CTL] = ctl_bytes;
+  m->bytes[CSXB_B_TABLES] = tables;
+  m->bytes[CSXB_B_X] = H.ncols * 8;
+  m->bytes[CSXB_B_Y] = rows_owned * 8;
+  m->bytes[CSXB_B_TOTAL] = nnz_stored * 8 + ctl_bytes + tables + H.ncols * 8 + rows_owned * 8;
+  m->bytes[CSXB_B_LAUNCHES] = launches;
+  m->uploaded = true;
+  return 0;
+}
+
+int64_t csxb_traffic(const csxb_matrix_t *m, int what) {
+  if (what < 0 || what > CSXB_B_LAUNCHES) return -1;
+  return m->bytes[what];
+}
+
+}  // extern "C"
+
+template <bool SYM>
+static void launch_main(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
+                        int overwrite, cudaStream_t s) {
+  dim3 grid((unsigned)pl.ntiles), block(TILE_ROWS);
+  if (pl.has_row_local && pl.has_cross) csx_spmv_kernel<true, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else csx_spmv_kernel<false, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+}
+
+extern "C" {
+
+int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, double *d_y, int overwrite, void *stream) {
+  if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool sym = m->host.symmetric;
+  if (sym)  // every scatter must land before any tile folds tbuf into y
+    for (size_t i = 0; i < m->pdev.size(); i++) {
+      const PartLayout &pl = m->layout.parts[i];
+      if (pl.ntiles && pl.has_row_local) csx_sym_scatter_kernel<<<(unsigned)pl.ntiles, TILE_ROWS, 0, s>>>(m->pdev[i], d_x);
+    }
+  for (size_t i = 0; i < m->pdev.size(); i++) {
+    const PartLayout &pl = m->layout.parts[i];
+    if (!pl.ntiles) continue;
+    if (sym) launch_main<true>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
+    else launch_main<false>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
+  }
+  // rows after the last partition's last non-empty row belong to nobody; VecInit(y,0) clears them (CsxKernels.cpp:93)
+  if (overwrite && m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total && m->covered_rows_end < m->host.nrows)
+    CUDA_TRY(cudaMemsetAsync(d_y + m->covered_rows_end, 0, (size_t)(m->host.nrows - m->covered_rows_end) * 8, s));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double beta, double *h_y, int overwrite) {
+  if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
+  int cur = -1;
+  CUDA_TRY(cudaGetDevice(&cur));
+  if (cur != m->device) CUDA_TRY(cudaSetDevice(m->device));
+  size_t nx = (size_t)std::max<int64_t>(m->host.ncols, 1), ny = (size_t)std::max<int64_t>(m->host.nrows, 1);
+  if (!m->d_x) CUDA_TRY(cudaMalloc((void **)&m->d_x, nx * 8));
+  if (!m->d_y) CUDA_TRY(cudaMalloc((void **)&m->d_y, ny * 8));
+  CUDA_TRY(cudaMemcpyAsync(m->d_x, h_x, (size_t)m->host.ncols * 8, cudaMemcpyHostToDevice, 0));
+  if (!overwrite) CUDA_TRY(cudaMemcpyAsync(m->d_y, h_y, (size_t)m->host.nrows * 8, cudaMemcpyHostToDevice, 0));
+  if (csxb_spmv(m, alpha, m->d_x, beta, m->d_y, overwrite, nullptr)) return -1;
+  // only the rows this handle computes travel back (one process per GPU owns one row range)
+  int64_t lo = m->layout.parts.empty() ? 0 : m->layout.parts.front().row_start;
+  int64_t hi = (m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total) ? m->host.nrows : m->covered_rows_end;
+  if (!overwrite) { lo = 0; hi = m->host.nrows; }
+  if (hi > lo) CUDA_TRY(cudaMemcpyAsync(h_y + lo, m->d_y + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  if (cur != m->device && cur >= 0) CUDA_TRY(cudaSetDevice(cur));
+  return 0;
+}
+
+int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t *cols) {
+  csxb_matrix *m = const_cast<csxb_matrix *>(mc);
+  if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
+  if (part < 0 || (size_t)part >= m->pdev.size()) return fail("invalid partition");
+  CUDA_TRY(cudaSetDevice(m->device));
+  const PartLayout &pl = m->layout.parts[part];
+  size_t n = (size_t)m->layout.total_values;
+  int *dr = nullptr, *dcl = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&dr, std::max<size_t>(n, 1) * 4));
+  CUDA_TRY(cudaMalloc((void **)&dcl, std::max<size_t>(n, 1) * 4));
+  CUDA_TRY(cudaMemset(dr, 0xff, std::max<size_t>(n, 1) * 4));
+  CUDA_TRY(cudaMemset(dcl, 0xff, std::max<size_t>(n, 1) * 4));
+  if (pl.ntiles) csx_decode_kernel<<<(unsigned)pl.ntiles, TILE_ROWS>>>(m->pdev[part], dr, dcl);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(rows, dr + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(cols, dcl + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dr); cudaFree(dcl);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// Builds the GPU side tables (segment table, cross-row unit table) by walking
+// the CSX ctl stream on the host.  The walk follows the unit grammar of
+// CtlBuilder.cpp:62-81 / CtlUtil.hpp:46-133 and the cursor rules of the kernel
+// templates (csx_spmv_tmpl.c:83-98; Element.hpp:657-666 for where a unit
+// leaves the column cursor).
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "gpu_layout.hpp"
+
+namespace spxb {
+namespace {
+
+inline uint64_t get_varint(const uint8_t *ctl, uint64_t &p) {
+  uint64_t v = 0;
+  unsigned shift = 0;
+  for (;;) {
+    uint8_t b = ctl[p++];
+    v |= (uint64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) break;
+    shift += 7;
+  }
+  return v;
+}
+
+// pattern id (CsxUtil.hpp:58-74, CsxUtil.cpp:27-33) -> kernel kind
+bool classify(long pid, KindEntry &ke) {
+  int type = (int)(pid / PATTERN_ID_OFFSET);
+  uint32_t d = (uint32_t)(pid % PATTERN_ID_OFFSET);
+  uint32_t kind, align = 0, delta = d;
+  if (type == T_NONE) {
+    if (d == 8) kind = K_DELTA8; else if (d == 16) kind = K_DELTA16; else if (d == 32) kind = K_DELTA32;
+    else if (d == 64) kind = K_DELTA64; else return false;
+    delta = d / 8;
+  } else if (type == T_HORIZ) kind = K_HORIZ;
+  else if (type == T_VERT) kind = K_VERT;
+  else if (type == T_DIAG) kind = K_DIAG;
+  else if (type == T_ADIAG) kind = K_ADIAG;
+  else if (is_brow(type)) {
+    align = blk_align(type);
+    if (align == 1) { kind = K_HORIZ; delta = 1; align = 0; }   // 1 x c block == horizontal run
+    else kind = K_BROW;                                          // delta = number of columns
+  } else if (is_bcol(type)) {
+    align = blk_align(type);
+    if (align == 1) { kind = K_VERT; delta = 1; align = 0; }     // r x 1 block == vertical run
+    else kind = K_BCOL;                                          // delta = number of rows
+  } else return false;
+  if (delta == 0) return false;
+  ke.kind_align = kind | (align << 8);
+  ke.delta = delta;
+  return true;
+}
+
+struct Pending { int64_t part; int64_t tile; XDesc d; };
+
+}  // namespace
+
+std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
+  out = DeviceLayout();
+  out.symmetric = m.symmetric;
+  out.full_colind = m.full_colind;
+  size_t np = m.parts.size();
+  out.parts.resize(np);
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> kindex;
+  std::vector<Pending> pend;
+
+  // global row -> (local partition, tile); partitions are contiguous and ordered
+  auto owner_of = [&](int64_t grow) -> int64_t {
+    for (size_t q = 0; q < np; q++)
+      if (grow >= m.parts[q].row_start && grow < m.parts[q].row_start + m.parts[q].nrows) return (int64_t)q;
+    return -1;
+  };
+
+  uint64_t vbase = 0, cbase = 0;
+  for (size_t pi = 0; pi < np; pi++) {
+    const CsxPartition &cp = m.parts[pi];
+    PartLayout &L = out.parts[pi];
+    L.nrows = cp.nrows; L.row_start = cp.row_start; L.nnz = cp.nnz; L.ctl_size = (int64_t)cp.ctl.size();
+    L.val_base = vbase; L.ctl_base = cbase;
+    vbase += (uint64_t)cp.nnz;
+    cbase += ((uint64_t)cp.ctl.size() + CTL_PAD + 15) & ~uint64_t(15);
+    L.nseg = (cp.nrows + SEG_ROWS - 1) / SEG_ROWS;
+    L.ntiles = (cp.nrows + TILE_ROWS - 1) / TILE_ROWS;
+    L.seg_ctl.assign((size_t)L.nseg + 1, 0);
+    L.seg_val.assign((size_t)L.nseg + 1, 0);
+    L.tile_xoff.assign((size_t)L.ntiles + 1, 0);
+    std::vector<uint8_t> tile_rl((size_t)L.ntiles, 0);
+    memset(L.idtab, 0, sizeof(L.idtab));
+    uint32_t id2k[64];
+    size_t nid = 0;
+    for (; nid < cp.id_map.size() && cp.id_map[nid] != -1; nid++) {
+      if (nid >= 64) return "too many unit kinds";
+      KindEntry ke;
+      if (!classify(cp.id_map[nid], ke)) return "unsupported pattern id " + std::to_string(cp.id_map[nid]);
+      L.idtab[nid] = ke;
+      auto key = std::make_pair(ke.kind_align, ke.delta);
+      auto it = kindex.find(key);
+      if (it == kindex.end()) {
+        if (out.ktab.size() >= 65535) return "too many distinct unit kinds on one device";
+        it = kindex.insert(std::make_pair(key, (uint32_t)out.ktab.size())).first;
+        out.ktab.push_back(ke);
+      }
+      id2k[nid] = it->second;
+    }
+
+    const uint8_t *ctl = cp.ctl.data();
+    uint64_t p = 0, end = cp.ctl.size();
+    int64_t row = 0, col = 0, v = 0;
+    int64_t next_seg = 0;   // first segment without an entry yet
+    bool first = true;
+    while (p < end) {
+      uint64_t unit_off = p;
+      uint8_t flags = ctl[p++], size = ctl[p++];
+      bool nr = (flags & 0x80) != 0;
+      if (nr) {
+        row += (flags & 0x40) ? (int64_t)get_varint(ctl, p) : 1;
+        col = 0;
+      }
+      if (m.full_colind) { uint32_t c; memcpy(&c, ctl + p, 4); p += 4; col = c; }
+      else col = (int64_t)((uint64_t)col + get_varint(ctl, p));   // modulo 2^64 (negative ucol)
+      if (row >= cp.nrows) return "ctl stream leaves the partition (row " + std::to_string(row) + ")";
+      if (nr || first) {  // first unit of a row: entry point for every segment up to this row's
+        int64_t s = row / SEG_ROWS;
+        for (; next_seg <= s; next_seg++) {
+          L.seg_ctl[next_seg] = unit_off | ((uint64_t)(next_seg == s ? row % SEG_ROWS : 0) << 56);
+          L.seg_val[next_seg] = (uint32_t)v;
+        }
+      }
+      first = false;
+      uint32_t id = flags & 0x3f;
+      if (id >= nid) return "ctl stream uses an unmapped unit id";
+      uint32_t kind = L.idtab[id].kind_align & 0xff, align = (L.idtab[id].kind_align >> 8) & 0xff;
+      uint32_t delta = L.idtab[id].delta;
+      if (size == 0) return "ctl unit of size 0";
+      if (kind_row_local(kind)) {
+        L.has_row_local = true;
+        tile_rl[row / TILE_ROWS] = 1;
+        if (kind == K_HORIZ) col += (int64_t)(size - 1) * delta;
+        else {
+          for (int k = 1; k < size; k++) {
+            uint64_t d = 0;
+            memcpy(&d, ctl + p, delta);   // little-endian fixed-width deltas
+            p += delta;
+            col += (int64_t)d;
+          }
+        }
+      } else {
+        L.has_cross = true;
+        int64_t span, cmin, cmax;   // rows spanned below the first one; column range
+        if (kind == K_VERT) { span = (int64_t)(size - 1) * delta; cmin = cmax = col; }
+        else if (kind == K_DIAG) { span = (int64_t)(size - 1) * delta; cmin = col; cmax = col + span; }
+        else if (kind == K_ADIAG) { span = (int64_t)(size - 1) * delta; cmax = col; cmin = col - span; }
+        else if (kind == K_BROW) {
+          if (size % align || size / align != delta) return "inconsistent block-row unit";
+          span = align - 1; cmin = col; cmax = col + delta - 1;
+        } else {
+          if (size % align || size / align != delta) return "inconsistent block-col unit";
+          span = delta - 1; cmin = col; cmax = col + align - 1;
+        }
+        if (row + span >= cp.nrows) return "cross-row unit leaves its partition";
+        if (cmin < 0 || cmax >= cp.ncols) return "unit leaves the column range";
+        XDesc d;
+        d.voff = (uint32_t)(L.val_base + (uint64_t)v);
+        d.row = (int32_t)(cp.row_start + row);
+        d.col = (int32_t)col;
+        d.meta = id2k[id] | ((uint32_t)size << 16) | (kind << 24);
+        if (kind == K_BROW || kind == K_BCOL) d.meta |= (align - 1) << 29;
+        else if (delta == 1) d.meta |= XD_DELTA1;
+        for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) pend.push_back(Pending{(int64_t)pi, t, d});
+        if (m.symmetric) {  // transposed image, listed under the tiles of its columns
+          XDesc td = d;
+          td.meta |= XD_TRANSPOSED;
+          int64_t g = cmin;
+          while (g <= cmax) {
+            int64_t q = owner_of(g);
+            if (q < 0) return "symmetric update targets a row that is not on this device";
+            int64_t rel = g - m.parts[q].row_start;
+            pend.push_back(Pending{q, rel / TILE_ROWS, td});
+            g = m.parts[q].row_start + (rel / TILE_ROWS + 1) * TILE_ROWS;   // first row of the next tile
+          }
+        }
+      }
+      v += size;
+    }
+    if (v != cp.nnz) return "ctl stream covers " + std::to_string(v) + " values, expected " + std::to_string(cp.nnz);
+    for (; next_seg <= L.nseg; next_seg++) { L.seg_ctl[next_seg] = end; L.seg_val[next_seg] = (uint32_t)v; }
+    for (int64_t t = 0; t < L.ntiles; t++) if (tile_rl[t]) L.tile_xoff[t] |= 0x80000000u;
+  }
+  out.total_values = vbase;
+  out.total_ctl = cbase;
+  if (vbase >= (uint64_t(1) << 32)) return "more than 2^32 values on one device";
+
+  // distribute the descriptors: stable counting sort by (partition, tile)
+  std::vector<std::vector<uint32_t>> cnt(np);
+  for (size_t q = 0; q < np; q++) cnt[q].assign((size_t)out.parts[q].ntiles + 1, 0);
+  for (const Pending &e : pend) cnt[e.part][e.tile + 1]++;
+  for (size_t q = 0; q < np; q++) {
+    PartLayout &L = out.parts[q];
+    for (int64_t t = 0; t < L.ntiles; t++) cnt[q][t + 1] += cnt[q][t];
+    if (cnt[q][L.ntiles] >= 0x80000000u) return "cross-row unit table too large";
+    L.xdesc.resize(cnt[q][L.ntiles]);
+    for (int64_t t = 0; t <= L.ntiles; t++) L.tile_xoff[t] |= cnt[q][t];
+  }
+  std::vector<std::vector<uint32_t>> fill(cnt);
+  for (const Pending &e : pend) out.parts[e.part].xdesc[fill[e.part][e.tile]++] = e.d;
+  return "";
+}
+
+}  // namespace spxb

@@ -1,0 +1,250 @@
+"""ctypes bindings for libsparsex_b200.so.
+
+Two layers are exposed, both straight through the C-ABI:
+
+* ``CsxMatrix``  — the engine ABI of include/csx_b200.h (csxb_*): tune on the
+  host, inspect the CSX arrays, upload, SpMV on raw device pointers (torch
+  tensors are only used as device-memory owners).
+* ``SpxApi``     — the SparseX drop-in API of include/sparsex/*.h (spx_*), the
+  call a user of the reference makes (src/api/matvec.c).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsparsex_b200.so")
+
+
+def lib():
+    """Load the product library; there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EngineError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the engine has no CPU fallback)" % path)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, dbl, cp = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_char_p
+    L.csxb_tune_csr.restype = vp
+    L.csxb_tune_csr.argtypes = [vp, vp, vp, i64, i64, cp, i32, i32, cp, C.c_size_t]
+    L.csxb_tune_mmf.restype = vp
+    L.csxb_tune_mmf.argtypes = [cp, cp, i32, i32, cp, C.c_size_t]
+    L.csxb_destroy.argtypes = [vp]
+    L.csxb_info.restype = i64
+    L.csxb_info.argtypes = [vp, i32]
+    L.csxb_part_info.restype = i64
+    L.csxb_part_info.argtypes = [vp, i32, i32]
+    L.csxb_part_copy.restype = i32
+    L.csxb_part_copy.argtypes = [vp, i32, i32, vp]
+    L.csxb_part_log.restype = cp
+    L.csxb_part_log.argtypes = [vp, i32]
+    L.csxb_upload.restype = i32
+    L.csxb_upload.argtypes = [vp, i32, i32]
+    L.csxb_last_error.restype = cp
+    L.csxb_traffic.restype = i64
+    L.csxb_traffic.argtypes = [vp, i32]
+    L.csxb_spmv.restype = i32
+    L.csxb_spmv.argtypes = [vp, dbl, vp, dbl, vp, i32, vp]
+    L.csxb_spmv_host.restype = i32
+    L.csxb_spmv_host.argtypes = [vp, dbl, vp, dbl, vp, i32]
+    L.csxb_decode_coords.restype = i32
+    L.csxb_decode_coords.argtypes = [vp, i32, vp, vp]
+    _LIB = L
+    return L
+
+
+def _opts(opts):
+    return ";".join("%s=%s" % (k, v) for k, v in (opts or {}).items()).encode()
+
+
+class Partition(object):
+    """Fields of csx_matrix_t (+ CSX-Sym extras) for one row partition."""
+    pass
+
+
+class CsxMatrix(object):
+    """A tuned matrix: csxb_matrix_t handle."""
+
+    # csxb_info / csxb_part_info / csxb_part_copy / csxb_traffic selectors (include/csx_b200.h)
+    NROWS, NCOLS, NNZ, SYMMETRIC, NPARTS, NPARTS_TOTAL, PART_LO, FULL_COLIND = range(8)
+    B_VALUES, B_CTL, B_TABLES, B_X, B_Y, B_TOTAL, B_LAUNCHES = range(7)
+
+    def __init__(self, handle, keepalive=None):
+        self._h = handle
+        self._keep = keepalive
+        L = lib()
+        self.nrows = L.csxb_info(handle, self.NROWS)
+        self.ncols = L.csxb_info(handle, self.NCOLS)
+        self.nnz = L.csxb_info(handle, self.NNZ)
+        self.symmetric = bool(L.csxb_info(handle, self.SYMMETRIC))
+        self.nparts = L.csxb_info(handle, self.NPARTS)
+        self.nparts_total = L.csxb_info(handle, self.NPARTS_TOTAL)
+        self.part_lo = L.csxb_info(handle, self.PART_LO)
+        self.uploaded = False
+
+    @classmethod
+    def tune_csr(cls, rowptr, colind, values, nrows, ncols, opts=None, part_lo=0, part_hi=-1):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        colind = np.ascontiguousarray(colind, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        err = C.create_string_buffer(1024)
+        h = lib().csxb_tune_csr(rowptr.ctypes.data, colind.ctypes.data, values.ctypes.data, nrows, ncols,
+                                _opts(opts), part_lo, part_hi, err, 1024)
+        if not h:
+            raise EngineError(err.value.decode())
+        return cls(h)
+
+    @classmethod
+    def tune_mmf(cls, path, opts=None, part_lo=0, part_hi=-1):
+        err = C.create_string_buffer(1024)
+        h = lib().csxb_tune_mmf(path.encode(), _opts(opts), part_lo, part_hi, err, 1024)
+        if not h:
+            raise EngineError(err.value.decode())
+        return cls(h)
+
+    def partition(self, p):
+        L = lib()
+        P = Partition()
+        info = [L.csxb_part_info(self._h, p, w) for w in range(11)]
+        (P.nnz, P.nrows, P.ncols, P.row_start, P.ctl_size, P.row_jumps, idl, mapl, dvl, ril, P.sampling_undefined) = info
+
+        def grab(what, n, dt):
+            a = np.empty(n, dt)
+            if n and L.csxb_part_copy(self._h, p, what, a.ctypes.data) != 0:
+                raise EngineError(L.csxb_last_error().decode())
+            return a
+        P.values = grab(0, P.nnz, np.float64)
+        P.ctl = grab(1, P.ctl_size, np.uint8)
+        P.id_map = grab(2, idl, np.int64)
+        ri = grab(3, ril * 3, np.int64).reshape(-1, 3)
+        P.rows_info = np.stack([ri[:, 0], ri[:, 1], ri[:, 2] & 0xffffffff], axis=1) if ril else ri
+        P.dvalues = grab(4, dvl, np.float64)
+        P.map_cpus = grab(5, mapl, np.uint32)
+        P.map_pos = grab(6, mapl, np.uint32)
+        P.log = L.csxb_part_log(self._h, p).decode()
+        return P
+
+    def upload(self, device=0, free_host=False):
+        if lib().csxb_upload(self._h, device, int(free_host)) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        self.uploaded = True
+        return self
+
+    def traffic(self):
+        L = lib()
+        keys = ["values", "ctl", "tables", "x", "y", "total", "launches"]
+        return {k: L.csxb_traffic(self._h, i) for i, k in enumerate(keys)}
+
+    def spmv_ptr(self, alpha, x_ptr, beta, y_ptr, overwrite, stream=0):
+        if lib().csxb_spmv(self._h, alpha, x_ptr, beta, y_ptr, int(overwrite), stream) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    def spmv(self, alpha, x, y, beta=0.0, overwrite=True, stream=None):
+        """x, y: torch CUDA float64 tensors (device-memory owners only)."""
+        import torch
+        assert x.is_cuda and y.is_cuda and x.dtype == torch.float64 and y.dtype == torch.float64
+        assert x.numel() == self.ncols and y.numel() == self.nrows and x.is_contiguous() and y.is_contiguous()
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self.spmv_ptr(alpha, x.data_ptr(), beta, y.data_ptr(), overwrite, s)
+        return y
+
+    def spmv_host(self, alpha, x, y, beta=0.0, overwrite=True):
+        """x, y: numpy float64 arrays in host memory; copies happen inside the call."""
+        assert x.dtype == np.float64 and y.dtype == np.float64 and x.flags.c_contiguous and y.flags.c_contiguous
+        if lib().csxb_spmv_host(self._h, alpha, x.ctypes.data, beta, y.ctypes.data, int(overwrite)) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return y
+
+    def decode_coords(self, p):
+        n = lib().csxb_part_info(self._h, p, 0)
+        r = np.empty(n, np.int32)
+        c = np.empty(n, np.int32)
+        if lib().csxb_decode_coords(self._h, p, r.ctypes.data, c.ctypes.data) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return r, c
+
+    def close(self):
+        if self._h:
+            lib().csxb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SpxVector(C.Structure):
+    """struct vector_struct (include/sparsex/common.h)."""
+    _fields_ = [("elements", C.POINTER(C.c_double)), ("size", C.c_size_t), ("alloc_type", C.c_int),
+                ("vec_mode", C.c_int)]
+
+
+class SpxApi(object):
+    """The spx_* functions with argument/return types declared."""
+
+    def __init__(self):
+        L = lib()
+        self.L = L
+        vp, i32, dbl, cp = C.c_void_p, C.c_int, C.c_double, C.c_char_p
+        VP = C.POINTER(SpxVector)
+        sig = {
+            "spx_init": (None, []), "spx_finalize": (None, []),
+            "spx_log_disable_all": (None, []), "spx_log_error_console": (None, []),
+            "spx_input_load_csr": (vp, [vp, vp, vp, i32, i32]),
+            "spx_input_load_mmf": (vp, [cp]),
+            "spx_input_destroy": (i32, [vp]),
+            "spx_mat_tune": (vp, [vp]),
+            "spx_mat_destroy": (i32, [vp]),
+            "spx_mat_get_nrows": (i32, [vp]), "spx_mat_get_ncols": (i32, [vp]), "spx_mat_get_nnz": (i32, [vp]),
+            "spx_mat_get_partition": (vp, [vp]),
+            "spx_mat_get_entry": (i32, [vp, i32, i32, C.POINTER(dbl)]),
+            "spx_mat_get_engine": (vp, [vp]),
+            "spx_partition_csr": (vp, [vp, i32, C.c_size_t]),
+            "spx_partition_get_rs": (C.POINTER(i32), [vp]), "spx_partition_get_re": (C.POINTER(i32), [vp]),
+            "spx_partition_destroy": (i32, [vp]),
+            "spx_option_set": (None, [cp, cp]), "spx_options_set_from_env": (None, []),
+            "spx_vec_create": (VP, [C.c_size_t, vp]),
+            "spx_vec_create_from_buff": (VP, [vp, C.POINTER(vp), C.c_size_t, vp, C.c_uint]),
+            "spx_vec_create_random": (VP, [C.c_size_t, vp]),
+            "spx_vec_init": (None, [VP, dbl]),
+            "spx_vec_init_rand_range": (None, [VP, dbl, dbl]),
+            "spx_vec_set_entry": (i32, [VP, i32, dbl]),
+            "spx_vec_scale": (None, [VP, VP, dbl]),
+            "spx_vec_scale_add": (None, [VP, VP, VP, dbl]),
+            "spx_vec_add": (None, [VP, VP, VP]), "spx_vec_sub": (None, [VP, VP, VP]),
+            "spx_vec_mul": (dbl, [VP, VP]),
+            "spx_vec_copy": (None, [VP, VP]), "spx_vec_compare": (i32, [VP, VP]),
+            "spx_vec_destroy": (None, [VP]),
+            "spx_matvec_mult": (i32, [dbl, vp, VP, VP]),
+            "spx_matvec_kernel": (i32, [dbl, vp, VP, dbl, VP]),
+            "spx_matvec_kernel_csr": (i32, [C.POINTER(vp), i32, i32, vp, vp, vp, dbl, VP, dbl, VP]),
+            "spx_device_synchronize": (None, []),
+            "spx_err_set_handler": (None, [vp]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+            setattr(self, name, f)
+
+    @staticmethod
+    def as_numpy(vec):
+        v = vec.contents
+        return np.ctypeslib.as_array(v.elements, shape=(v.size,))
+
+
+def load_spx_api():
+    return SpxApi()

@@ -1,0 +1,207 @@
+"""GPU parity tests (run with -m gpu on the B200 box).
+
+Every check goes through the C-ABI of libsparsex_b200.so (csxb_* / spx_*) and
+compares against the oracle (oracle/: CPU restatement of the reference) on the
+same seeded inputs:
+  * CSX encoding (ctl, values, id_map, rows_info) bit-exact,
+  * decoded (row, column) per value from the device-side traversal bit-exact,
+  * y = alpha*A*x (+ beta*y) within 1e-12 relative (componentwise against
+    |A||x|) — the tolerance BASELINE.json's north_star states.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN
+from tests.matrices import (poisson2d, random_structured, rmat, stencil27,
+                            sym_block_banded)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _abs_bound(rowptr, colind, values, x, n):
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    b = np.zeros(n)
+    np.add.at(b, rows, np.abs(values) * np.abs(x[colind]))
+    return b
+
+
+def _csr_spmv(rowptr, colind, values, x, n):
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    y = np.zeros(n)
+    np.add.at(y, rows, values * x[colind])
+    return y
+
+
+def check_matrix(rowptr, colind, values, n, m, opts, seed=0, check_decode=True, oracle_spmv=True):
+    """Tune with the engine and the oracle, compare encodings, decoded coordinates and products."""
+    torch = _torch()
+    from oracle.pyoracle import OracleMatrix
+    from sparsex_b200 import CsxMatrix
+
+    rng = np.random.default_rng(seed)
+    oopts = dict(opts)
+    oopts["oracle.undefined_sampling"] = "break"
+    O = OracleMatrix.from_csr(rowptr, colind, values, n, m).tune(oopts)
+    A = CsxMatrix.tune_csr(rowptr, colind, values, n, m, opts)
+    assert A.nparts == len(O.parts)
+    for p in range(A.nparts):
+        P, Q = A.partition(p), O.parts[p]
+        assert np.array_equal(P.ctl, Q.ctl), "ctl differs (%s | %s)" % (P.log, O.log)
+        assert np.array_equal(P.values, Q.values)
+        assert np.array_equal(P.id_map, Q.id_map)
+        assert np.array_equal(P.rows_info, Q.rows_info.astype(np.int64))
+    A.upload(0)
+    sym = str(opts.get("spx.matrix.symmetric", "false")) == "true"
+    if check_decode and not sym:
+        for p in range(A.nparts):
+            r, c = A.decode_coords(p)
+            ro, co = O.decode(p)
+            assert np.array_equal(r, ro) and np.array_equal(c, co), "device-decoded coordinates differ"
+    x = rng.uniform(-1, 1, m)
+    y0 = rng.uniform(-1, 1, n)
+    bound = _abs_bound(rowptr, colind, values, x, n) + 1e-300
+    dx = torch.from_numpy(x).cuda()
+    # spx_matvec_mult semantics
+    dy = torch.from_numpy(y0.copy()).cuda()
+    A.spmv(0.5, dx, dy, overwrite=True)
+    y = dy.cpu().numpy()
+    yref = O.spmv(0.5, x) if oracle_spmv else 0.5 * _csr_spmv(rowptr, colind, values, x, n)
+    err = np.max(np.abs(y - yref) / (0.5 * bound + np.abs(yref) * 0 + 1e-300))
+    assert err <= TOL, "mult: componentwise relative error %.3e (%s)" % (err, O.log)
+    # spx_matvec_kernel semantics
+    dy = torch.from_numpy(y0.copy()).cuda()
+    A.spmv(0.75, dx, dy, beta=-0.3, overwrite=False)
+    y = dy.cpu().numpy()
+    yref = O.spmv(0.75, x, beta=-0.3, y=y0) if oracle_spmv else 0.75 * _csr_spmv(rowptr, colind, values, x, n) - 0.3 * y0
+    err = np.max(np.abs(y - yref) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300))
+    assert err <= TOL, "kernel: componentwise relative error %.3e (%s)" % (err, O.log)
+    # host-buffer path (copies inside the call)
+    yh = np.zeros(n)
+    A.spmv_host(0.5, x, yh)
+    yref = O.spmv(0.5, x) if oracle_spmv else 0.5 * _csr_spmv(rowptr, colind, values, x, n)
+    assert np.max(np.abs(yh - yref) / (0.5 * bound)) <= TOL
+    A.close()
+    return O.log
+
+
+XFORMS = ["none", "h", "v", "d", "ad", "br", "bc", "all", "h,d", "bc,v,ad", "br3{2,3},h{1}", "d{1},ad{2},v{1}"]
+
+
+@pytest.mark.parametrize("name", ["demopatt", "test", "test2", "test3"])
+def test_reference_fixtures(name):
+    """The reference's bundled matrices under the option sets of test/scripts/test-sparsex.sh.in."""
+    from oracle.pyoracle import OracleMatrix
+    M = OracleMatrix.from_mmf(os.path.join(GOLDEN, "matrices", name + ".mtx.sorted"))
+    rp, ci, va = M.csr()
+    for xf in XFORMS:
+        for extra in ({}, {"spx.preproc.sampling": "none"}, {"spx.rt.nr_threads": 2},
+                      {"spx.rt.nr_threads": 2, "spx.preproc.sampling.nr_samples": 1, "spx.preproc.sampling.portion": 0.4},
+                      {"spx.matrix.full_colind": "true"}):
+            o = {"spx.preproc.xform": xf}
+            o.update(extra)
+            check_matrix(rp, ci, va, M.nrows, M.ncols, o)
+
+
+@pytest.mark.parametrize("name", ["symmetric", "symmetric-very-sparse"])
+def test_reference_symmetric_fixtures(name):
+    from oracle.pyoracle import OracleMatrix
+    M = OracleMatrix.from_mmf(os.path.join(GOLDEN, "matrices", name + ".mtx.sorted"))
+    rp, ci, va = M.csr()
+    for xf in XFORMS:
+        for extra in ({}, {"spx.preproc.sampling": "none"}, {"spx.rt.nr_threads": 2},
+                      {"spx.preproc.sampling.nr_samples": 2, "spx.preproc.sampling.portion": 0.4}):
+            for sym in ("true", "false"):
+                o = {"spx.preproc.xform": xf, "spx.matrix.symmetric": sym}
+                o.update(extra)
+                check_matrix(rp, ci, va, M.nrows, M.ncols, o)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_structured(seed):
+    """Ragged random matrices seeded with every substructure kind, all option families."""
+    rng = np.random.default_rng(100 + seed)
+    for trial in range(4):
+        n = int(rng.integers(5, 700))
+        sym = trial % 2 == 0
+        m = n if sym else int(rng.integers(5, 700))
+        rp, ci, va = random_structured(rng, n, m, symmetric=sym)
+        for xf in XFORMS:
+            extras = [{}, {"spx.preproc.sampling": "none"}, {"spx.rt.nr_threads": int(rng.integers(2, 6))},
+                      {"spx.matrix.split_blocks": "false"},
+                      {"spx.matrix.min_unit_size": 2, "spx.matrix.max_unit_size": int(rng.integers(8, 255)),
+                       "spx.matrix.min_coverage": 0.01}]
+            for extra in extras:
+                for s in (("true", "false") if sym else ("false",)):
+                    o = {"spx.preproc.xform": xf, "spx.matrix.symmetric": s}
+                    o.update(extra)
+                    check_matrix(rp, ci, va, n, m, o, seed=seed)
+
+
+def test_empty_and_degenerate():
+    """Empty rows at both ends, an empty matrix, single-element rows, a dense row of maximum unit length."""
+    # leading / trailing empty rows
+    rp = np.array([0, 0, 0, 2, 2, 5, 5, 5], np.int32)
+    ci = np.array([0, 3, 1, 2, 6], np.int32)
+    va = np.arange(1.0, 6.0)
+    for xf in ("none", "all"):
+        check_matrix(rp, ci, va, 7, 7, {"spx.preproc.xform": xf})
+        check_matrix(rp, ci, va, 7, 7, {"spx.preproc.xform": xf, "spx.rt.nr_threads": 3})
+    # dense rows longer than one unit (255) and longer than one warp pass
+    n = 40
+    m = 1000
+    rng = np.random.default_rng(7)
+    rows = []
+    for r in range(n):
+        k = int(rng.integers(1, m)) if r % 3 else m
+        rows.append(np.sort(rng.choice(m, k, replace=False)))
+    rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    ci = np.concatenate(rows).astype(np.int32)
+    va = rng.standard_normal(ci.size)
+    for xf in ("none", "h", "all"):
+        check_matrix(rp, ci, va, n, m, {"spx.preproc.xform": xf})
+    # wide column jumps: delta16 / delta32 units
+    m = 300000
+    rows = [np.sort(rng.choice(m, 50, replace=False)) for _ in range(64)]
+    rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    ci = np.concatenate(rows).astype(np.int32)
+    va = rng.standard_normal(ci.size)
+    check_matrix(rp, ci, va, 64, m, {"spx.preproc.xform": "none"})
+    check_matrix(rp, ci, va, 64, m, {"spx.preproc.xform": "none", "spx.matrix.full_colind": "true"})
+
+
+@pytest.mark.parametrize("opts", [{}, {"spx.preproc.xform": "none"}, {"spx.preproc.xform": "br,bc"},
+                                  {"spx.rt.nr_threads": 4}, {"spx.matrix.symmetric": "true"},
+                                  {"spx.matrix.symmetric": "true", "spx.rt.nr_threads": 3}])
+def test_poisson2d(opts):
+    rp, ci, va, n = poisson2d(160)
+    check_matrix(rp, ci, va, n, n, opts)
+
+
+@pytest.mark.parametrize("opts", [{}, {"spx.preproc.xform": "br,bc"}, {"spx.preproc.xform": "bc3{3},h{1}"},
+                                  {"spx.matrix.symmetric": "true"}])
+def test_stencil27(opts):
+    rp, ci, va, n = stencil27(24)
+    check_matrix(rp, ci, va, n, n, opts)
+
+
+@pytest.mark.parametrize("opts", [{"spx.matrix.symmetric": "true"}, {"spx.matrix.symmetric": "true", "spx.rt.nr_threads": 2},
+                                  {"spx.matrix.symmetric": "true", "spx.preproc.xform": "br3{3},bc3{3}"}, {}])
+def test_sym_block_banded(opts):
+    rp, ci, va, n = sym_block_banded(4000, b=64)
+    check_matrix(rp, ci, va, n, n, opts)
+
+
+@pytest.mark.parametrize("opts", [{"spx.preproc.xform": "none"}, {"spx.preproc.xform": "none", "spx.rt.nr_threads": 8}, {}])
+def test_rmat(opts):
+    rp, ci, va, n = rmat(14)
+    check_matrix(rp, ci, va, n, n, opts)
