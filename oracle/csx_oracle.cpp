@@ -157,7 +157,10 @@ struct Partition {
     size_t cnt = 0;
     for (const Elem &e : elems) {
       if (e.row != row_prev) {
-        assert(e.row > row_prev);
+        if (e.row < row_prev)
+          throw OracleError("set_rowptr: rows not ascending (row " + std::to_string(e.row) + " after " +
+                            std::to_string(row_prev) + ", type " + std::to_string(type) + ", nr_rows " +
+                            std::to_string(nr_rows) + ")");
         for (int k = 0; k < e.row - row_prev; k++) rowptr.push_back((int)cnt);
         row_prev = e.row;
       }
@@ -518,6 +521,13 @@ struct EncodingManager {
         size_t window_end = sort_splits[selected_splits[i] + 1];
         size_t window_size = window_end - window_start;
         if (window_start >= window_end - 1) break;  // "quick fix for windows of size 0"
+        if (window_start > spm->rowptr_size() - 1) {
+          // after an encoding round the trailing rows can be empty and the rebuilt rowptr shorter than
+          // the split table: GetWindow then reads rowptr_[rs] out of bounds (SparsePartition.hpp:780-786)
+          if (opt.undefined_sampling == "break") { undefined_hit = true; break; }
+          throw OracleError("undefined: sampling window starts past the rebuilt rowptr "
+                            "(SparsePartition.hpp:780-786)");
+        }
         Partition w; int es = 0;
         if (!get_window(window_start, window_size, w, es)) break;
         samples_nnz += sort_splits_nzeros[selected_splits[i]];

@@ -511,6 +511,10 @@ class Miner {
         if (undef) { if (undefined_) *undefined_ = true; break; }
         size_t ws = splits_[picked_[i]], we = splits_[picked_[i] + 1];
         if (ws >= we - 1) break;                       // windows of one row end the sampling (:720-722)
+        if (ws > spm_->nrowptr() - 1) {                // window starts past the rebuilt rowptr: the reference
+          if (undefined_) *undefined_ = true;          // reads rowptr_[rs] out of bounds here (undefined)
+          break;
+        }
         Part w;
         if (!window(ws, we - ws, w)) break;            // empty window (:726-729)
         sampled += split_nnz_[picked_[i]];

@@ -10,20 +10,34 @@ def _csr_from_coo(r, c, v, n, m):
     return np.cumsum(rowptr).astype(np.int32), c.astype(np.int32), v.astype(np.float64)
 
 
+def _stencil_csr(n, offsets_cols_vals, perturb, seed):
+    """Rows are emitted in natural order with ascending columns: no sort needed."""
+    k = len(offsets_cols_vals)
+    cols = np.empty((n, k), np.int64)
+    vals = np.empty((n, k), np.float64)
+    mask = np.empty((n, k), bool)
+    for j, (ok, col, val) in enumerate(offsets_cols_vals):
+        mask[:, j] = ok
+        cols[:, j] = col
+        vals[:, j] = val
+    rowptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int32)
+    ci = cols[mask].astype(np.int32)
+    va = vals[mask]
+    if perturb:
+        va = va * (1 + 1e-3 * np.random.default_rng(seed).random(va.size))
+    return rowptr, ci, va, n
+
+
 def poisson2d(g, perturb=True, seed=1):
     """5-point Laplacian on a g x g grid, natural ordering (config 2: g = 4096)."""
     n = g * g
     i = np.arange(n, dtype=np.int64)
     gx, gy = i % g, i // g
-    rows, cols, vals = [], [], []
+    spec = []
     for dy, dx, val in ((-1, 0, -1.0), (0, -1, -1.0), (0, 0, 4.0), (0, 1, -1.0), (1, 0, -1.0)):
         ok = (gx + dx >= 0) & (gx + dx < g) & (gy + dy >= 0) & (gy + dy < g)
-        rows.append(i[ok]); cols.append(i[ok] + dy * g + dx); vals.append(np.full(ok.sum(), val))
-    r, c, v = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
-    if perturb:
-        v = v * (1 + 1e-3 * np.random.default_rng(seed).random(v.size))
-    rp, ci, va = _csr_from_coo(r, c, v, n, n)
-    return rp, ci, va, n
+        spec.append((ok, i + dy * g + dx, val))
+    return _stencil_csr(n, spec, perturb, seed)
 
 
 def stencil27(g, perturb=True, seed=1):
@@ -31,18 +45,13 @@ def stencil27(g, perturb=True, seed=1):
     n = g ** 3
     i = np.arange(n, dtype=np.int64)
     gx, gy, gz = i % g, (i // g) % g, i // (g * g)
-    rows, cols, vals = [], [], []
+    spec = []
     for dz in (-1, 0, 1):
         for dy in (-1, 0, 1):
             for dx in (-1, 0, 1):
                 ok = ((gx + dx >= 0) & (gx + dx < g) & (gy + dy >= 0) & (gy + dy < g) & (gz + dz >= 0) & (gz + dz < g))
-                rows.append(i[ok]); cols.append(i[ok] + (dz * g + dy) * g + dx)
-                vals.append(np.full(ok.sum(), 26.0 if (dx, dy, dz) == (0, 0, 0) else -1.0))
-    r, c, v = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
-    if perturb:
-        v = v * (1 + 1e-3 * np.random.default_rng(seed).random(v.size))
-    rp, ci, va = _csr_from_coo(r, c, v, n, n)
-    return rp, ci, va, n
+                spec.append((ok, i + (dz * g + dy) * g + dx, 26.0 if (dx, dy, dz) == (0, 0, 0) else -1.0))
+    return _stencil_csr(n, spec, perturb, seed)
 
 
 def sym_block_banded(nb, b=16, bs=3, seed=3):
