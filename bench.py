@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — CSX SpMV throughput of the B200 engine (and of the CPU reference arm).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c4|c5|small] [--impl reference]
+
+A *step* is one SpMV  y = alpha*A*x  over the whole matrix (the hot path of
+BASELINE.json: spx_matvec_mult after spx_mat_tune).  For N > 1 the rows are the
+reference's nnz-balanced partitions with spx.rt.nr_threads = N, one partition
+per rank, and every step ends with the exchange of the y pieces into the next
+x (NCCL all-gather over NVLink) — strong scaling on a fixed matrix.
+
+Metric: GFLOP/s = 2 * nnz * K / t  (reference convention, src/bench/SparsexModule.cpp:80).
+Timing: W untimed steps, then exactly K steps between a barrier + synchronize on both sides,
+CUDA events on the launching stream, max over ranks.  The matrix (values alone: 671 MB for c2)
+is far larger than the 126 MB L2, so consecutive steps cannot be served from cache.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, generator kwargs, tuning options, cpu sample kwargs)
+    "c2": ("c2_poisson2d_4096", dict(kind="poisson2d", g=4096), {}, dict(kind="poisson2d", g=2048)),
+    "c3": ("c3_stencil27_256", dict(kind="stencil27", g=256), {}, dict(kind="stencil27", g=96)),
+    "c3b": ("c3_stencil27_256_blocks", dict(kind="stencil27", g=256), {"spx.preproc.xform": "br,bc"},
+            dict(kind="stencil27", g=96)),
+    "c4": ("c4_sym_block_banded_30M", dict(kind="symbb", nb=10_000_000, b=1024), {"spx.matrix.symmetric": "true"},
+           dict(kind="symbb", nb=500_000, b=1024)),
+    "c5": ("c5_rmat_26", dict(kind="rmat", scale=26), {"spx.preproc.xform": "none"}, dict(kind="rmat", scale=20)),
+    "small": ("small_poisson2d_512", dict(kind="poisson2d", g=512), {}, dict(kind="poisson2d", g=256)),
+}
+
+
+def generate(kind, **kw):
+    from tests import matrices as M
+    if kind == "poisson2d":
+        return M.poisson2d(kw["g"])
+    if kind == "stencil27":
+        return M.stencil27(kw["g"])
+    if kind == "symbb":
+        return M.sym_block_banded(kw["nb"], b=kw["b"])
+    if kind == "rmat":
+        return M.rmat(kw["scale"])
+    raise ValueError(kind)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=1)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch from the committed ncu --set full capture, if one exists for this workload."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------- CPU arm --
+def cpu_reference_run(sample_kw, opts, steps, warmup, threads=None):
+    """The reference's CPU path on this box's host cores: CSX encoded with spx.rt.nr_threads = T,
+    one persistent thread per partition.  Uses oracle/_ref (the reference's own kernel templates
+    compiled by gcc) when it was built, else the oracle's port of the same unit loops."""
+    from oracle.pyoracle import OracleMatrix
+    T = threads or (os.cpu_count() or 1)
+    rp, ci, va, n = generate(**sample_kw)
+    o = dict(opts)
+    o["spx.rt.nr_threads"] = T
+    o["oracle.undefined_sampling"] = "break"
+    t0 = time.time()
+    M = OracleMatrix.from_csr(rp, ci, va, n, n).tune(o)
+    tune_s = time.time() - t0
+    nnz = int(rp[-1])
+    x = np.random.default_rng(2).uniform(-1, 1, n)
+    kind = "port"
+    runner = M.bench
+    try:
+        from oracle import refkernels
+        if refkernels.available():
+            runner = refkernels.Runner(M).bench
+            kind = "reference"
+    except Exception:
+        pass
+    if warmup:
+        runner(0.5, x, warmup)
+    secs = runner(0.5, x, steps)
+    return {"value": 2.0 * nnz * steps / secs / 1e9, "unit": "GFLOP/s", "cores": T, "kind": kind,
+            "sample": "%s, %d rows, %d nnz, %d SpMVs, tune %.1f s, %s" % (sample_kw, n, nnz, steps, tune_s, M.log[:80]),
+            "ms_per_step": secs / steps * 1e3, "nnz": nnz}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name, gen_kw, opts, sample_kw = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(sample_kw, opts, max(args.steps, 1), args.warmup)
+        line = {"impl": "reference", "metric": "csx_spmv_gflops", "value": r["value"], "unit": "GFLOP/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "note": "CPU arm runs a bounded sample of the workload: " + r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sparsex_b200
+    from sparsex_b200.engine import CsxMatrix, SpxVector
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    api = sparsex_b200.load_spx_api()
+    api.spx_init()
+
+    # ---- load + tune through the public API (spx_input_load_csr / spx_mat_tune) ----
+    t0 = time.time()
+    rp, ci, va, n = generate(**gen_kw)
+    gen_s = time.time() - t0
+    nnz = int(rp[-1])
+    all_opts = dict(opts)
+    all_opts["spx.rt.nr_threads"] = world
+    all_opts["spx.b200.rows_info"] = "false"
+    for k, v in all_opts.items():
+        api.spx_option_set(k.encode(), str(v).encode())
+    api.spx_option_set(b"spx.b200.device", str(local_rank).encode())
+    api.spx_option_set(b"spx.b200.part_lo", str(rank).encode())
+    api.spx_option_set(b"spx.b200.part_hi", str(rank + 1).encode())
+    t0 = time.time()
+    inp = api.spx_input_load_csr(rp.ctypes.data, ci.ctypes.data, va.ctypes.data, n, n)
+    A = api.spx_mat_tune(inp)
+    if not A:
+        raise SystemExit("spx_mat_tune failed")
+    tune_s = time.time() - t0
+    api.spx_input_destroy(inp)
+    eng = CsxMatrix(api.spx_mat_get_engine(A))
+    eng._h_owned = False
+    part = eng.partition(0) if False else None  # values were kept on the host; only the log is needed below
+    enc_log = sparsex_b200.lib().csxb_part_log(eng._h, 0).decode()
+    row_lo = sparsex_b200.lib().csxb_part_info(eng._h, 0, 3)
+    row_n = sparsex_b200.lib().csxb_part_info(eng._h, 0, 1)
+    traffic = eng.traffic()
+    del rp, ci, va
+
+    # ---- device-resident timed region -----------------------------------------
+    alpha = 0.1 if world > 1 else 0.5
+    rng = np.random.default_rng(2)
+    x = torch.from_numpy(rng.uniform(-1, 1, n)).cuda()
+    y = torch.zeros(n, dtype=torch.float64, device="cuda")
+    counts = None
+    if world > 1:
+        info = torch.tensor([row_lo, row_n], dtype=torch.int64, device="cuda")
+        allinfo = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(allinfo, info)
+        counts = [(int(t[0]), int(t[1])) for t in allinfo]
+        xviews = [x[lo:lo + cnt] for lo, cnt in counts]
+
+    def step():
+        eng.spmv(alpha, x, y, overwrite=True)
+        if world > 1:  # x_{k+1} := y_k ; unequal piece sizes -> grouped broadcasts inside all_gather
+            dist.all_gather(xviews, y[row_lo:row_lo + row_n])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        eng.spmv(alpha, x, y, overwrite=True)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_gather(xviews, y[row_lo:row_lo + row_n])
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, kernel_ms = float(t[0]), float(t[1])
+    value = 2.0 * nnz * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end to end through spx_matvec_mult with host buffers ---------------------
+    xh = torch.from_numpy(rng.uniform(-1, 1, n)).pin_memory()
+    yh = torch.zeros(n, dtype=torch.float64).pin_memory()
+    vx = api.spx_vec_create_from_buff(xh.data_ptr(), None, n, None, 43)
+    vy = api.spx_vec_create_from_buff(yh.data_ptr(), None, n, None, 43)
+    for _ in range(2):
+        api.spx_matvec_mult(alpha, A, vx, vy)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        if api.spx_matvec_mult(alpha, A, vx, vy) != 0:
+            raise SystemExit("spx_matvec_mult failed")
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    e2e = {"value": 2.0 * nnz * args.e2e_steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n * world,
+           "d2h_bytes_per_step": 8 * n, "steps": args.e2e_steps,
+           "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory)"}
+    # check the device-resident result against the host-buffer path on the same x
+    x.copy_(xh, non_blocking=False)
+    eng.spmv(alpha, x, y, overwrite=True)
+    torch.cuda.synchronize()
+    dev = y[row_lo:row_lo + row_n].cpu().numpy()
+    hostp = yh.numpy()[row_lo:row_lo + row_n]
+    self_check = float(np.max(np.abs(dev - hostp)) / (np.max(np.abs(hostp)) + 1e-300))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = traffic["total"] / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": "csx_spmv_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "rows": n, "nnz": nnz, "options": {k: str(v) for k, v in all_opts.items()},
+                           "encoding_rank0": enc_log.strip(), "alpha": alpha,
+                           "step": "y = alpha*A*x (spx_matvec_mult semantics)" + (
+                               "; then NCCL all-gather of the y pieces into x" if world > 1 else ""),
+                           "l2_policy": "inputs larger than L2: %.0f MB of values+ctl per GPU vs 126 MB L2" % (
+                               (traffic["values"] + traffic["ctl"]) / 1e6),
+                           "tune_s": round(tune_s, 2), "generate_s": round(gen_s, 2),
+                           "self_check_rel": self_check},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": ncu_traffic(name), "peak_source": peak_src,
+                             "kernel": "csx_spmv_kernel (rank 0 partition)", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes": traffic["total"],
+                             "bytes": {k: traffic[k] for k in ("values", "ctl", "tables", "x", "y")},
+                             "frac_of_8TBs_nominal": achieved / 8000.0},
+                "e2e": e2e, "gpu_launches": int(traffic["launches"]) * args.steps, "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = cpu_reference_run(sample_kw, opts, 32, 2)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"],
+                                        "sample": r["sample"]}
+            except Exception as ex:  # the CPU baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port",
+                                        "sample": "failed: %r" % (ex,)}
+        print(json.dumps(line))
+    api.spx_vec_destroy(vx)
+    api.spx_vec_destroy(vy)
+    eng._h = None  # owned by the spx matrix handle
+    api.spx_mat_destroy(A)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

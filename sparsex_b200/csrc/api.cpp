@@ -31,6 +31,7 @@ std::map<std::string, std::string> &props() {
 }
 int g_device = 0;
 bool g_async = false;
+int g_part_lo = 0, g_part_hi = -1;   // one process per GPU: encode and own only partitions [lo, hi)
 int g_log_level = 2;  // 0 none, 1 error, 2 warning, 3 info, 4 verbose, 5 debug
 FILE *g_log_file = nullptr;
 
@@ -161,6 +162,8 @@ void spx_option_set(const char *option, const char *value) {  // matvec.c:753-75
   std::string k(option), v(value);
   if (k == "spx.b200.device") { g_device = atoi(value); return; }
   if (k == "spx.b200.async") { g_async = (v == "true" || v == "1"); return; }
+  if (k == "spx.b200.part_lo") { g_part_lo = atoi(value); return; }
+  if (k == "spx.b200.part_hi") { g_part_hi = atoi(value); return; }
   spxb::TuneOptions probe;
   std::string e = probe.set(k, v);
   if (!e.empty()) {
@@ -234,7 +237,8 @@ spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
   std::string opts = options_string();
   csxb_matrix_t *m = nullptr;
   if (in->type == 'C')
-    m = csxb_tune_csr(in->rowptr, in->colind, in->values, in->nrows, in->ncols, opts.c_str(), 0, -1, err, sizeof(err));
+    m = csxb_tune_csr(in->rowptr, in->colind, in->values, in->nrows, in->ncols, opts.c_str(), g_part_lo, g_part_hi, err,
+                      sizeof(err));
   else if (in->type == 'M')
     m = csxb_tune_coo_internal(*in->coo, opts.c_str(), err, sizeof(err));
   if (!m) { spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
@@ -395,7 +399,17 @@ static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx
     spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
     return SPX_FAILURE;
   }
-  if (y_host) cudaMemcpyAsync(y->elements, A->stage_y, (size_t)A->nrows * 8, cudaMemcpyDeviceToHost, 0);
+  if (y_host) {  // only the rows this handle owns travel back (all of y when every partition is local)
+    int np = (int)csxb_info(A->csx, CSXB_NPARTS);
+    bool all = np == (int)csxb_info(A->csx, CSXB_NPARTS_TOTAL);
+    long lo = 0, hi = A->nrows;
+    if (!all && np > 0) {
+      lo = (long)csxb_part_info(A->csx, 0, CSXB_P_ROW_START);
+      hi = (long)csxb_part_info(A->csx, np - 1, CSXB_P_ROW_START) + (long)csxb_part_info(A->csx, np - 1, CSXB_P_NROWS);
+      if ((int)csxb_info(A->csx, CSXB_PART_LO) + np == (int)csxb_info(A->csx, CSXB_NPARTS_TOTAL)) hi = A->nrows;
+    }
+    if (hi > lo) cudaMemcpyAsync(y->elements + lo, A->stage_y + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, 0);
+  }
   if (y_host || !g_async) {
     cudaError_t e = cudaStreamSynchronize(0);
     if (e != cudaSuccess) {

@@ -591,7 +591,9 @@ template <bool SYM>
 static void launch_main(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
                         int overwrite, cudaStream_t s) {
   dim3 grid((unsigned)pl.ntiles), block(TILE_ROWS);
-  if (pl.has_row_local && pl.has_cross) csx_spmv_kernel<true, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  // descriptors can also come from other partitions (transposed images under CSX-Sym)
+  const bool has_xd = !pl.xdesc.empty();
+  if (pl.has_row_local && has_xd) csx_spmv_kernel<true, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
   else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
   else csx_spmv_kernel<false, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
 }
