@@ -167,3 +167,37 @@ extern "C" double csxo_bench(void *hv, double alpha, const double *x, double *y,
   pthread_barrier_destroy(&bar);
   return secs;
 }
+
+// Same persistent-thread protocol, but each partition runs a function compiled from the reference's own
+// kernel templates (oracle/_ref, see refkernels.py).  fns[i] has the spmv_fn_t signature of
+// SpmvMethod.hpp:25-26; csx[i] points to a csx_matrix_t; xvec/yvec point to vector_t structs.
+typedef void (*ref_spmv_fn)(void *, void *, void *, double, void *);
+struct ref_vector { double *elements; size_t size; int alloc_type; int vec_mode; };
+extern "C" double csxo_ref_bench(int nparts, void **fns, void **csx, void *xvec, void *yvec, double alpha, int loops) {
+  ref_vector *y = (ref_vector *)yvec;
+  size_t nt = (size_t)nparts;
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, (unsigned)nt);
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nt; t++)
+    th.emplace_back([&, t]() {
+      cpu_set_t set; CPU_ZERO(&set); CPU_SET((int)t, &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+      for (int l = 0; l < loops; l++) {
+        pthread_barrier_wait(&bar);
+        ((ref_spmv_fn)fns[t])(csx[t], xvec, yvec, alpha, nullptr);
+        pthread_barrier_wait(&bar);
+      }
+    });
+  auto t0 = std::chrono::steady_clock::now();
+  for (int l = 0; l < loops; l++) {
+    for (size_t i = 0; i < y->size; i++) y->elements[i] = 0;   // VecInit(y, 0), CsxKernels.cpp:93
+    pthread_barrier_wait(&bar);
+    ((ref_spmv_fn)fns[0])(csx[0], xvec, yvec, alpha, nullptr);
+    pthread_barrier_wait(&bar);
+  }
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&bar);
+  return secs;
+}

@@ -177,7 +177,9 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
             if (q < 0) return "symmetric update targets a row that is not on this device";
             int64_t rel = g - m.parts[q].row_start;
             pend.push_back(Pending{q, rel / TILE_ROWS, td});
-            g = m.parts[q].row_start + (rel / TILE_ROWS + 1) * TILE_ROWS;   // first row of the next tile
+            // first row of the next tile, or of the next partition if that comes first
+            g = std::min(m.parts[q].row_start + (rel / TILE_ROWS + 1) * TILE_ROWS,
+                         m.parts[q].row_start + m.parts[q].nrows);
           }
         }
       }
