@@ -982,6 +982,7 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
     out.nrows = nrows; out.ncols = ncols; out.nnz = cur.n;
     out.symmetric = opt.symmetric; out.full_colind = opt.full_colind;
     out.nparts_total = np; out.part_lo = part_lo;
+    out.rows_per_thread = opt.rows_per_thread;
     out.parts.resize(part_hi - part_lo);
     bool sym = opt.symmetric;
     if (sym && nrows != ncols) throw TuneError("spx.matrix.symmetric requires a square matrix");
@@ -1076,6 +1077,10 @@ std::string TuneOptions::set(const std::string &k, const std::string &v) {
     else if (k == "spx.matrix.min_coverage") min_coverage = std::stod(v);
     else if (k == "spx.b200.rows_info") return as_bool(build_rows_info);
     else if (k == "spx.b200.host_threads") host_threads = std::stoi(v);
+    else if (k == "spx.b200.rows_per_thread") {
+      rows_per_thread = std::stoi(v);
+      if (rows_per_thread != 0 && rows_per_thread != 1 && rows_per_thread != 4) return "spx.b200.rows_per_thread must be 0, 1 or 4";
+    }
     else return "unknown option \"" + k + "\"";
   } catch (std::exception &) {
     return "invalid value \"" + v + "\" while setting property \"" + k + "\"";

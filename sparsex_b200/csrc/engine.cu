@@ -47,6 +47,7 @@ struct PartDev {
   long long nrows, row_start;  // owned rows
   uint32_t val_base;
   int full_colind;
+  int rpt;                     // rows per thread: a tile has CTA_THREADS * rpt rows
   KindEntry idtab[64];
 };
 
@@ -222,6 +223,48 @@ __device__ __forceinline__ void gather_desc(const uint4 d, const KindEntry *__re
   }
 }
 
+// rows a descriptor can contribute to: [lo, hi] (global rows; columns for a transposed image)
+template <bool SYM>
+__device__ __forceinline__ bool desc_touches(const uint4 d, const KindEntry *__restrict__ ktab, int row_lo, int row_hi) {
+  const uint32_t meta = d.w, kind = (meta >> 24) & 0xf, size = (meta >> 16) & 0xff;
+  const int r = (int)d.y, c = (int)d.z;
+  int lo, hi;
+  if (kind <= K_ADIAG) {
+    uint32_t delta = (meta & XD_DELTA1) ? 1u : __ldg(&ktab[meta & 0xffff].delta);
+    int span = (int)((size - 1) * delta);
+    if (!SYM || !(meta & XD_TRANSPOSED)) { lo = r; hi = r + span; }
+    else if (kind == K_VERT) { lo = hi = c; }
+    else if (kind == K_DIAG) { lo = c; hi = c + span; }
+    else { lo = c - span; hi = c; }
+  } else {
+    uint32_t a = (meta >> 29) + 1, other = size / a;   // BROW: a rows x other cols ; BCOL: other rows x a cols
+    int rows = kind == K_BROW ? (int)a : (int)other, cols = kind == K_BROW ? (int)other : (int)a;
+    if (!SYM || !(meta & XD_TRANSPOSED)) { lo = r; hi = r + rows - 1; }
+    else { lo = c; hi = c + cols - 1; }
+  }
+  return lo <= row_hi && hi >= row_lo;
+}
+
+// Linear kinds contribute at most one element per row: returns its value index and x index.
+template <bool SYM>
+__device__ __forceinline__ bool linear_probe(const uint4 d, const KindEntry *__restrict__ ktab, int myrow, uint32_t &vi, int &xi) {
+  const uint32_t meta = d.w, kind = (meta >> 24) & 0xf, size = (meta >> 16) & 0xff;
+  const int r = (int)d.y, c = (int)d.z;
+  const bool tr = SYM && (meta & XD_TRANSPOSED);
+  int t = !tr ? myrow - r : (kind == K_ADIAG ? c - myrow : myrow - c);
+  if (t < 0) return false;
+  uint32_t k = (uint32_t)t;
+  if (!(meta & XD_DELTA1)) {
+    uint32_t delta = __ldg(&ktab[meta & 0xffff].delta);
+    k = (uint32_t)t / delta;
+    if (k * delta != (uint32_t)t) return false;
+  }
+  if (k >= size) return false;
+  vi = d.x + k;
+  xi = !tr ? (kind == K_VERT ? c : (kind == K_DIAG ? c + t : c - t)) : r + t;
+  return true;
+}
+
 struct SpmvWalkOp {
   const double *__restrict__ values;  // partition base applied
   const double *__restrict__ x;
@@ -241,37 +284,94 @@ struct SpmvGatherOp {
   __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * __ldg(x + xi); }
 };
 
-template <bool WALK, bool XD, bool SYM>
-__global__ void __launch_bounds__(TILE_ROWS) csx_spmv_kernel(const __grid_constant__ PartDev P, const double *__restrict__ x,
-                                                             double *__restrict__ y, double alpha, double beta,
-                                                             int overwrite) {
+// One CTA = one tile of CTA_THREADS * RPT rows; warp w owns RPT consecutive 32-row segments and lane L
+// owns rows  tile0 + (w*RPT + k)*32 + L,  k < RPT  (RPT independent accumulators per thread).
+template <bool WALK, bool XD, bool SYM, int RPT>
+__global__ void __launch_bounds__(CTA_THREADS) csx_spmv_kernel(const __grid_constant__ PartDev P,
+                                                               const double *__restrict__ x, double *__restrict__ y,
+                                                               double alpha, double beta, int overwrite) {
+  __shared__ uint4 s_desc[XD ? CTA_THREADS : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = blockIdx.x;
-  const long long seg = tile * (TILE_ROWS / SEG_ROWS) + warp;
-  const long long lrow = seg * SEG_ROWS + lane;
-  if (seg * SEG_ROWS >= P.nrows) return;
+  const long long seg0 = (tile * (CTA_THREADS / SEG_ROWS) + warp) * RPT;
+  const long long lrow0 = seg0 * SEG_ROWS;             // first row of this warp (partition relative)
+  const bool warp_active = lrow0 < P.nrows;
   const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
-  double acc = 0;
-  if (WALK && (tx0 & 0x80000000u)) {
-    SpmvWalkOp op{P.values + P.val_base, x, 0.0, 0.0, lane};
-    walk_segment(P, seg, lane, op);
-    acc = op.acc;
-  }
-  if (XD) {
-    SpmvGatherOp op{P.values, x, 0.0};
-    const int myrow = (int)(P.row_start + lrow);
-    const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
-    for (uint32_t j = b; j < e; j++) gather_desc<SYM>(__ldg(P.xdesc + j), P.ktab, myrow, op);
-    acc += op.acc;
-  }
-  if (lrow < P.nrows) {
-    const long long g = P.row_start + lrow;
-    if (SYM) {  // diagonal (CsxJit.hpp:373-394 new-row hook) + reduce of the local vector
-      acc += __ldg(P.dvalues + lrow) * __ldg(x + g);
-      acc += P.tbuf[g];
-      P.tbuf[g] = 0.0;
+  double acc[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; k++) acc[k] = 0.0;
+
+  if (WALK && warp_active && (tx0 & 0x80000000u)) {
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      if ((seg0 + k) * SEG_ROWS < P.nrows) {
+        SpmvWalkOp op{P.values + P.val_base, x, 0.0, 0.0, lane};
+        walk_segment(P, seg0 + k, lane, op);
+        acc[k] += op.acc;
+      }
     }
-    y[g] = overwrite ? alpha * acc : alpha * acc + beta * y[g];
+  }
+
+  if (XD) {
+    const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
+    const int grow0 = (int)(P.row_start + lrow0);       // global rows of this warp: [grow0, grow0 + 32*RPT)
+    const double *__restrict__ values = P.values;
+    for (uint32_t base = b; base < e; base += CTA_THREADS) {
+      const uint32_t n = min((uint32_t)CTA_THREADS, e - base);
+      if (base != b) __syncthreads();
+      if (threadIdx.x < n) s_desc[threadIdx.x] = __ldg(P.xdesc + base + threadIdx.x);
+      __syncthreads();
+      if (!warp_active) continue;
+      for (uint32_t w0 = 0; w0 < n; w0 += 32) {
+        const uint32_t j = w0 + lane;
+        bool hit = false;
+        if (j < n) hit = desc_touches<SYM>(s_desc[j], P.ktab, grow0, grow0 + 32 * RPT - 1);
+        uint32_t mask = __ballot_sync(FULL, hit);
+        while (mask) {
+          const uint4 d = s_desc[w0 + __ffs(mask) - 1];
+          mask &= mask - 1;
+          const uint32_t kind = (d.w >> 24) & 0xf;
+          // one element per row: every linear kind except the transposed image of a vertical unit,
+          // which folds the whole unit into the single row of its column
+          if (kind <= K_ADIAG && !(SYM && kind == K_VERT && (d.w & XD_TRANSPOSED))) {
+            // issue all RPT value / x loads of this unit before using them
+            double v[RPT], xv[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+              uint32_t vi; int xi;
+              v[k] = 0.0; xv[k] = 0.0;
+              if (linear_probe<SYM>(d, P.ktab, grow0 + k * 32 + lane, vi, xi)) { v[k] = __ldg(values + vi); xv[k] = __ldg(x + xi); }
+            }
+#pragma unroll
+            for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+              SpmvGatherOp op{values, x, 0.0};
+              gather_desc<SYM>(d, P.ktab, grow0 + k * 32 + lane, op);
+              acc[k] += op.acc;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (warp_active) {
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const long long lrow = lrow0 + k * 32 + lane;
+      if (lrow < P.nrows) {
+        const long long g = P.row_start + lrow;
+        double a = acc[k];
+        if (SYM) {  // diagonal (CsxJit.hpp:373-394 new-row hook) + reduce of the local vector
+          a += __ldg(P.dvalues + lrow) * __ldg(x + g);
+          a += P.tbuf[g];
+          P.tbuf[g] = 0.0;
+        }
+        y[g] = overwrite ? alpha * a : alpha * a + beta * y[g];
+      }
+    }
   }
 }
 
@@ -288,14 +388,17 @@ struct SymScatterOp {
   }
   __device__ __forceinline__ void row_done(int) {}
 };
-__global__ void __launch_bounds__(TILE_ROWS) csx_sym_scatter_kernel(const __grid_constant__ PartDev P, const double *__restrict__ x) {
+__global__ void __launch_bounds__(CTA_THREADS) csx_sym_scatter_kernel(const __grid_constant__ PartDev P,
+                                                                      const double *__restrict__ x) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = blockIdx.x;
-  const long long seg = tile * (TILE_ROWS / SEG_ROWS) + warp;
-  if (seg * SEG_ROWS >= P.nrows) return;
   if (!(__ldg(P.tile_xoff + tile) & 0x80000000u)) return;
-  SymScatterOp op{P.values + P.val_base, x, P.tbuf, P.row_start + seg * SEG_ROWS};
-  walk_segment(P, seg, lane, op);
+  for (int k = 0; k < P.rpt; k++) {
+    const long long seg = (tile * (CTA_THREADS / SEG_ROWS) + warp) * P.rpt + k;
+    if (seg * SEG_ROWS >= P.nrows) return;
+    SymScatterOp op{P.values + P.val_base, x, P.tbuf, P.row_start + seg * SEG_ROWS};
+    walk_segment(P, seg, lane, op);
+  }
 }
 
 // Parity aid: the same traversal, storing the decoded coordinates per value.
@@ -310,21 +413,23 @@ struct DecodeGatherOp {
   int myrow;
   __device__ __forceinline__ void add(uint32_t vi, int col) { rows[vi] = myrow; cols[vi] = col; }
 };
-__global__ void __launch_bounds__(TILE_ROWS) csx_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
+__global__ void __launch_bounds__(CTA_THREADS) csx_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = blockIdx.x;
-  const long long seg = tile * (TILE_ROWS / SEG_ROWS) + warp;
-  if (seg * SEG_ROWS >= P.nrows) return;
   const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
-  if (tx0 & 0x80000000u) {
-    DecodeWalkOp op{rows + P.val_base, cols + P.val_base, P.row_start + seg * SEG_ROWS};
-    walk_segment(P, seg, lane, op);
-  }
-  DecodeGatherOp op{rows, cols, (int)(P.row_start + seg * SEG_ROWS + lane)};
-  for (uint32_t j = tx0 & 0x7fffffffu; j < (tx1 & 0x7fffffffu); j++) {
-    uint4 d = __ldg(P.xdesc + j);
-    if (d.w & XD_TRANSPOSED) continue;
-    gather_desc<false>(d, P.ktab, op.myrow, op);
+  for (int k = 0; k < P.rpt; k++) {
+    const long long seg = (tile * (CTA_THREADS / SEG_ROWS) + warp) * P.rpt + k;
+    if (seg * SEG_ROWS >= P.nrows) return;
+    if (tx0 & 0x80000000u) {
+      DecodeWalkOp op{rows + P.val_base, cols + P.val_base, P.row_start + seg * SEG_ROWS};
+      walk_segment(P, seg, lane, op);
+    }
+    DecodeGatherOp op{rows, cols, (int)(P.row_start + seg * SEG_ROWS + lane)};
+    for (uint32_t j = tx0 & 0x7fffffffu; j < (tx1 & 0x7fffffffu); j++) {
+      uint4 d = __ldg(P.xdesc + j);
+      if (d.w & XD_TRANSPOSED) continue;
+      gather_desc<false>(d, P.ktab, op.myrow, op);
+    }
   }
 }
 
@@ -561,6 +666,7 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     }
     P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
     P.full_colind = L.full_colind;
+    P.rpt = pl.rpt;
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
     nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
@@ -587,15 +693,21 @@ int64_t csxb_traffic(const csxb_matrix_t *m, int what) {
 
 }  // extern "C"
 
+template <bool SYM, int RPT>
+static void launch_main_rpt(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
+                            int overwrite, cudaStream_t s) {
+  dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
+  // descriptors can also come from other partitions (transposed images under CSX-Sym)
+  const bool has_xd = !pl.xdesc.empty();
+  if (pl.has_row_local && has_xd) csx_spmv_kernel<true, true, SYM, RPT><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM, RPT><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else csx_spmv_kernel<false, true, SYM, RPT><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+}
 template <bool SYM>
 static void launch_main(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
                         int overwrite, cudaStream_t s) {
-  dim3 grid((unsigned)pl.ntiles), block(TILE_ROWS);
-  // descriptors can also come from other partitions (transposed images under CSX-Sym)
-  const bool has_xd = !pl.xdesc.empty();
-  if (pl.has_row_local && has_xd) csx_spmv_kernel<true, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else csx_spmv_kernel<false, true, SYM><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  if (pl.rpt == 4) launch_main_rpt<SYM, 4>(P, pl, x, y, alpha, beta, overwrite, s);
+  else launch_main_rpt<SYM, 1>(P, pl, x, y, alpha, beta, overwrite, s);
 }
 
 extern "C" {
@@ -607,7 +719,7 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   if (sym)  // every scatter must land before any tile folds tbuf into y
     for (size_t i = 0; i < m->pdev.size(); i++) {
       const PartLayout &pl = m->layout.parts[i];
-      if (pl.ntiles && pl.has_row_local) csx_sym_scatter_kernel<<<(unsigned)pl.ntiles, TILE_ROWS, 0, s>>>(m->pdev[i], d_x);
+      if (pl.ntiles && pl.has_row_local) csx_sym_scatter_kernel<<<(unsigned)pl.ntiles, CTA_THREADS, 0, s>>>(m->pdev[i], d_x);
     }
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
@@ -655,7 +767,7 @@ int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t
   CUDA_TRY(cudaMalloc((void **)&dcl, std::max<size_t>(n, 1) * 4));
   CUDA_TRY(cudaMemset(dr, 0xff, std::max<size_t>(n, 1) * 4));
   CUDA_TRY(cudaMemset(dcl, 0xff, std::max<size_t>(n, 1) * 4));
-  if (pl.ntiles) csx_decode_kernel<<<(unsigned)pl.ntiles, TILE_ROWS>>>(m->pdev[part], dr, dcl);
+  if (pl.ntiles) csx_decode_kernel<<<(unsigned)pl.ntiles, CTA_THREADS>>>(m->pdev[part], dr, dcl);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy(rows, dr + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(cols, dcl + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));

@@ -54,6 +54,9 @@ bool classify(long pid, KindEntry &ke) {
 
 struct Pending { int64_t part; int64_t tile; XDesc d; };
 
+// rows per thread of a partition's tiles (a later partition's value is needed while an earlier one is decoded)
+inline int tile_rpt(int64_t nrows, int forced) { return forced ? forced : (nrows >= (int64_t(1) << 20) ? 4 : 1); }
+
 }  // namespace
 
 std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
@@ -81,6 +84,9 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     vbase += (uint64_t)cp.nnz;
     cbase += ((uint64_t)cp.ctl.size() + CTL_PAD + 15) & ~uint64_t(15);
     L.nseg = (cp.nrows + SEG_ROWS - 1) / SEG_ROWS;
+    // big partitions: 4 rows per thread (more loads in flight per thread, fewer carry-in descriptors)
+    L.rpt = tile_rpt(cp.nrows, m.rows_per_thread);
+    const int64_t TILE_ROWS = L.tile_rows();
     L.ntiles = (cp.nrows + TILE_ROWS - 1) / TILE_ROWS;
     L.seg_ctl.assign((size_t)L.nseg + 1, 0);
     L.seg_val.assign((size_t)L.nseg + 1, 0);
@@ -176,10 +182,10 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
             int64_t q = owner_of(g);
             if (q < 0) return "symmetric update targets a row that is not on this device";
             int64_t rel = g - m.parts[q].row_start;
-            pend.push_back(Pending{q, rel / TILE_ROWS, td});
+            const int64_t qt = out.parts[q].rpt ? (int64_t)CTA_THREADS * tile_rpt(m.parts[q].nrows, m.rows_per_thread) : 0;
+            pend.push_back(Pending{q, rel / qt, td});
             // first row of the next tile, or of the next partition if that comes first
-            g = std::min(m.parts[q].row_start + (rel / TILE_ROWS + 1) * TILE_ROWS,
-                         m.parts[q].row_start + m.parts[q].nrows);
+            g = std::min(m.parts[q].row_start + (rel / qt + 1) * qt, m.parts[q].row_start + m.parts[q].nrows);
           }
         }
       }

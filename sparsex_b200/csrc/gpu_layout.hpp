@@ -15,7 +15,7 @@
 //   * cross-row unit table (XDT) — vertical, diagonal, anti-diagonal and block
 //     units update several rows.  Each such unit gets a 16-byte descriptor
 //     (value offset, start row, start column, kind/size) that is listed under
-//     every 256-row tile it touches, including tiles after the one it starts
+//     every row tile (256 or 1024 rows) it touches, including tiles after the one it starts
 //     in ("carry-in").  The thread that owns a row gathers its contributions
 //     from the descriptors of its tile: conflict free, no atomics, y written
 //     once.  For CSX-Sym the transposed image of every cross-row unit is
@@ -31,7 +31,7 @@
 namespace spxb {
 
 constexpr int SEG_ROWS = 32;     // rows per warp segment
-constexpr int TILE_ROWS = 256;   // rows per XDT tile == threads per CTA
+constexpr int CTA_THREADS = 256; // threads per CTA; a tile has CTA_THREADS * rpt rows
 constexpr int CTL_PAD = 32;      // readable bytes past the end of ctl
 
 // unit kinds as the kernels see them
@@ -59,6 +59,8 @@ struct PartLayout {
   uint64_t val_base = 0, ctl_base = 0;   // offsets into the device-wide arrays
   bool has_row_local = false, has_cross = false;
   int64_t nseg = 0, ntiles = 0;
+  int rpt = 1;                           // rows per thread (1 or 4): tile_rows = CTA_THREADS * rpt
+  int64_t tile_rows() const { return (int64_t)CTA_THREADS * rpt; }
   KindEntry idtab[64];                   // ctl unit id -> kind
   std::vector<uint64_t> seg_ctl;         // nseg + 1 ; [63:56] row within segment, [55:0] ctl offset (partition relative)
   std::vector<uint32_t> seg_val;         // nseg + 1 ; value index (partition relative)

@@ -49,7 +49,7 @@ def check_matrix(rowptr, colind, values, n, m, opts, seed=0, check_decode=True, 
     from sparsex_b200 import CsxMatrix
 
     rng = np.random.default_rng(seed)
-    oopts = dict(opts)
+    oopts = {k: v for k, v in opts.items() if not k.startswith("spx.b200.")}
     oopts["oracle.undefined_sampling"] = "break"
     O = OracleMatrix.from_csr(rowptr, colind, values, n, m).tune(oopts)
     A = CsxMatrix.tune_csr(rowptr, colind, values, n, m, opts)
@@ -177,6 +177,30 @@ def test_empty_and_degenerate():
     va = rng.standard_normal(ci.size)
     check_matrix(rp, ci, va, 64, m, {"spx.preproc.xform": "none"})
     check_matrix(rp, ci, va, 64, m, {"spx.preproc.xform": "none", "spx.matrix.full_colind": "true"})
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_structured_four_rows_per_thread(seed):
+    """Same inputs with the 1024-row tile shape (4 rows per thread) that large partitions use."""
+    rng = np.random.default_rng(300 + seed)
+    for trial in range(3):
+        n = int(rng.integers(900, 4000))
+        sym = trial % 2 == 0
+        m = n if sym else int(rng.integers(900, 4000))
+        rp, ci, va = random_structured(rng, n, m, symmetric=sym)
+        for xf in XFORMS:
+            for extra in ({}, {"spx.rt.nr_threads": int(rng.integers(2, 4))}, {"spx.preproc.sampling": "none"}):
+                for s in (("true", "false") if sym else ("false",)):
+                    o = {"spx.preproc.xform": xf, "spx.matrix.symmetric": s, "spx.b200.rows_per_thread": 4}
+                    o.update(extra)
+                    check_matrix(rp, ci, va, n, m, o, seed=seed)
+
+
+def test_large_partition_auto_tile():
+    """>= 2^20 rows: the automatic choice of the 4-rows-per-thread tile."""
+    rp, ci, va, n = poisson2d(1100)
+    check_matrix(rp, ci, va, n, n, {})
+    check_matrix(rp, ci, va, n, n, {"spx.matrix.symmetric": "true"}, check_decode=False)
 
 
 @pytest.mark.parametrize("opts", [{}, {"spx.preproc.xform": "none"}, {"spx.preproc.xform": "br,bc"},
