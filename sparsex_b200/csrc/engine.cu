@@ -285,23 +285,28 @@ struct SpmvGatherOp {
 };
 
 // One CTA = one tile of CTA_THREADS * RPT rows; warp w owns RPT consecutive 32-row segments and lane L
-// owns rows  tile0 + (w*RPT + k)*32 + L,  k < RPT  (RPT independent accumulators per thread).
-template <bool WALK, bool XD, bool SYM, int RPT>
-__global__ void __launch_bounds__(CTA_THREADS) csx_spmv_kernel(const __grid_constant__ PartDev P,
-                                                               const double *__restrict__ x, double *__restrict__ y,
-                                                               double alpha, double beta, int overwrite) {
-  __shared__ uint4 s_desc[XD ? CTA_THREADS : 1];
+// owns rows  tile0 + (w*RPT + k)*32 + L,  k < RPT  (RPT independent accumulators per thread).  Warps never
+// synchronise with each other.  KSET specialises phase B for the set of unit kinds the partition's table holds:
+//   KSET_ANY    every cross-row kind, CSX-Sym images included
+//   KSET_DIAG1  only diagonal units of stride 1 (what the stencil matrices of the baseline configs encode to)
+// The kernel is bandwidth-bound and latency-sensitive: it is compiled for 8 resident CTAs per SM (32 registers).
+enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
+template <bool WALK, bool XD, bool SYM, int RPT, int KSET>
+__global__ void __launch_bounds__(CTA_THREADS, XD ? 8 : 4) csx_spmv_kernel(const __grid_constant__ PartDev P,
+                                                                           const double *__restrict__ x,
+                                                                           double *__restrict__ y, double alpha,
+                                                                           double beta, int overwrite) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = blockIdx.x;
   const long long seg0 = (tile * (CTA_THREADS / SEG_ROWS) + warp) * RPT;
   const long long lrow0 = seg0 * SEG_ROWS;             // first row of this warp (partition relative)
-  const bool warp_active = lrow0 < P.nrows;
+  if (lrow0 >= P.nrows) return;
   const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
   double acc[RPT];
 #pragma unroll
   for (int k = 0; k < RPT; k++) acc[k] = 0.0;
 
-  if (WALK && warp_active && (tx0 & 0x80000000u)) {
+  if (WALK && (tx0 & 0x80000000u)) {
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
       if ((seg0 + k) * SEG_ROWS < P.nrows) {
@@ -316,6 +321,120 @@ __global__ void __launch_bounds__(CTA_THREADS) csx_spmv_kernel(const __grid_cons
     const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
     const int grow0 = (int)(P.row_start + lrow0);       // global rows of this warp: [grow0, grow0 + 32*RPT)
     const double *__restrict__ values = P.values;
+    // each lane inspects one descriptor of the tile; the ones that reach this warp's rows are
+    // then visited by the whole warp (warp-uniform loop over the ballot mask)
+    for (uint32_t base = b; base < e; base += 32) {
+      const uint32_t j = base + lane;
+      bool hit = false;
+      if (j < e) {
+        const uint4 d = __ldg(P.xdesc + j);
+        if (KSET == KSET_DIAG1) hit = (int)d.y <= grow0 + 32 * RPT - 1 && (int)d.y + (int)((d.w >> 16) & 0xff) > grow0;
+        else hit = desc_touches<SYM>(d, P.ktab, grow0, grow0 + 32 * RPT - 1);
+      }
+      uint32_t mask = __ballot_sync(FULL, hit);
+      while (mask) {
+        const uint4 d = __ldg(P.xdesc + base + __ffs(mask) - 1);
+        mask &= mask - 1;
+        if (KSET == KSET_DIAG1) {  // diag_tmpl.c with delta 1: y[r+k] += x[c+k] * v[k]
+          const int t0 = grow0 + lane - (int)d.y;
+          const uint32_t size = (d.w >> 16) & 0xff;
+          double v[RPT], xv[RPT];
+#pragma unroll
+          for (int k = 0; k < RPT; k++) {
+            const int t = t0 + k * 32;
+            v[k] = 0.0; xv[k] = 0.0;
+            if ((uint32_t)t < size) { v[k] = __ldg(values + d.x + t); xv[k] = __ldg(x + (int)d.z + t); }
+          }
+#pragma unroll
+          for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
+          continue;
+        }
+        const uint32_t kind = (d.w >> 24) & 0xf;
+        // one element per row: every linear kind except the transposed image of a vertical unit,
+        // which folds the whole unit into the single row of its column
+        if (kind <= K_ADIAG && !(SYM && kind == K_VERT && (d.w & XD_TRANSPOSED))) {
+          double v[RPT], xv[RPT];  // issue all RPT value / x loads of this unit before using them
+#pragma unroll
+          for (int k = 0; k < RPT; k++) {
+            uint32_t vi; int xi;
+            v[k] = 0.0; xv[k] = 0.0;
+            if (linear_probe<SYM>(d, P.ktab, grow0 + k * 32 + lane, vi, xi)) { v[k] = __ldg(values + vi); xv[k] = __ldg(x + xi); }
+          }
+#pragma unroll
+          for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < RPT; k++) {
+            SpmvGatherOp op{values, x, 0.0};
+            gather_desc<SYM>(d, P.ktab, grow0 + k * 32 + lane, op);
+            acc[k] += op.acc;
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int k = 0; k < RPT; k++) {
+    const long long lrow = lrow0 + k * 32 + lane;
+    if (lrow < P.nrows) {
+      const long long g = P.row_start + lrow;
+      double a = acc[k];
+      if (SYM) {  // diagonal (CsxJit.hpp:373-394 new-row hook) + reduce of the local vector
+        a += __ldg(P.dvalues + lrow) * __ldg(x + g);
+        a += P.tbuf[g];
+        P.tbuf[g] = 0.0;
+      }
+      y[g] = overwrite ? alpha * a : alpha * a + beta * y[g];
+    }
+  }
+}
+
+// ---- experimental variants of phase B (selected with csxb_debug_variant; used to tune the shipped kernel) ----
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+template <int RPT, int BATCH, int STAGE, bool NOALLOC, int MINB = 1>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) csx_xd_exp_kernel(const __grid_constant__ PartDev P,
+                                                                 const double *__restrict__ x, double *__restrict__ y,
+                                                                 double alpha) {
+  __shared__ uint4 s_desc[STAGE == 0 ? CTA_THREADS : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x;
+  const long long seg0 = (tile * (CTA_THREADS / SEG_ROWS) + warp) * RPT;
+  const long long lrow0 = seg0 * SEG_ROWS;
+  const bool warp_active = lrow0 < P.nrows;
+  const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
+  const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
+  const int grow0 = (int)(P.row_start + lrow0);
+  const double *__restrict__ values = P.values;
+  double acc[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; k++) acc[k] = 0.0;
+
+  auto consume = [&](const uint4 *dd, int nd) {
+    double v[BATCH][RPT], xv[BATCH][RPT];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+#pragma unroll
+      for (int k = 0; k < RPT; k++) {
+        uint32_t vi; int xi;
+        v[u][k] = 0.0; xv[u][k] = 0.0;
+        if (u < nd && linear_probe<false>(dd[u], P.ktab, grow0 + k * 32 + lane, vi, xi)) {
+          v[u][k] = NOALLOC ? ld_stream_f64(values + vi) : __ldg(values + vi);
+          xv[u][k] = __ldg(x + xi);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; u++)
+#pragma unroll
+      for (int k = 0; k < RPT; k++) acc[k] += v[u][k] * xv[u][k];
+  };
+
+  if (STAGE == 0) {
     for (uint32_t base = b; base < e; base += CTA_THREADS) {
       const uint32_t n = min((uint32_t)CTA_THREADS, e - base);
       if (base != b) __syncthreads();
@@ -325,52 +444,39 @@ __global__ void __launch_bounds__(CTA_THREADS) csx_spmv_kernel(const __grid_cons
       for (uint32_t w0 = 0; w0 < n; w0 += 32) {
         const uint32_t j = w0 + lane;
         bool hit = false;
-        if (j < n) hit = desc_touches<SYM>(s_desc[j], P.ktab, grow0, grow0 + 32 * RPT - 1);
+        if (j < n) hit = desc_touches<false>(s_desc[j], P.ktab, grow0, grow0 + 32 * RPT - 1);
         uint32_t mask = __ballot_sync(FULL, hit);
         while (mask) {
-          const uint4 d = s_desc[w0 + __ffs(mask) - 1];
-          mask &= mask - 1;
-          const uint32_t kind = (d.w >> 24) & 0xf;
-          // one element per row: every linear kind except the transposed image of a vertical unit,
-          // which folds the whole unit into the single row of its column
-          if (kind <= K_ADIAG && !(SYM && kind == K_VERT && (d.w & XD_TRANSPOSED))) {
-            // issue all RPT value / x loads of this unit before using them
-            double v[RPT], xv[RPT];
+          uint4 dd[BATCH];
+          int nd = 0;
 #pragma unroll
-            for (int k = 0; k < RPT; k++) {
-              uint32_t vi; int xi;
-              v[k] = 0.0; xv[k] = 0.0;
-              if (linear_probe<SYM>(d, P.ktab, grow0 + k * 32 + lane, vi, xi)) { v[k] = __ldg(values + vi); xv[k] = __ldg(x + xi); }
-            }
-#pragma unroll
-            for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
-          } else {
-#pragma unroll
-            for (int k = 0; k < RPT; k++) {
-              SpmvGatherOp op{values, x, 0.0};
-              gather_desc<SYM>(d, P.ktab, grow0 + k * 32 + lane, op);
-              acc[k] += op.acc;
-            }
-          }
+          for (int u = 0; u < BATCH; u++)
+            if (mask) { dd[u] = s_desc[w0 + __ffs(mask) - 1]; mask &= mask - 1; nd = u + 1; }
+          consume(dd, nd);
         }
       }
     }
+  } else if (warp_active) {
+    for (uint32_t base = b; base < e; base += 32) {
+      const uint32_t j = base + lane;
+      bool hit = false;
+      if (j < e) hit = desc_touches<false>(__ldg(P.xdesc + j), P.ktab, grow0, grow0 + 32 * RPT - 1);
+      uint32_t mask = __ballot_sync(FULL, hit);
+      while (mask) {
+        uint4 dd[BATCH];
+        int nd = 0;
+#pragma unroll
+        for (int u = 0; u < BATCH; u++)
+          if (mask) { dd[u] = __ldg(P.xdesc + base + __ffs(mask) - 1); mask &= mask - 1; nd = u + 1; }
+        consume(dd, nd);
+      }
+    }
   }
-
   if (warp_active) {
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
       const long long lrow = lrow0 + k * 32 + lane;
-      if (lrow < P.nrows) {
-        const long long g = P.row_start + lrow;
-        double a = acc[k];
-        if (SYM) {  // diagonal (CsxJit.hpp:373-394 new-row hook) + reduce of the local vector
-          a += __ldg(P.dvalues + lrow) * __ldg(x + g);
-          a += P.tbuf[g];
-          P.tbuf[g] = 0.0;
-        }
-        y[g] = overwrite ? alpha * a : alpha * a + beta * y[g];
-      }
+      if (lrow < P.nrows) y[P.row_start + lrow] = alpha * acc[k];
     }
   }
 }
@@ -693,21 +799,28 @@ int64_t csxb_traffic(const csxb_matrix_t *m, int what) {
 
 }  // extern "C"
 
-template <bool SYM, int RPT>
-static void launch_main_rpt(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
-                            int overwrite, cudaStream_t s) {
+template <bool SYM, int RPT, int KSET>
+static void launch_main_k(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
+                          int overwrite, cudaStream_t s) {
   dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
   // descriptors can also come from other partitions (transposed images under CSX-Sym)
   const bool has_xd = !pl.xdesc.empty();
-  if (pl.has_row_local && has_xd) csx_spmv_kernel<true, true, SYM, RPT><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM, RPT><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else csx_spmv_kernel<false, true, SYM, RPT><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  if (pl.has_row_local && has_xd) csx_spmv_kernel<true, true, SYM, RPT, KSET><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM, RPT, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else csx_spmv_kernel<false, true, SYM, RPT, KSET><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
 }
 template <bool SYM>
 static void launch_main(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
                         int overwrite, cudaStream_t s) {
-  if (pl.rpt == 4) launch_main_rpt<SYM, 4>(P, pl, x, y, alpha, beta, overwrite, s);
-  else launch_main_rpt<SYM, 1>(P, pl, x, y, alpha, beta, overwrite, s);
+  // kernels are pre-compiled per (tile shape, unit-kind set) — the counterpart of the per-partition JIT (CsxJit.hpp)
+  const bool diag1 = !SYM && pl.xd_diag1_only && !pl.xdesc.empty();
+  if (pl.rpt == 4) {
+    if (diag1) launch_main_k<SYM, 4, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
+    else launch_main_k<SYM, 4, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
+  } else {
+    if (diag1) launch_main_k<SYM, 1, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
+    else launch_main_k<SYM, 1, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
+  }
 }
 
 extern "C" {
@@ -752,6 +865,33 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
   if (hi > lo) CUDA_TRY(cudaMemcpyAsync(h_y + lo, m->d_y + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, 0));
   CUDA_TRY(cudaStreamSynchronize(0));
   if (cur != m->device && cur >= 0) CUDA_TRY(cudaSetDevice(cur));
+  return 0;
+}
+
+// Experimental phase-B variants for partitions made of linear cross-row units only (tuning aid, not API).
+int csxb_debug_variant(csxb_matrix_t *m, int variant, double alpha, const double *d_x, double *d_y, void *stream) {
+  if (!m->uploaded || m->pdev.size() != 1) return fail("debug variant needs one uploaded partition");
+  const PartLayout &pl = m->layout.parts[0];
+  if (pl.rpt != 4) return fail("debug variant needs a 4-rows-per-thread partition");  // row-local units are skipped
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
+  const PartDev &P = m->pdev[0];
+  switch (variant) {
+    case 0: csx_xd_exp_kernel<4, 1, 0, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 1: csx_xd_exp_kernel<4, 2, 0, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 2: csx_xd_exp_kernel<4, 1, 1, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 3: csx_xd_exp_kernel<4, 2, 1, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 4: csx_xd_exp_kernel<4, 2, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 5: csx_xd_exp_kernel<4, 3, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 6: csx_xd_exp_kernel<4, 4, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 7: csx_xd_exp_kernel<4, 2, 0, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 8: csx_xd_exp_kernel<4, 1, 1, false, 8><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 9: csx_xd_exp_kernel<4, 1, 1, false, 7><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 10: csx_xd_exp_kernel<4, 1, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    case 11: csx_xd_exp_kernel<4, 1, 1, true, 8><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
+    default: return fail("unknown variant");
+  }
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -211,7 +211,11 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     for (int64_t t = 0; t <= L.ntiles; t++) L.tile_xoff[t] |= cnt[q][t];
   }
   std::vector<std::vector<uint32_t>> fill(cnt);
-  for (const Pending &e : pend) out.parts[e.part].xdesc[fill[e.part][e.tile]++] = e.d;
+  for (const Pending &e : pend) {
+    out.parts[e.part].xdesc[fill[e.part][e.tile]++] = e.d;
+    if (((e.d.meta >> 24) & 0xf) != K_DIAG || !(e.d.meta & XD_DELTA1) || (e.d.meta & XD_TRANSPOSED))
+      out.parts[e.part].xd_diag1_only = false;
+  }
   return "";
 }
 

@@ -58,6 +58,7 @@ struct PartLayout {
   int64_t nrows = 0, row_start = 0, nnz = 0, ctl_size = 0;
   uint64_t val_base = 0, ctl_base = 0;   // offsets into the device-wide arrays
   bool has_row_local = false, has_cross = false;
+  bool xd_diag1_only = true;             // every descriptor of this partition's table is a direct diagonal unit of stride 1
   int64_t nseg = 0, ntiles = 0;
   int rpt = 1;                           // rows per thread (1 or 4): tile_rows = CTA_THREADS * rpt
   int64_t tile_rows() const { return (int64_t)CTA_THREADS * rpt; }
