@@ -338,12 +338,14 @@ __global__ void __launch_bounds__(CTA_THREADS, XD ? 8 : 4) csx_spmv_kernel(const
         if (KSET == KSET_DIAG1) {  // diag_tmpl.c with delta 1: y[r+k] += x[c+k] * v[k]
           const int t0 = grow0 + lane - (int)d.y;
           const uint32_t size = (d.w >> 16) & 0xff;
+          // one base pointer per stream; the RPT rows of this lane sit at fixed 256-byte strides from it
+          const double *__restrict__ vp = values + ((long long)d.x + t0);
+          const double *__restrict__ xp = x + ((long long)(int)d.z + t0);
           double v[RPT], xv[RPT];
 #pragma unroll
           for (int k = 0; k < RPT; k++) {
-            const int t = t0 + k * 32;
             v[k] = 0.0; xv[k] = 0.0;
-            if ((uint32_t)t < size) { v[k] = __ldg(values + d.x + t); xv[k] = __ldg(x + (int)d.z + t); }
+            if ((uint32_t)(t0 + k * 32) < size) { v[k] = __ldg(vp + k * 32); xv[k] = __ldg(xp + k * 32); }
           }
 #pragma unroll
           for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
