@@ -227,18 +227,35 @@ def main():
     rng = np.random.default_rng(2)
     x = torch.from_numpy(rng.uniform(-1, 1, n)).cuda()
     y = torch.zeros(n, dtype=torch.float64, device="cuda")
-    counts = None
+    exchange = None
+    xbuf = [x, y]   # ping-pong: the SpMV writes the own rows of the other buffer, the exchange fills the halo
     if world > 1:
-        info = torch.tensor([row_lo, row_n], dtype=torch.int64, device="cuda")
-        allinfo = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(allinfo, info)
-        counts = [(int(t[0]), int(t[1])) for t in allinfo]
-        xviews = [x[lo:lo + cnt] for lo, cnt in counts]
+        from sparsex_b200.dist import PieceExchange, WindowExchange, gather_row_ranges
+        L = sparsex_b200.lib()
+        ranges = gather_row_ranges(row_lo, row_n, "cuda")
+        win = torch.tensor([L.csxb_part_info(eng._h, 0, 11), L.csxb_part_info(eng._h, 0, 12)], dtype=torch.int64, device="cuda")
+        allwin = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(allwin, win)
+        windows = [(int(t[0]), int(t[1])) for t in allwin]
+        wx = WindowExchange(ranges, windows, rank)
+        frac = torch.tensor([wx.fraction], dtype=torch.float64, device="cuda")
+        dist.all_reduce(frac, op=dist.ReduceOp.MAX)
+        if float(frac[0]) < 0.5:
+            exchange, exchange_kind = wx, "halo exchange (grouped NCCL send/recv of the column windows, %.2g%% of the vector)" % (100 * float(frac[0]))
+        else:
+            pieces = [PieceExchange(xbuf[0], ranges), PieceExchange(xbuf[1], ranges)]
+            exchange_kind = "NCCL all-gather of the y pieces"
+    state = {"cur": 0}
 
     def step():
-        eng.spmv(alpha, x, y, overwrite=True)
-        if world > 1:  # x_{k+1} := y_k ; unequal piece sizes -> grouped broadcasts inside all_gather
-            dist.all_gather(xviews, y[row_lo:row_lo + row_n])
+        src, dst = xbuf[state["cur"]], xbuf[1 - state["cur"]]
+        eng.spmv(alpha, src, dst, overwrite=True)
+        if world > 1:
+            if exchange is not None:
+                exchange(dst)
+            else:  # dst's own rows -> every rank's dst
+                pieces[1 - state["cur"]](dst[row_lo:row_lo + row_n])
+            state["cur"] = 1 - state["cur"]
 
     def barrier():
         if world > 1:
@@ -255,11 +272,16 @@ def main():
     barrier()
     e0.record()
     for i in range(args.steps):
+        src, dst = xbuf[state["cur"]], xbuf[1 - state["cur"]]
         kev[i][0].record()
-        eng.spmv(alpha, x, y, overwrite=True)
+        eng.spmv(alpha, src, dst, overwrite=True)
         kev[i][1].record()
         if world > 1:
-            dist.all_gather(xviews, y[row_lo:row_lo + row_n])
+            if exchange is not None:
+                exchange(dst)
+            else:
+                pieces[1 - state["cur"]](dst[row_lo:row_lo + row_n])
+            state["cur"] = 1 - state["cur"]
     e1.record()
     barrier()
     clocks = sampler.finish()
@@ -294,6 +316,7 @@ def main():
            "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory)"}
     # check the device-resident result against the host-buffer path on the same x
     x.copy_(xh, non_blocking=False)
+    y.zero_()
     eng.spmv(alpha, x, y, overwrite=True)
     torch.cuda.synchronize()
     dev = y[row_lo:row_lo + row_n].cpu().numpy()
@@ -309,7 +332,7 @@ def main():
                 "config": {"workload": name, "rows": n, "nnz": nnz, "options": {k: str(v) for k, v in all_opts.items()},
                            "encoding_rank0": enc_log.strip(), "alpha": alpha,
                            "step": "y = alpha*A*x (spx_matvec_mult semantics)" + (
-                               "; then NCCL all-gather of the y pieces into x" if world > 1 else ""),
+                               "; then " + exchange_kind + " into the next x" if world > 1 else ""),
                            "l2_policy": "inputs larger than L2: %.0f MB of values+ctl per GPU vs 126 MB L2" % (
                                (traffic["values"] + traffic["ctl"]) / 1e6),
                            "tune_s": round(tune_s, 2), "generate_s": round(gen_s, 2),

@@ -53,7 +53,8 @@ int64_t csxb_info(const csxb_matrix_t *m, int what);
  * (0 .. CSXB_NPARTS-1).  Used by spx_mat_get_partition and by the parity tests. */
 enum { CSXB_P_NNZ = 0, CSXB_P_NROWS = 1, CSXB_P_NCOLS = 2, CSXB_P_ROW_START = 3, CSXB_P_CTL_SIZE = 4,
        CSXB_P_ROW_JUMPS = 5, CSXB_P_ID_MAP_LEN = 6, CSXB_P_MAP_LEN = 7, CSXB_P_DVALUES_LEN = 8,
-       CSXB_P_ROWS_INFO_LEN = 9, CSXB_P_SAMPLING_UNDEFINED = 10 };
+       CSXB_P_ROWS_INFO_LEN = 9, CSXB_P_SAMPLING_UNDEFINED = 10,
+       CSXB_P_COL_MIN = 11, CSXB_P_COL_MAX = 12 /* zero-based column window the partition reads */ };
 int64_t csxb_part_info(const csxb_matrix_t *m, int part, int what);
 /* what: values f64[nnz] | ctl u8[ctl_size] | id_map i64[len] | rows_info {i64 rowptr,i64 valptr,i32 span,i32 pad}[nrows]
  *       | dvalues f64 | map_cpus u32 | map_pos u32 */

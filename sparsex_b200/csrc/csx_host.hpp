@@ -58,6 +58,7 @@ struct CsxPartition {
   std::vector<uint8_t> ctl;
   int64_t nnz = 0, nrows = 0, ncols = 0, row_start = 0;
   bool row_jumps = false;
+  int64_t col_min = 0, col_max = -1;   // zero-based column window the partition reads (empty: min > max)
   std::vector<long> id_map;            // unit id -> pattern id, terminated by -1
   std::vector<RowInfo64> rows_info;    // optional (build_rows_info)
   std::vector<double> dvalues;         // CSX-Sym: diagonal of the partition's rows

@@ -15,6 +15,7 @@
 //   CSX-Sym              SparsePartition.hpp:965-1074, CsxBuild.hpp:204-288, 400-581
 // Non-NUMA semantics (SPX_USE_NUMA == 0) throughout.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -856,7 +857,7 @@ struct Cursor {
 
 // SparsePartition::SetElems (:508-541) / SparsePartitionSym::SetElems (:1087-1129).
 // `keep == false` only advances the cursor (partition not owned by this process).
-struct SplitResult { int64_t taken = 0; int64_t rows = 0; int64_t diag = 0; };
+struct SplitResult { int64_t taken = 0; int64_t rows = 0; int64_t diag = 0; int32_t cmin = INT32_MAX, cmax = 0; };
 SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sym, bool keep, Part &p,
                            std::vector<double> &pool, std::vector<double> &diag) {
   SplitResult res;
@@ -879,6 +880,7 @@ SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sy
       p.e.push_back(Rec{row, col, 0, 0, 1, 0, (uint64_t)pool.size()});
       pool.push_back(cur.v());
     }
+    res.cmin = std::min(res.cmin, col); res.cmax = std::max(res.cmax, col);
     last_row = row;
     cnt++;
   }
@@ -998,6 +1000,10 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
       parts[i].nr_cols = ncols;
       SplitResult r = take_partition(cur, row_start, limit, sym, keep, parts[i], pools[i], diags[i]);
       if (!keep) { parts[i].row_start = row_start; parts[i].nr_rows = r.rows; }
+      if (i >= part_lo && i < part_hi && r.cmax >= r.cmin) {
+        out.parts[i - part_lo].col_min = r.cmin - 1;
+        out.parts[i - part_lo].col_max = r.cmax - 1;
+      }
       row_start += r.rows;
       done += (uint64_t)r.taken;
     }

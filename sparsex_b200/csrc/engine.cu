@@ -666,6 +666,8 @@ int64_t csxb_part_info(const csxb_matrix_t *m, int part, int what) {
     case CSXB_P_DVALUES_LEN: return (int64_t)p.dvalues.size();
     case CSXB_P_ROWS_INFO_LEN: return (int64_t)p.rows_info.size();
     case CSXB_P_SAMPLING_UNDEFINED: return p.sampling_undefined;
+    case CSXB_P_COL_MIN: return p.col_min;
+    case CSXB_P_COL_MAX: return p.col_max;
   }
   return -1;
 }
@@ -786,9 +788,14 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
   m->bytes[CSXB_B_VALUES] = nnz_stored * 8;
   m->bytes[CSXB_B_CTL] = ctl_bytes;
   m->bytes[CSXB_B_TABLES] = tables;
-  m->bytes[CSXB_B_X] = H.ncols * 8;
+  // x: the column window the local partitions read (the whole vector when every partition is local)
+  int64_t cmin = H.ncols, cmax = -1;
+  for (auto &p : H.parts) if (p.col_max >= p.col_min) { cmin = std::min(cmin, p.col_min); cmax = std::max(cmax, p.col_max); }
+  int64_t xcols = (int)H.parts.size() == H.nparts_total ? H.ncols : std::max<int64_t>(0, cmax - cmin + 1);
+  if (H.symmetric) xcols = H.ncols;
+  m->bytes[CSXB_B_X] = xcols * 8;
   m->bytes[CSXB_B_Y] = rows_owned * 8;
-  m->bytes[CSXB_B_TOTAL] = nnz_stored * 8 + ctl_bytes + tables + H.ncols * 8 + rows_owned * 8;
+  m->bytes[CSXB_B_TOTAL] = nnz_stored * 8 + ctl_bytes + tables + xcols * 8 + rows_owned * 8;
   m->bytes[CSXB_B_LAUNCHES] = launches;
   m->uploaded = true;
   return 0;

@@ -49,3 +49,43 @@ class PieceExchange(object):
         for v, r, (_, cnt) in zip(self.views, self.recv, self.ranges):
             v.copy_(r[:cnt])
         return self.x
+
+
+class WindowExchange(object):
+    """Sends every rank only the part of the other ranks' y pieces that its rows read.
+
+    window[r] = (first, last) zero-based column the partition of rank r touches (CSXB_P_COL_MIN/MAX).  For
+    banded matrices this is a halo of a few thousand elements per neighbour instead of the whole vector; when
+    a window covers (almost) everything the plain all-gather of PieceExchange is used.  All sends and receives
+    of a step go out as one grouped NCCL launch (batch_isend_irecv).
+    """
+
+    def __init__(self, ranges, windows, rank):
+        self.rank, self.plan_send, self.plan_recv = rank, [], []
+        world = len(ranges)
+        need = 0
+        for q in range(world):          # owner
+            qlo, qn = ranges[q]
+            for r in range(world):      # reader
+                if q == r or qn == 0:
+                    continue
+                wlo, whi = windows[r]
+                lo, hi = max(qlo, wlo), min(qlo + qn, whi + 1)
+                if hi <= lo:
+                    continue
+                if q == rank:
+                    self.plan_send.append((r, lo, hi))
+                if r == rank:
+                    self.plan_recv.append((q, lo, hi))
+                    need += hi - lo
+        total_other = sum(n for i, (_, n) in enumerate(ranges) if i != rank)
+        self.fraction = need / max(total_other, 1)
+
+    def __call__(self, buf):
+        """buf: full-length vector whose own rows were just written by the local SpMV."""
+        ops = [dist.P2POp(dist.isend, buf[lo:hi], peer) for peer, lo, hi in self.plan_send]
+        ops += [dist.P2POp(dist.irecv, buf[lo:hi], peer) for peer, lo, hi in self.plan_recv]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return buf
