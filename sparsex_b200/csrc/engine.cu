@@ -1,19 +1,16 @@
 // CUDA kernels (sm_100a) and the csxb_* C-ABI of the B200 CSX SpMV engine.
 //
-// Execution model (see gpu_layout.hpp for the tables):
-//   grid  = one CTA per 256-row tile of a partition, 8 warps, no CTA-wide sync;
-//   warp  = one 32-row segment, lane L owns row 32*seg + L for the whole kernel:
-//     phase A  walk the ctl bytes of the units that start in the segment; unit
-//              heads and varints are decoded redundantly by all lanes from an
-//              8-byte register window, delta bodies are loaded one element per
-//              lane and turned into columns with a warp prefix sum; row-local
-//              units (delta8/16/32/64, horizontal) are multiplied here and
-//              folded into the owning lane with a shuffle reduction per row;
-//     phase B  every lane gathers the contributions of the cross-row units
-//              (vertical, diagonal, anti-diagonal, block) listed for its tile;
-//     epilogue y = alpha*acc + beta*y, one coalesced 256-byte store per warp.
-// SpMV is HBM-bound fp64 work: no tensor cores, no atomics on the main path,
-// every value and ctl byte is read once, y is written once.
+// Execution model (see gpu_layout.hpp for the tables), two kernels per SpMV on one stream:
+//   1. csx_spmv_kernel   one CTA per tile of 256 / 1024 rows; every thread owns rows and gathers the
+//                        contributions of the long cross-row units (vertical, diagonal, anti-diagonal)
+//                        listed for its tile, then writes y = alpha*acc + beta*y once per row.
+//                        No atomics, deterministic, streams values with coalesced loads.
+//   2. csx_chunk_kernel  one warp per chunk of the ctl stream: unit heads and varints are parsed from a
+//                        shared-memory copy of the chunk, delta bodies are turned into columns with a
+//                        segmented warp prefix sum, block / short substructure elements get their
+//                        coordinates from the unit geometry; rows are reduced with segmented shuffle
+//                        reductions and added to y with fp64 red operations.
+// SpMV is HBM-bound fp64 work: no tensor cores; every value and ctl byte is read once.
 //
 // Reference semantics reproduced: src/templates/csx_spmv_tmpl.c:66-101 and the
 // nine unit templates (delta/horiz/vert/diag/rdiag/block_row/block_col), the
@@ -37,15 +34,14 @@ using namespace spxb;
 struct PartDev {
   const uint8_t *ctl;          // this partition's ctl bytes (16-byte aligned, CTL_PAD readable bytes behind)
   const double *values;        // device-wide values array
-  const uint64_t *seg_ctl;
-  const uint32_t *seg_val;
+  const ChunkEntry *chunks;    // chunk kernel entry points
   const uint32_t *tile_xoff;
   const uint4 *xdesc;
   const KindEntry *ktab;
   const double *dvalues;       // CSX-Sym: diagonal of the owned rows
-  double *tbuf;                // CSX-Sym: transposed contributions of row-local units, zero between calls
   long long nrows, row_start;  // owned rows
   uint32_t val_base;
+  uint32_t nchunks;
   int full_colind;
   int rpt;                     // rows per thread: a tile has CTA_THREADS * rpt rows
   KindEntry idtab[64];
@@ -53,113 +49,10 @@ struct PartDev {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// 8-byte register window over the ctl stream; every lane of the warp holds the
-// same state (uniform control flow), loads are warp-broadcast.
-struct CtlReader {
-  const uint8_t *base;
-  uint64_t pos;
-  uint64_t w;
-  int avail;
-  __device__ __forceinline__ CtlReader(const uint8_t *b, uint64_t p) : base(b), pos(p), w(0), avail(0) {}
-  __device__ __forceinline__ uint32_t byte() {
-    if (avail == 0) {
-      uint64_t a = __ldg(reinterpret_cast<const unsigned long long *>(base + (pos & ~7ull)));
-      unsigned sh = (unsigned)(pos & 7);
-      w = a >> (8 * sh);
-      avail = 8 - (int)sh;
-    }
-    uint32_t b = (uint32_t)(w & 0xff);
-    w >>= 8; avail--; pos++;
-    return b;
-  }
-  __device__ __forceinline__ uint64_t varint() {  // CtlUtil.hpp:110-133
-    uint64_t v = 0;
-    unsigned shift = 0;
-    for (;;) {
-      uint32_t b = byte();
-      v |= (uint64_t)(b & 0x7f) << shift;
-      if (!(b & 0x80)) break;
-      shift += 7;
-    }
-    return v;
-  }
-  __device__ __forceinline__ uint32_t u32() { uint32_t v = byte(); v |= byte() << 8; v |= byte() << 16; v |= byte() << 24; return v; }
-  __device__ __forceinline__ void skip(uint64_t n) { pos += n; avail = 0; }
-};
-
-// low 32 bits of the little-endian fixed-width delta at byte address a
-__device__ __forceinline__ uint32_t load_delta(const uint8_t *ctl, uint64_t a, uint32_t w, bool aligned) {
-  if (w == 1) return __ldg(ctl + a);
-  if (aligned) {
-    if (w == 2) return __ldg(reinterpret_cast<const unsigned short *>(ctl + a));
-    return __ldg(reinterpret_cast<const unsigned int *>(ctl + a));  // w == 4 or low half of w == 8
-  }
-  uint32_t v = __ldg(ctl + a) | ((uint32_t)__ldg(ctl + a + 1) << 8);
-  if (w > 2) v |= ((uint32_t)__ldg(ctl + a + 2) << 16) | ((uint32_t)__ldg(ctl + a + 3) << 24);
-  return v;
-}
-
-__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(FULL, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
-}
-
-// Phase A.  Op::elem(value index within the partition, row within the segment, column)
-// is called by the lane that owns the element, Op::row_done(row) by all lanes.
-template <class Op>
-__device__ __forceinline__ void walk_segment(const PartDev &P, long long seg, int lane, Op &op) {
-  uint64_t e0 = __ldg(reinterpret_cast<const unsigned long long *>(P.seg_ctl + seg));
-  uint64_t e1 = __ldg(reinterpret_cast<const unsigned long long *>(P.seg_ctl + seg + 1));
-  const uint64_t OFF = (1ull << 56) - 1;
-  uint64_t pend = e1 & OFF;
-  if ((e0 & OFF) >= pend) return;
-  int row = (int)(e0 >> 56);
-  uint32_t v = __ldg(P.seg_val + seg);
-  uint32_t col = 0;
-  bool first = true;
-  CtlReader rd(P.ctl, e0 & OFF);
-  while (rd.pos < pend) {
-    uint32_t flags = rd.byte(), size = rd.byte();
-    if (flags & 0x80) {  // new row (csx_spmv_tmpl.c:86-91); the entry unit's row comes from the table
-      uint32_t jmp = 1;
-      if (flags & 0x40) jmp = (uint32_t)rd.varint();
-      if (!first) { op.row_done(row); row += (int)jmp; }
-      col = 0;
-    }
-    first = false;
-    if (P.full_colind) col = rd.u32(); else col += (uint32_t)rd.varint();  // modulo 2^32 == modulo 2^64 truncated
-    KindEntry ke = P.idtab[flags & 0x3f];
-    uint32_t kind = ke.kind_align & 0xff, delta = ke.delta;
-    if (kind <= K_DELTA64) {  // delta_tmpl.c:20-37
-      uint64_t pb = rd.pos;
-      uint32_t wl = delta > 4 ? 4 : delta;
-      bool aligned = ((reinterpret_cast<uintptr_t>(P.ctl) + pb) & (wl - 1)) == 0;
-      for (uint32_t base = 0; base < size; base += 32) {
-        uint32_t j = base + lane;
-        uint32_t d = 0;
-        if (j < size && j > 0) d = load_delta(P.ctl, pb + (uint64_t)(j - 1) * delta, delta, aligned);
-        uint32_t mycol = col + warp_scan_incl(d, lane);
-        if (j < size) op.elem(v + j, row, mycol);
-        col = __shfl_sync(FULL, mycol, 31);
-      }
-      rd.skip((uint64_t)(size - 1) * delta);
-    } else if (kind == K_HORIZ) {  // horiz_tmpl.c:20-37
-      for (uint32_t j = lane; j < size; j += 32) op.elem(v + j, row, col + j * delta);
-      col += (size - 1) * delta;
-    }
-    // cross-row units leave the cursor on their first element (Element.hpp:657-666)
-    v += size;
-  }
-  op.row_done(row);
 }
 
 // Phase B.  Op::add(device-wide value index, x index) for every element of
@@ -265,18 +158,6 @@ __device__ __forceinline__ bool linear_probe(const uint4 d, const KindEntry *__r
   return true;
 }
 
-struct SpmvWalkOp {
-  const double *__restrict__ values;  // partition base applied
-  const double *__restrict__ x;
-  double part, acc;
-  int lane;
-  __device__ __forceinline__ void elem(uint32_t vi, int, uint32_t col) { part += __ldg(values + vi) * __ldg(x + col); }
-  __device__ __forceinline__ void row_done(int row) {
-    double s = warp_sum(part);
-    if (lane == row) acc += s;
-    part = 0;
-  }
-};
 struct SpmvGatherOp {
   const double *__restrict__ values;  // device-wide
   const double *__restrict__ x;
@@ -284,41 +165,31 @@ struct SpmvGatherOp {
   __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * __ldg(x + xi); }
 };
 
-// One CTA = one tile of CTA_THREADS * RPT rows; warp w owns RPT consecutive 32-row segments and lane L
-// owns rows  tile0 + (w*RPT + k)*32 + L,  k < RPT  (RPT independent accumulators per thread).  Warps never
-// synchronise with each other.  KSET specialises phase B for the set of unit kinds the partition's table holds:
-//   KSET_ANY    every cross-row kind, CSX-Sym images included
+// ---- kernel 1: gather over the cross-row unit table + y initialisation --------------------------
+// One CTA = one tile of CTA_THREADS * RPT rows; warp w owns RPT consecutive 32-row groups and lane L owns
+// rows  tile0 + (w*RPT + k)*32 + L,  k < RPT  (RPT independent accumulators per thread).  Warps never
+// synchronise with each other.  Every owned row of y is written exactly once here
+// (y = alpha*acc + beta*y); the chunk kernel adds the remaining units afterwards.
+// KSET specialises the gather for the set of unit kinds the partition's table holds:
+//   KSET_ANY    vertical / diagonal / anti-diagonal units of any stride, CSX-Sym images included
 //   KSET_DIAG1  only diagonal units of stride 1 (what the stencil matrices of the baseline configs encode to)
-// The kernel is bandwidth-bound and latency-sensitive: it is compiled for 8 resident CTAs per SM (32 registers).
+// The kernel is bandwidth-bound and latency-sensitive: compiled for 8 resident CTAs per SM (32 registers).
 enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
-template <bool WALK, bool XD, bool SYM, int RPT, int KSET>
-__global__ void __launch_bounds__(CTA_THREADS, XD ? 8 : 4) csx_spmv_kernel(const __grid_constant__ PartDev P,
-                                                                           const double *__restrict__ x,
-                                                                           double *__restrict__ y, double alpha,
-                                                                           double beta, int overwrite) {
+template <bool XD, bool SYM, int RPT, int KSET>
+__global__ void __launch_bounds__(CTA_THREADS, 8) csx_spmv_kernel(const __grid_constant__ PartDev P,
+                                                                  const double *__restrict__ x,
+                                                                  double *__restrict__ y, double alpha, double beta,
+                                                                  int overwrite) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = blockIdx.x;
-  const long long seg0 = (tile * (CTA_THREADS / SEG_ROWS) + warp) * RPT;
-  const long long lrow0 = seg0 * SEG_ROWS;             // first row of this warp (partition relative)
+  const long long lrow0 = ((tile * (CTA_THREADS / 32) + warp) * RPT) * 32;   // first row of this warp (partition relative)
   if (lrow0 >= P.nrows) return;
-  const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
   double acc[RPT];
 #pragma unroll
   for (int k = 0; k < RPT; k++) acc[k] = 0.0;
 
-  if (WALK && (tx0 & 0x80000000u)) {
-#pragma unroll
-    for (int k = 0; k < RPT; k++) {
-      if ((seg0 + k) * SEG_ROWS < P.nrows) {
-        SpmvWalkOp op{P.values + P.val_base, x, 0.0, 0.0, lane};
-        walk_segment(P, seg0 + k, lane, op);
-        acc[k] += op.acc;
-      }
-    }
-  }
-
   if (XD) {
-    const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
+    const uint32_t b = __ldg(P.tile_xoff + tile), e = __ldg(P.tile_xoff + tile + 1);
     const int grow0 = (int)(P.row_start + lrow0);       // global rows of this warp: [grow0, grow0 + 32*RPT)
     const double *__restrict__ values = P.values;
     // each lane inspects one descriptor of the tile; the ones that reach this warp's rows are
@@ -351,10 +222,9 @@ __global__ void __launch_bounds__(CTA_THREADS, XD ? 8 : 4) csx_spmv_kernel(const
           for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
           continue;
         }
-        const uint32_t kind = (d.w >> 24) & 0xf;
-        // one element per row: every linear kind except the transposed image of a vertical unit,
-        // which folds the whole unit into the single row of its column
-        if (kind <= K_ADIAG && !(SYM && kind == K_VERT && (d.w & XD_TRANSPOSED))) {
+        // one element per row, except the transposed image of a vertical unit, which folds the whole
+        // unit into the single row of its column
+        if (!(SYM && ((d.w >> 24) & 0xf) == K_VERT && (d.w & XD_TRANSPOSED))) {
           double v[RPT], xv[RPT];  // issue all RPT value / x loads of this unit before using them
 #pragma unroll
           for (int k = 0; k < RPT; k++) {
@@ -382,159 +252,218 @@ __global__ void __launch_bounds__(CTA_THREADS, XD ? 8 : 4) csx_spmv_kernel(const
     if (lrow < P.nrows) {
       const long long g = P.row_start + lrow;
       double a = acc[k];
-      if (SYM) {  // diagonal (CsxJit.hpp:373-394 new-row hook) + reduce of the local vector
-        a += __ldg(P.dvalues + lrow) * __ldg(x + g);
-        a += P.tbuf[g];
-        P.tbuf[g] = 0.0;
-      }
+      if (SYM) a += __ldg(P.dvalues + lrow) * __ldg(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
       y[g] = overwrite ? alpha * a : alpha * a + beta * y[g];
     }
   }
 }
 
-// ---- experimental variants of phase B (selected with csxb_debug_variant; used to tune the shipped kernel) ----
-__device__ __forceinline__ double ld_stream_f64(const double *p) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+// ---- kernel 2: chunk kernel ------------------------------------------------------------------------
+// One warp = one chunk of the ctl stream (gpu_layout.hpp).  Handles every unit that is not in the table:
+// delta8/16/32/64 and horizontal units (delta_tmpl.c, horiz_tmpl.c), block-row / block-column units
+// (block_row_tmpl.c, block_col_tmpl.c) and short vertical / diagonal / anti-diagonal units, plus their
+// CSX-Sym transposed updates (*_sym_tmpl.c).  Runs after kernel 1 on the same stream and adds into y.
+constexpr int CHUNK_WARPS = 4;
+struct ChunkSmem {
+  uint4 raw[(CHUNK_MAX_BYTES + 32) / 16];   // staged ctl bytes (16-byte aligned copy window)
+  uint4 units[CHUNK_MAX_UNITS];             // parsed unit heads
+  uint8_t map[CHUNK_MAX_ELEMS];             // element -> unit
+};
+
+__device__ __forceinline__ uint64_t smem_varint(const uint8_t *c, uint32_t &pos) {  // CtlUtil.hpp:110-133
+  uint64_t v = 0;
+  unsigned shift = 0;
+  for (;;) {
+    uint32_t b = c[pos++];
+    v |= (uint64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) break;
+    shift += 7;
+  }
   return v;
 }
-template <int RPT, int BATCH, int STAGE, bool NOALLOC, int MINB = 1>
-__global__ void __launch_bounds__(CTA_THREADS, MINB) csx_xd_exp_kernel(const __grid_constant__ PartDev P,
-                                                                 const double *__restrict__ x, double *__restrict__ y,
-                                                                 double alpha) {
-  __shared__ uint4 s_desc[STAGE == 0 ? CTA_THREADS : 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = blockIdx.x;
-  const long long seg0 = (tile * (CTA_THREADS / SEG_ROWS) + warp) * RPT;
-  const long long lrow0 = seg0 * SEG_ROWS;
-  const bool warp_active = lrow0 < P.nrows;
-  const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
-  const uint32_t b = tx0 & 0x7fffffffu, e = tx1 & 0x7fffffffu;
-  const int grow0 = (int)(P.row_start + lrow0);
-  const double *__restrict__ values = P.values;
-  double acc[RPT];
-#pragma unroll
-  for (int k = 0; k < RPT; k++) acc[k] = 0.0;
 
-  auto consume = [&](const uint4 *dd, int nd) {
-    double v[BATCH][RPT], xv[BATCH][RPT];
-#pragma unroll
-    for (int u = 0; u < BATCH; u++) {
-#pragma unroll
-      for (int k = 0; k < RPT; k++) {
-        uint32_t vi; int xi;
-        v[u][k] = 0.0; xv[u][k] = 0.0;
-        if (u < nd && linear_probe<false>(dd[u], P.ktab, grow0 + k * 32 + lane, vi, xi)) {
-          v[u][k] = NOALLOC ? ld_stream_f64(values + vi) : __ldg(values + vi);
-          xv[u][k] = __ldg(x + xi);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < BATCH; u++)
-#pragma unroll
-      for (int k = 0; k < RPT; k++) acc[k] += v[u][k] * xv[u][k];
-  };
+// F::round(active, value index within the partition, partition-relative row, column) is called by all lanes
+// once per 32 elements (warp-uniform), F::finish() once at the end.
+template <class F>
+__device__ __forceinline__ void process_chunk(const PartDev &P, const ChunkEntry ce, ChunkSmem &S, int lane, F &f) {
+  // 1. stage the chunk's ctl bytes: 16-byte coalesced copies of the aligned window that contains them
+  const uint8_t *g = P.ctl + ce.ctl_off;
+  const uint32_t nbytes = ce.pad;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+  const uint4 *src = reinterpret_cast<const uint4 *>(g - mis);
+  for (uint32_t i = lane; i * 16 < mis + nbytes; i += 32) S.raw[i] = __ldg(src + i);
+  __syncwarp();
+  const uint8_t *c = reinterpret_cast<const uint8_t *>(S.raw) + mis;
 
-  if (STAGE == 0) {
-    for (uint32_t base = b; base < e; base += CTA_THREADS) {
-      const uint32_t n = min((uint32_t)CTA_THREADS, e - base);
-      if (base != b) __syncthreads();
-      if (threadIdx.x < n) s_desc[threadIdx.x] = __ldg(P.xdesc + base + threadIdx.x);
-      __syncthreads();
-      if (!warp_active) continue;
-      for (uint32_t w0 = 0; w0 < n; w0 += 32) {
-        const uint32_t j = w0 + lane;
-        bool hit = false;
-        if (j < n) hit = desc_touches<false>(s_desc[j], P.ktab, grow0, grow0 + 32 * RPT - 1);
-        uint32_t mask = __ballot_sync(FULL, hit);
-        while (mask) {
-          uint4 dd[BATCH];
-          int nd = 0;
-#pragma unroll
-          for (int u = 0; u < BATCH; u++)
-            if (mask) { dd[u] = s_desc[w0 + __ffs(mask) - 1]; mask &= mask - 1; nd = u + 1; }
-          consume(dd, nd);
-        }
-      }
+  // 2. parse the unit heads (every lane runs the same scalar code; lane 0 records)
+  uint32_t pos = 0, ne = 0, nu = 0;
+  int row = ce.row;
+  bool firstu = true;
+  while (pos < nbytes) {
+    const uint32_t flags = c[pos], size = c[pos + 1];
+    pos += 2;
+    const bool nr = (flags & 0x80) != 0;
+    if (nr) {  // csx_spmv_tmpl.c:86-91; the entry unit's row comes from the table
+      uint32_t jmp = 1;
+      if (flags & 0x40) jmp = (uint32_t)smem_varint(c, pos);
+      if (!firstu) row += (int)jmp;
     }
-  } else if (warp_active) {
-    for (uint32_t base = b; base < e; base += 32) {
-      const uint32_t j = base + lane;
-      bool hit = false;
-      if (j < e) hit = desc_touches<false>(__ldg(P.xdesc + j), P.ktab, grow0, grow0 + 32 * RPT - 1);
-      uint32_t mask = __ballot_sync(FULL, hit);
-      while (mask) {
-        uint4 dd[BATCH];
-        int nd = 0;
-#pragma unroll
-        for (int u = 0; u < BATCH; u++)
-          if (mask) { dd[u] = __ldg(P.xdesc + base + __ffs(mask) - 1); mask &= mask - 1; nd = u + 1; }
-        consume(dd, nd);
-      }
-    }
+    uint32_t ucol;
+    if (P.full_colind) { ucol = c[pos] | (c[pos + 1] << 8) | (c[pos + 2] << 16) | ((uint32_t)c[pos + 3] << 24); pos += 4; }
+    else ucol = (uint32_t)smem_varint(c, pos);   // modulo 2^32 == modulo 2^64 truncated (negative ucol)
+    const KindEntry ke = P.idtab[flags & 0x3f];
+    const uint32_t kind = ke.kind_align & 0xff, align = (ke.kind_align >> 8) & 0xff;
+    const bool reset = firstu || nr || P.full_colind;    // column cursor restarts at this unit
+    const uint32_t inc0 = (firstu && !P.full_colind) ? ce.cursor + ucol : ucol;
+    if (lane == 0)
+      S.units[nu] = make_uint4(ne | (size << 11) | (kind << 19) | ((uint32_t)reset << 23) | (align << 24),
+                               pos | (ke.delta << 12), inc0, (uint32_t)row);
+    for (uint32_t k = lane; k < size; k += 32) S.map[ne + k] = (uint8_t)nu;
+    if (kind <= K_DELTA64) pos += (size - 1) * ke.delta;
+    ne += size; nu++;
+    firstu = false;
   }
-  if (warp_active) {
-#pragma unroll
-    for (int k = 0; k < RPT; k++) {
-      const long long lrow = lrow0 + k * 32 + lane;
-      if (lrow < P.nrows) y[P.row_start + lrow] = alpha * acc[k];
+  __syncwarp();
+
+  // 3. decode 32 elements per round
+  uint32_t carry = 0;
+  for (uint32_t e0 = 0; e0 < ne; e0 += 32) {
+    const uint32_t idx = e0 + lane;
+    const bool active = idx < ne;
+    uint32_t inc = 0, flag = 1, kind = 0, delta = 0, align = 0, j = 0;
+    int row_e = -1;
+    if (active) {
+      const uint4 u = S.units[S.map[idx]];
+      j = idx - (u.x & 0x7ff);
+      kind = (u.x >> 19) & 0xf; align = (u.x >> 24) & 0xf;
+      delta = u.y >> 12;
+      row_e = (int)u.w;
+      flag = 0;
+      if (j == 0) { inc = u.z; flag = (u.x >> 23) & 1; }
+      else if (kind <= K_DELTA64) {   // little-endian fixed-width delta; low 32 bits suffice
+        const uint8_t *b = c + (u.y & 0xfff) + (j - 1) * delta;
+        inc = b[0];
+        if (delta >= 2) inc |= (uint32_t)b[1] << 8;
+        if (delta >= 4) inc |= ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+      } else if (kind == K_HORIZ) inc = delta;
     }
+    // segmented inclusive prefix sum of the cursor increments (segments start where the cursor restarts)
+    uint32_t cur = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t tv = __shfl_up_sync(FULL, cur, o), tf = __shfl_up_sync(FULL, flag, o);
+      if (lane >= o) { if (!flag) cur += tv; flag |= tf; }
+    }
+    if (!flag) cur += carry;
+    carry = __shfl_sync(FULL, cur, 31);
+    // element coordinates from the unit geometry (cursor = unit start for substructures)
+    uint32_t col_e = cur;
+    if (kind == K_VERT) row_e += (int)(j * delta);
+    else if (kind == K_DIAG) { row_e += (int)(j * delta); col_e += j * delta; }
+    else if (kind == K_ADIAG) { row_e += (int)(j * delta); col_e -= j * delta; }
+    else if (kind == K_BROW) { row_e += (int)(j % align); col_e += j / align; }   // column-major values
+    else if (kind == K_BCOL) { row_e += (int)(j / align); col_e += j % align; }   // row-major values
+    f.round(active, ce.val_off + idx, row_e, col_e);
   }
+  f.finish();
 }
 
-// CSX-Sym, first phase: transposed contributions of the row-local units
-// (delta_sym_tmpl.c / horiz_sym_tmpl.c: cur[col] += x[row] * v) go to the local
-// vector tbuf with fp64 reductions; the main kernel folds tbuf into y.
-struct SymScatterOp {
-  const double *__restrict__ values;
+template <bool SYM>
+struct SpmvChunkOp {
+  const double *__restrict__ values;  // partition base applied
   const double *__restrict__ x;
-  double *tbuf;
-  long long row0;  // global row of the segment's first row
-  __device__ __forceinline__ void elem(uint32_t vi, int row, uint32_t col) {
-    atomicAdd(tbuf + col, __ldg(values + vi) * __ldg(x + row0 + row));
+  double *__restrict__ y;
+  long long row_start;
+  double alpha;
+  int lane;
+  int run_row;      // row whose products are being accumulated lane-wise (-1: none)
+  double run_acc;
+  __device__ __forceinline__ void flush() {
+    if (run_row >= 0) {
+      const double s = warp_sum(run_acc);
+      if (lane == 0) atomicAdd(y + row_start + run_row, alpha * s);
+    }
+    run_row = -1; run_acc = 0.0;
   }
-  __device__ __forceinline__ void row_done(int) {}
+  __device__ __forceinline__ void round(bool active, uint32_t vi, int row, uint32_t col) {
+    double p = 0.0;
+    if (active) {
+      const double v = __ldg(values + vi);
+      p = v * __ldg(x + col);
+      if (SYM) atomicAdd(y + col, alpha * v * __ldg(x + row_start + row));   // transposed update
+    }
+    // whole round in one row (long rows): keep lane-wise partial sums, reduce once per row
+    const int row0 = __shfl_sync(FULL, row, 0);
+    if (__all_sync(FULL, row == row0)) {
+      if (row0 != run_row) { flush(); run_row = row0; }
+      run_acc += p;
+      return;
+    }
+    flush();
+    // segmented sum over runs of equal rows; the last lane of a run adds it to y
+    const int prev = __shfl_up_sync(FULL, row, 1), next = __shfl_down_sync(FULL, row, 1);
+    uint32_t flag = (lane == 0) || (prev != row);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tv = __shfl_up_sync(FULL, p, o);
+      const uint32_t tf = __shfl_up_sync(FULL, flag, o);
+      if (lane >= o) { if (!flag) p += tv; flag |= tf; }
+    }
+    if (active && (lane == 31 || next != row)) atomicAdd(y + row_start + row, alpha * p);
+  }
+  __device__ __forceinline__ void finish() { flush(); }
 };
-__global__ void __launch_bounds__(CTA_THREADS) csx_sym_scatter_kernel(const __grid_constant__ PartDev P,
-                                                                      const double *__restrict__ x) {
+
+template <bool SYM>
+__global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_chunk_kernel(const __grid_constant__ PartDev P,
+                                                                     const double *__restrict__ x,
+                                                                     double *__restrict__ y, double alpha) {
+  __shared__ ChunkSmem smem[CHUNK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = blockIdx.x;
-  if (!(__ldg(P.tile_xoff + tile) & 0x80000000u)) return;
-  for (int k = 0; k < P.rpt; k++) {
-    const long long seg = (tile * (CTA_THREADS / SEG_ROWS) + warp) * P.rpt + k;
-    if (seg * SEG_ROWS >= P.nrows) return;
-    SymScatterOp op{P.values + P.val_base, x, P.tbuf, P.row_start + seg * SEG_ROWS};
-    walk_segment(P, seg, lane, op);
-  }
+  const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
+  if (ch >= P.nchunks) return;
+  const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(P.chunks + ch));
+  const unsigned long long b = __ldg(reinterpret_cast<const unsigned long long *>(P.chunks + ch) + 2);
+  ChunkEntry ce;
+  ce.ctl_off = a.x; ce.val_off = (uint32_t)a.y; ce.cursor = (uint32_t)(a.y >> 32);
+  ce.row = (int32_t)(uint32_t)b; ce.pad = (uint32_t)(b >> 32);
+  SpmvChunkOp<SYM> op{P.values + P.val_base, x, y, P.row_start, alpha, lane, -1, 0.0};
+  process_chunk(P, ce, smem[warp], lane, op);
 }
 
-// Parity aid: the same traversal, storing the decoded coordinates per value.
-struct DecodeWalkOp {
+// Parity aid: the same traversals, storing the decoded coordinates per value (csxb_decode_coords).
+struct DecodeChunkOp {
   int *rows, *cols;   // partition base applied
-  long long row0;
-  __device__ __forceinline__ void elem(uint32_t vi, int row, uint32_t col) { rows[vi] = (int)(row0 + row); cols[vi] = (int)col; }
-  __device__ __forceinline__ void row_done(int) {}
+  long long row_start;
+  __device__ __forceinline__ void round(bool active, uint32_t vi, int row, uint32_t col) {
+    if (active) { rows[vi] = (int)(row_start + row); cols[vi] = (int)col; }
+  }
+  __device__ __forceinline__ void finish() {}
 };
+__global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_decode_chunk_kernel(const __grid_constant__ PartDev P, int *rows,
+                                                                            int *cols) {
+  __shared__ ChunkSmem smem[CHUNK_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
+  if (ch >= P.nchunks) return;
+  const ChunkEntry ce = P.chunks[ch];
+  DecodeChunkOp op{rows + P.val_base, cols + P.val_base, P.row_start};
+  process_chunk(P, ce, smem[warp], lane, op);
+}
 struct DecodeGatherOp {
   int *rows, *cols;   // device-wide
   int myrow;
   __device__ __forceinline__ void add(uint32_t vi, int col) { rows[vi] = myrow; cols[vi] = col; }
 };
-__global__ void __launch_bounds__(CTA_THREADS) csx_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(CTA_THREADS) csx_decode_gather_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
   const long long tile = blockIdx.x;
-  const uint32_t tx0 = __ldg(P.tile_xoff + tile), tx1 = __ldg(P.tile_xoff + tile + 1);
+  const uint32_t b = __ldg(P.tile_xoff + tile), e = __ldg(P.tile_xoff + tile + 1);
   for (int k = 0; k < P.rpt; k++) {
-    const long long seg = (tile * (CTA_THREADS / SEG_ROWS) + warp) * P.rpt + k;
-    if (seg * SEG_ROWS >= P.nrows) return;
-    if (tx0 & 0x80000000u) {
-      DecodeWalkOp op{rows + P.val_base, cols + P.val_base, P.row_start + seg * SEG_ROWS};
-      walk_segment(P, seg, lane, op);
-    }
-    DecodeGatherOp op{rows, cols, (int)(P.row_start + seg * SEG_ROWS + lane)};
-    for (uint32_t j = tx0 & 0x7fffffffu; j < (tx1 & 0x7fffffffu); j++) {
-      uint4 d = __ldg(P.xdesc + j);
+    const long long lrow = (tile * P.rpt + k) * CTA_THREADS + threadIdx.x;
+    if (lrow >= P.nrows) return;
+    DecodeGatherOp op{rows, cols, (int)(P.row_start + lrow)};
+    for (uint32_t j = b; j < e; j++) {
+      const uint4 d = __ldg(P.xdesc + j);
       if (d.w & XD_TRANSPOSED) continue;
       gather_desc<false>(d, P.ktab, op.myrow, op);
     }
@@ -558,7 +487,7 @@ struct csxb_matrix {
   int device = -1;
   std::vector<void *> allocs;
   std::vector<PartDev> pdev;
-  double *d_values = nullptr, *d_tbuf = nullptr;
+  double *d_values = nullptr;
   double *d_x = nullptr, *d_y = nullptr;   // staging for csxb_spmv_host
   int64_t covered_rows_end = 0;
   int64_t bytes[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -744,13 +673,6 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
   m->d_values = (double *)dv;
   KindEntry *d_ktab = nullptr;
   if (dev_copy(m, L.ktab.data(), L.ktab.size(), &d_ktab)) return -1;
-  if (H.symmetric) {
-    void *t = nullptr;
-    CUDA_TRY(cudaMalloc(&t, std::max<int64_t>(H.nrows, 1) * 8));
-    m->allocs.push_back(t);
-    CUDA_TRY(cudaMemset(t, 0, std::max<int64_t>(H.nrows, 1) * 8));
-    m->d_tbuf = (double *)t;
-  }
   int64_t tables = (int64_t)L.ktab.size() * 8, nnz_stored = 0, ctl_bytes = 0, rows_owned = 0, launches = 0;
   m->pdev.resize(L.parts.size());
   for (size_t i = 0; i < L.parts.size(); i++) {
@@ -762,16 +684,16 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     if (!hp.ctl.empty()) CUDA_TRY(cudaMemcpy((uint8_t *)dc + pl.ctl_base, hp.ctl.data(), hp.ctl.size(), cudaMemcpyHostToDevice));
     P.ctl = (const uint8_t *)dc + pl.ctl_base;
     P.values = m->d_values;
-    uint64_t *sc = nullptr; uint32_t *sv = nullptr, *tx = nullptr; XDesc *xd = nullptr;
-    if (dev_copy(m, pl.seg_ctl.data(), pl.seg_ctl.size(), &sc)) return -1;
-    if (dev_copy(m, pl.seg_val.data(), pl.seg_val.size(), &sv)) return -1;
+    uint32_t *tx = nullptr; XDesc *xd = nullptr; ChunkEntry *ch = nullptr;
+    if (dev_copy(m, pl.chunks.data(), pl.chunks.size(), &ch)) return -1;
     if (dev_copy(m, pl.tile_xoff.data(), pl.tile_xoff.size(), &tx)) return -1;
     if (dev_copy(m, pl.xdesc.data(), pl.xdesc.size(), &xd)) return -1;
-    P.seg_ctl = sc; P.seg_val = sv; P.tile_xoff = tx; P.xdesc = (const uint4 *)xd; P.ktab = d_ktab;
+    P.chunks = ch; P.nchunks = (uint32_t)pl.chunks.size();
+    P.tile_xoff = tx; P.xdesc = (const uint4 *)xd; P.ktab = d_ktab;
     if (H.symmetric) {
       double *dd = nullptr;
       if (dev_copy(m, hp.dvalues.data(), hp.dvalues.size(), &dd)) return -1;
-      P.dvalues = dd; P.tbuf = m->d_tbuf;
+      P.dvalues = dd;
       tables += (int64_t)hp.dvalues.size() * 8;
     }
     P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
@@ -780,8 +702,8 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
     nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
-    if (pl.has_row_local) tables += (int64_t)pl.seg_ctl.size() * 8 + (int64_t)pl.seg_val.size() * 4;
-    if (pl.nrows) launches += 1 + (H.symmetric && pl.has_row_local ? 1 : 0);
+    tables += (int64_t)pl.chunks.size() * (int64_t)sizeof(ChunkEntry);
+    if (pl.nrows) launches += 1 + (pl.chunks.empty() ? 0 : 1);
     m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
     if (free_host) std::vector<double>().swap(hp.values);
   }
@@ -809,26 +731,24 @@ int64_t csxb_traffic(const csxb_matrix_t *m, int what) {
 }  // extern "C"
 
 template <bool SYM, int RPT, int KSET>
-static void launch_main_k(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
-                          int overwrite, cudaStream_t s) {
+static void launch_gather_k(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
+                            int overwrite, cudaStream_t s) {
   dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
   // descriptors can also come from other partitions (transposed images under CSX-Sym)
-  const bool has_xd = !pl.xdesc.empty();
-  if (pl.has_row_local && has_xd) csx_spmv_kernel<true, true, SYM, RPT, KSET><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else if (pl.has_row_local) csx_spmv_kernel<true, false, SYM, RPT, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else csx_spmv_kernel<false, true, SYM, RPT, KSET><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
 }
 template <bool SYM>
-static void launch_main(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
-                        int overwrite, cudaStream_t s) {
+static void launch_gather(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
+                          int overwrite, cudaStream_t s) {
   // kernels are pre-compiled per (tile shape, unit-kind set) — the counterpart of the per-partition JIT (CsxJit.hpp)
   const bool diag1 = !SYM && pl.xd_diag1_only && !pl.xdesc.empty();
   if (pl.rpt == 4) {
-    if (diag1) launch_main_k<SYM, 4, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
-    else launch_main_k<SYM, 4, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
+    if (diag1) launch_gather_k<SYM, 4, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
+    else launch_gather_k<SYM, 4, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
   } else {
-    if (diag1) launch_main_k<SYM, 1, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
-    else launch_main_k<SYM, 1, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
+    if (diag1) launch_gather_k<SYM, 1, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
+    else launch_gather_k<SYM, 1, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
   }
 }
 
@@ -838,16 +758,20 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
   cudaStream_t s = (cudaStream_t)stream;
   const bool sym = m->host.symmetric;
-  if (sym)  // every scatter must land before any tile folds tbuf into y
-    for (size_t i = 0; i < m->pdev.size(); i++) {
-      const PartLayout &pl = m->layout.parts[i];
-      if (pl.ntiles && pl.has_row_local) csx_sym_scatter_kernel<<<(unsigned)pl.ntiles, CTA_THREADS, 0, s>>>(m->pdev[i], d_x);
-    }
+  // kernel 1 of every partition first: it initialises y, and under CSX-Sym the chunk kernel of one
+  // partition adds into rows that another partition owns
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
     if (!pl.ntiles) continue;
-    if (sym) launch_main<true>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
-    else launch_main<false>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
+    if (sym) launch_gather<true>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
+    else launch_gather<false>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
+  }
+  for (size_t i = 0; i < m->pdev.size(); i++) {
+    const PartLayout &pl = m->layout.parts[i];
+    if (pl.chunks.empty()) continue;
+    const unsigned grid = (unsigned)((pl.chunks.size() + CHUNK_WARPS - 1) / CHUNK_WARPS);
+    if (sym) csx_chunk_kernel<true><<<grid, CHUNK_WARPS * 32, 0, s>>>(m->pdev[i], d_x, d_y, alpha);
+    else csx_chunk_kernel<false><<<grid, CHUNK_WARPS * 32, 0, s>>>(m->pdev[i], d_x, d_y, alpha);
   }
   // rows after the last partition's last non-empty row belong to nobody; VecInit(y,0) clears them (CsxKernels.cpp:93)
   if (overwrite && m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total && m->covered_rows_end < m->host.nrows)
@@ -877,33 +801,6 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
   return 0;
 }
 
-// Experimental phase-B variants for partitions made of linear cross-row units only (tuning aid, not API).
-int csxb_debug_variant(csxb_matrix_t *m, int variant, double alpha, const double *d_x, double *d_y, void *stream) {
-  if (!m->uploaded || m->pdev.size() != 1) return fail("debug variant needs one uploaded partition");
-  const PartLayout &pl = m->layout.parts[0];
-  if (pl.rpt != 4) return fail("debug variant needs a 4-rows-per-thread partition");  // row-local units are skipped
-  cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
-  const PartDev &P = m->pdev[0];
-  switch (variant) {
-    case 0: csx_xd_exp_kernel<4, 1, 0, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 1: csx_xd_exp_kernel<4, 2, 0, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 2: csx_xd_exp_kernel<4, 1, 1, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 3: csx_xd_exp_kernel<4, 2, 1, false><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 4: csx_xd_exp_kernel<4, 2, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 5: csx_xd_exp_kernel<4, 3, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 6: csx_xd_exp_kernel<4, 4, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 7: csx_xd_exp_kernel<4, 2, 0, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 8: csx_xd_exp_kernel<4, 1, 1, false, 8><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 9: csx_xd_exp_kernel<4, 1, 1, false, 7><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 10: csx_xd_exp_kernel<4, 1, 1, true><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    case 11: csx_xd_exp_kernel<4, 1, 1, true, 8><<<grid, block, 0, s>>>(P, d_x, d_y, alpha); break;
-    default: return fail("unknown variant");
-  }
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
 int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t *cols) {
   csxb_matrix *m = const_cast<csxb_matrix *>(mc);
   if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
@@ -916,7 +813,9 @@ int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t
   CUDA_TRY(cudaMalloc((void **)&dcl, std::max<size_t>(n, 1) * 4));
   CUDA_TRY(cudaMemset(dr, 0xff, std::max<size_t>(n, 1) * 4));
   CUDA_TRY(cudaMemset(dcl, 0xff, std::max<size_t>(n, 1) * 4));
-  if (pl.ntiles) csx_decode_kernel<<<(unsigned)pl.ntiles, CTA_THREADS>>>(m->pdev[part], dr, dcl);
+  if (pl.ntiles && !pl.xdesc.empty()) csx_decode_gather_kernel<<<(unsigned)pl.ntiles, CTA_THREADS>>>(m->pdev[part], dr, dcl);
+  if (!pl.chunks.empty())
+    csx_decode_chunk_kernel<<<(unsigned)((pl.chunks.size() + CHUNK_WARPS - 1) / CHUNK_WARPS), CHUNK_WARPS * 32>>>(m->pdev[part], dr, dcl);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy(rows, dr + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(cols, dcl + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));

@@ -83,15 +83,11 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     L.val_base = vbase; L.ctl_base = cbase;
     vbase += (uint64_t)cp.nnz;
     cbase += ((uint64_t)cp.ctl.size() + CTL_PAD + 15) & ~uint64_t(15);
-    L.nseg = (cp.nrows + SEG_ROWS - 1) / SEG_ROWS;
     // big partitions: 4 rows per thread (more loads in flight per thread, fewer carry-in descriptors)
     L.rpt = tile_rpt(cp.nrows, m.rows_per_thread);
     const int64_t TILE_ROWS = L.tile_rows();
     L.ntiles = (cp.nrows + TILE_ROWS - 1) / TILE_ROWS;
-    L.seg_ctl.assign((size_t)L.nseg + 1, 0);
-    L.seg_val.assign((size_t)L.nseg + 1, 0);
     L.tile_xoff.assign((size_t)L.ntiles + 1, 0);
-    std::vector<uint8_t> tile_rl((size_t)L.ntiles, 0);
     memset(L.idtab, 0, sizeof(L.idtab));
     uint32_t id2k[64];
     size_t nid = 0;
@@ -113,8 +109,14 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     const uint8_t *ctl = cp.ctl.data();
     uint64_t p = 0, end = cp.ctl.size();
     int64_t row = 0, col = 0, v = 0;
-    int64_t next_seg = 0;   // first segment without an entry yet
     bool first = true;
+    // open chunk of consecutive chunk-kernel units
+    bool open = false;
+    int64_t ch_elems = 0, ch_units = 0;
+    uint64_t ch_start = 0;
+    auto close_chunk = [&](uint64_t at) {
+      if (open) { L.chunks.back().pad = (uint32_t)(at - ch_start); open = false; }
+    };
     while (p < end) {
       uint64_t unit_off = p;
       uint8_t flags = ctl[p++], size = ctl[p++];
@@ -123,56 +125,67 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         row += (flags & 0x40) ? (int64_t)get_varint(ctl, p) : 1;
         col = 0;
       }
+      const int64_t cursor_before = (nr || first) ? 0 : col;
       if (m.full_colind) { uint32_t c; memcpy(&c, ctl + p, 4); p += 4; col = c; }
       else col = (int64_t)((uint64_t)col + get_varint(ctl, p));   // modulo 2^64 (negative ucol)
       if (row >= cp.nrows) return "ctl stream leaves the partition (row " + std::to_string(row) + ")";
-      if (nr || first) {  // first unit of a row: entry point for every segment up to this row's
-        int64_t s = row / SEG_ROWS;
-        for (; next_seg <= s; next_seg++) {
-          L.seg_ctl[next_seg] = unit_off | ((uint64_t)(next_seg == s ? row % SEG_ROWS : 0) << 56);
-          L.seg_val[next_seg] = (uint32_t)v;
-        }
-      }
       first = false;
       uint32_t id = flags & 0x3f;
       if (id >= nid) return "ctl stream uses an unmapped unit id";
       uint32_t kind = L.idtab[id].kind_align & 0xff, align = (L.idtab[id].kind_align >> 8) & 0xff;
       uint32_t delta = L.idtab[id].delta;
       if (size == 0) return "ctl unit of size 0";
-      if (kind_row_local(kind)) {
-        L.has_row_local = true;
-        tile_rl[row / TILE_ROWS] = 1;
-        if (kind == K_HORIZ) col += (int64_t)(size - 1) * delta;
-        else {
-          for (int k = 1; k < size; k++) {
-            uint64_t d = 0;
-            memcpy(&d, ctl + p, delta);   // little-endian fixed-width deltas
-            p += delta;
-            col += (int64_t)d;
-          }
+      const int64_t start_col = col;
+      uint64_t body = kind <= K_DELTA64 ? (uint64_t)(size - 1) * delta : 0;
+      if (p + body > end) return "ctl stream truncated";
+      // geometry: rows spanned below the first one, column range
+      int64_t span = 0, cmin = start_col, cmax = start_col;
+      if (kind <= K_DELTA64) {
+        for (int k = 1; k < size; k++) {
+          uint64_t d = 0;
+          memcpy(&d, ctl + p, delta);   // little-endian fixed-width deltas
+          p += delta;
+          col += (int64_t)d;
         }
+        cmax = col;
+      } else if (kind == K_HORIZ) { col += (int64_t)(size - 1) * delta; cmax = col; }
+      else if (kind == K_VERT) span = (int64_t)(size - 1) * delta;
+      else if (kind == K_DIAG) { span = (int64_t)(size - 1) * delta; cmax = start_col + span; }
+      else if (kind == K_ADIAG) { span = (int64_t)(size - 1) * delta; cmin = start_col - span; }
+      else if (kind == K_BROW) {
+        if (size % align || size / align != delta) return "inconsistent block-row unit";
+        span = align - 1; cmax = start_col + delta - 1;
       } else {
-        L.has_cross = true;
-        int64_t span, cmin, cmax;   // rows spanned below the first one; column range
-        if (kind == K_VERT) { span = (int64_t)(size - 1) * delta; cmin = cmax = col; }
-        else if (kind == K_DIAG) { span = (int64_t)(size - 1) * delta; cmin = col; cmax = col + span; }
-        else if (kind == K_ADIAG) { span = (int64_t)(size - 1) * delta; cmax = col; cmin = col - span; }
-        else if (kind == K_BROW) {
-          if (size % align || size / align != delta) return "inconsistent block-row unit";
-          span = align - 1; cmin = col; cmax = col + delta - 1;
-        } else {
-          if (size % align || size / align != delta) return "inconsistent block-col unit";
-          span = delta - 1; cmin = col; cmax = col + align - 1;
+        if (size % align || size / align != delta) return "inconsistent block-col unit";
+        span = delta - 1; cmax = start_col + align - 1;
+      }
+      if (row + span >= cp.nrows) return "cross-row unit leaves its partition";
+      if (cmin < 0 || cmax >= cp.ncols) return "unit leaves the column range";
+
+      if (!goes_to_xdt(kind, size)) {
+        // chunk kernel: extend the open chunk or start a new one at this unit
+        uint64_t ubytes = p - unit_off;
+        if (open && (ch_elems + size > CHUNK_MAX_ELEMS || ch_units + 1 > CHUNK_MAX_UNITS ||
+                     (unit_off - ch_start) + ubytes > (uint64_t)CHUNK_MAX_BYTES))
+          close_chunk(unit_off);
+        if (!open) {
+          ChunkEntry ce;
+          ce.ctl_off = unit_off; ce.val_off = (uint32_t)v; ce.cursor = (uint32_t)cursor_before;
+          ce.row = (int32_t)row; ce.pad = 0;
+          L.chunks.push_back(ce);
+          open = true; ch_elems = 0; ch_units = 0; ch_start = unit_off;
         }
-        if (row + span >= cp.nrows) return "cross-row unit leaves its partition";
-        if (cmin < 0 || cmax >= cp.ncols) return "unit leaves the column range";
+        ch_elems += size; ch_units += 1;
+        L.has_flat = true;
+        L.flat_elems += size;
+      } else {
+        close_chunk(unit_off);   // the chunk kernel never sees table units
         XDesc d;
         d.voff = (uint32_t)(L.val_base + (uint64_t)v);
         d.row = (int32_t)(cp.row_start + row);
-        d.col = (int32_t)col;
+        d.col = (int32_t)start_col;
         d.meta = id2k[id] | ((uint32_t)size << 16) | (kind << 24);
-        if (kind == K_BROW || kind == K_BCOL) d.meta |= (align - 1) << 29;
-        else if (delta == 1) d.meta |= XD_DELTA1;
+        if (delta == 1) d.meta |= XD_DELTA1;
         for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) pend.push_back(Pending{(int64_t)pi, t, d});
         if (m.symmetric) {  // transposed image, listed under the tiles of its columns
           XDesc td = d;
@@ -182,7 +195,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
             int64_t q = owner_of(g);
             if (q < 0) return "symmetric update targets a row that is not on this device";
             int64_t rel = g - m.parts[q].row_start;
-            const int64_t qt = out.parts[q].rpt ? (int64_t)CTA_THREADS * tile_rpt(m.parts[q].nrows, m.rows_per_thread) : 0;
+            const int64_t qt = (int64_t)CTA_THREADS * tile_rpt(m.parts[q].nrows, m.rows_per_thread);
             pend.push_back(Pending{q, rel / qt, td});
             // first row of the next tile, or of the next partition if that comes first
             g = std::min(m.parts[q].row_start + (rel / qt + 1) * qt, m.parts[q].row_start + m.parts[q].nrows);
@@ -191,9 +204,8 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       }
       v += size;
     }
+    close_chunk(end);
     if (v != cp.nnz) return "ctl stream covers " + std::to_string(v) + " values, expected " + std::to_string(cp.nnz);
-    for (; next_seg <= L.nseg; next_seg++) { L.seg_ctl[next_seg] = end; L.seg_val[next_seg] = (uint32_t)v; }
-    for (int64_t t = 0; t < L.ntiles; t++) if (tile_rl[t]) L.tile_xoff[t] |= 0x80000000u;
   }
   out.total_values = vbase;
   out.total_ctl = cbase;
@@ -208,7 +220,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     for (int64_t t = 0; t < L.ntiles; t++) cnt[q][t + 1] += cnt[q][t];
     if (cnt[q][L.ntiles] >= 0x80000000u) return "cross-row unit table too large";
     L.xdesc.resize(cnt[q][L.ntiles]);
-    for (int64_t t = 0; t <= L.ntiles; t++) L.tile_xoff[t] |= cnt[q][t];
+    for (int64_t t = 0; t <= L.ntiles; t++) L.tile_xoff[t] = cnt[q][t];
   }
   std::vector<std::vector<uint32_t>> fill(cnt);
   for (const Pending &e : pend) {

@@ -5,22 +5,27 @@
 // (src/templates/csx_spmv_tmpl.c:66-101) the GPU gets from two side tables
 // built once at tune time by decoding ctl on the host:
 //
-//   * segment table — one entry per 32 consecutive rows ("warp segment"):
-//     byte offset of the first unit that starts in the segment, index of its
-//     first value, and the row it belongs to.  A warp enters the ctl stream
-//     there and decodes unit heads (flags, size, varints) and delta bodies in
-//     registers; it executes the units that live in one row (delta8/16/32/64,
-//     horizontal) with one lane per element.
+//   * chunk table — the ctl stream is cut at unit boundaries into chunks of
+//     at most 1024 non-zeros / 128 units / 4 KB of ctl ("warp-segmented ctl
+//     chunks").  An entry holds the byte offset of the chunk's first unit, the
+//     index of its first value, the row it belongs to and the column cursor at
+//     that point, i.e. the decoder state a warp needs to start there.  A warp
+//     stages the chunk's ctl bytes in shared memory, parses the unit heads
+//     (flags, size, varints), then decodes all elements of the chunk 32 at a
+//     time: delta bodies become columns through a segmented warp prefix sum,
+//     substructure elements get (row, column) from their unit's geometry.
+//     Rows are reduced inside the warp with a segmented shuffle reduction and
+//     added to y with fp64 red operations (a row may span chunks).
 //
-//   * cross-row unit table (XDT) — vertical, diagonal, anti-diagonal and block
-//     units update several rows.  Each such unit gets a 16-byte descriptor
-//     (value offset, start row, start column, kind/size) that is listed under
-//     every row tile (256 or 1024 rows) it touches, including tiles after the one it starts
-//     in ("carry-in").  The thread that owns a row gathers its contributions
-//     from the descriptors of its tile: conflict free, no atomics, y written
-//     once.  For CSX-Sym the transposed image of every cross-row unit is
-//     listed under the tiles of its *columns*, which makes the symmetric
-//     update of those units a gather as well.
+//   * cross-row unit table (XDT) — long vertical / diagonal / anti-diagonal
+//     units (>= XDT_MIN_SIZE elements) are better served by a gather: each gets
+//     a 16-byte descriptor (value offset, start row, start column, kind/size)
+//     listed under every row tile (256 or 1024 rows) it touches, including
+//     tiles after the one it starts in ("carry-in").  The thread that owns a
+//     row gathers its contributions from the descriptors of its tile: conflict
+//     free, no atomics.  For CSX-Sym the transposed image of such a unit is
+//     listed under the tiles of its *columns*, so the symmetric update of
+//     those units is a gather as well.  The chunk kernel skips these units.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -30,9 +35,12 @@
 
 namespace spxb {
 
-constexpr int SEG_ROWS = 32;     // rows per warp segment
-constexpr int CTA_THREADS = 256; // threads per CTA; a tile has CTA_THREADS * rpt rows
-constexpr int CTL_PAD = 32;      // readable bytes past the end of ctl
+constexpr int CTA_THREADS = 256;      // gather kernel: threads per CTA; a tile has CTA_THREADS * rpt rows
+constexpr int CTL_PAD = 32;           // readable bytes past the end of ctl
+constexpr int XDT_MIN_SIZE = 8;       // linear cross-row units at least this long go to the XDT
+constexpr int CHUNK_MAX_ELEMS = 1024; // chunk limits (chunk kernel shared-memory budget)
+constexpr int CHUNK_MAX_UNITS = 128;
+constexpr int CHUNK_MAX_BYTES = 4096;
 
 // unit kinds as the kernels see them
 enum Kind : uint32_t {
@@ -40,33 +48,42 @@ enum Kind : uint32_t {
   K_VERT = 5, K_DIAG = 6, K_ADIAG = 7, K_BROW = 8, K_BCOL = 9                // cross-row
 };
 inline bool kind_row_local(uint32_t k) { return k <= K_HORIZ; }
+inline bool goes_to_xdt(uint32_t kind, uint32_t size) { return kind >= K_VERT && kind <= K_ADIAG && size >= (uint32_t)XDT_MIN_SIZE; }
 
 // 16-byte cross-row unit descriptor (device layout: uint4)
 struct XDesc {
   uint32_t voff;   // index of the unit's first value in the device-wide values array
   int32_t row;     // global 0-based row of the unit's first element
   int32_t col;     // global 0-based column of the unit's first element
-  uint32_t meta;   // [0:16) kind-table index  [16:24) size  [24:28) kind  [28] transposed
-                   // [29:32) linear kinds: bit29 = (delta == 1); block kinds: align - 1
+  uint32_t meta;   // [0:16) kind-table index  [16:24) size  [24:28) kind  [28] transposed  [29] stride == 1
 };
 constexpr uint32_t XD_TRANSPOSED = 1u << 28;
 constexpr uint32_t XD_DELTA1 = 1u << 29;
 
 struct KindEntry { uint32_t kind_align; uint32_t delta; };  // kind | align << 8 ; stride or free block dim
 
+// 24-byte chunk entry (device layout: 3 x u64)
+struct ChunkEntry {
+  uint64_t ctl_off;   // byte offset of the chunk's first unit head (partition relative)
+  uint32_t val_off;   // index of its first value (partition relative, XDT units included)
+  uint32_t cursor;    // column cursor before that unit (0 when the unit starts a row)
+  int32_t row;        // partition-relative row of that unit
+  uint32_t pad;
+};
+
 struct PartLayout {
   int64_t nrows = 0, row_start = 0, nnz = 0, ctl_size = 0;
   uint64_t val_base = 0, ctl_base = 0;   // offsets into the device-wide arrays
-  bool has_row_local = false, has_cross = false;
+  bool has_flat = false;                 // some unit is handled by the chunk kernel
   bool xd_diag1_only = true;             // every descriptor of this partition's table is a direct diagonal unit of stride 1
-  int64_t nseg = 0, ntiles = 0;
+  int64_t ntiles = 0;
   int rpt = 1;                           // rows per thread (1 or 4): tile_rows = CTA_THREADS * rpt
   int64_t tile_rows() const { return (int64_t)CTA_THREADS * rpt; }
   KindEntry idtab[64];                   // ctl unit id -> kind
-  std::vector<uint64_t> seg_ctl;         // nseg + 1 ; [63:56] row within segment, [55:0] ctl offset (partition relative)
-  std::vector<uint32_t> seg_val;         // nseg + 1 ; value index (partition relative)
-  std::vector<uint32_t> tile_xoff;       // ntiles + 1 ; bit 31 of entry t: tile t has row-local units
+  std::vector<ChunkEntry> chunks;        // nchunks + 1 (the last entry marks the end of the stream)
+  std::vector<uint32_t> tile_xoff;       // ntiles + 1
   std::vector<XDesc> xdesc;
+  int64_t flat_elems = 0;                // non-zeros handled by the chunk kernel
 };
 
 struct DeviceLayout {
