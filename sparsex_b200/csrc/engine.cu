@@ -282,8 +282,8 @@ __device__ __forceinline__ uint64_t smem_varint(const uint8_t *c, uint32_t &pos)
   return v;
 }
 
-// F::round(active, value index within the partition, partition-relative row, column) is called by all lanes
-// once per 32 elements (warp-uniform), F::finish() once at the end.
+// F::fetch(active, value index within the partition, partition-relative row, column) returns the lane's product,
+// F::reduce(active, row, product) folds a 32-element round into y (both warp-uniform calls), F::finish() ends the chunk.
 template <class F>
 __device__ __forceinline__ void process_chunk(const PartDev &P, const ChunkEntry ce, ChunkSmem &S, int lane, F &f) {
   // 1. stage the chunk's ctl bytes: 16-byte coalesced copies of the aligned window that contains them
@@ -299,18 +299,28 @@ __device__ __forceinline__ void process_chunk(const PartDev &P, const ChunkEntry
   uint32_t pos = 0, ne = 0, nu = 0;
   int row = ce.row;
   bool firstu = true;
+  const uint32_t *cw = reinterpret_cast<const uint32_t *>(S.raw);   // word view for 4-byte unaligned reads
   while (pos < nbytes) {
-    const uint32_t flags = c[pos], size = c[pos + 1];
-    pos += 2;
+    // four head bytes at once: flags, size and (the common case) a one- or two-byte column varint
+    const uint32_t bp = mis + pos;
+    const uint32_t w4 = __funnelshift_r(cw[bp >> 2], cw[(bp >> 2) + 1], (bp & 3) * 8);
+    const uint32_t flags = w4 & 0xff, size = (w4 >> 8) & 0xff;
     const bool nr = (flags & 0x80) != 0;
-    if (nr) {  // csx_spmv_tmpl.c:86-91; the entry unit's row comes from the table
-      uint32_t jmp = 1;
-      if (flags & 0x40) jmp = (uint32_t)smem_varint(c, pos);
-      if (!firstu) row += (int)jmp;
-    }
     uint32_t ucol;
-    if (P.full_colind) { ucol = c[pos] | (c[pos + 1] << 8) | (c[pos + 2] << 16) | ((uint32_t)c[pos + 3] << 24); pos += 4; }
-    else ucol = (uint32_t)smem_varint(c, pos);   // modulo 2^32 == modulo 2^64 truncated (negative ucol)
+    if (!(flags & 0x40) && !P.full_colind && (w4 & 0x80800000u) != 0x80800000u) {
+      const uint32_t b2 = (w4 >> 16) & 0xff, b3 = w4 >> 24;
+      if (b2 < 0x80) { ucol = b2; pos += 3; } else { ucol = (b2 & 0x7f) | (b3 << 7); pos += 4; }
+      if (nr && !firstu) row += 1;
+    } else {
+      pos += 2;
+      if (nr) {  // csx_spmv_tmpl.c:86-91; the entry unit's row comes from the table
+        uint32_t jmp = 1;
+        if (flags & 0x40) jmp = (uint32_t)smem_varint(c, pos);
+        if (!firstu) row += (int)jmp;
+      }
+      if (P.full_colind) { ucol = c[pos] | (c[pos + 1] << 8) | (c[pos + 2] << 16) | ((uint32_t)c[pos + 3] << 24); pos += 4; }
+      else ucol = (uint32_t)smem_varint(c, pos);   // modulo 2^32 == modulo 2^64 truncated (negative ucol)
+    }
     const KindEntry ke = P.idtab[flags & 0x3f];
     const uint32_t kind = ke.kind_align & 0xff, align = (ke.kind_align >> 8) & 0xff;
     const bool reset = firstu || nr || P.full_colind;    // column cursor restarts at this unit
@@ -325,45 +335,65 @@ __device__ __forceinline__ void process_chunk(const PartDev &P, const ChunkEntry
   }
   __syncwarp();
 
-  // 3. decode 32 elements per round
+  // 3. decode 64 elements per iteration (two independent 32-element rounds: their loads overlap)
   uint32_t carry = 0;
-  for (uint32_t e0 = 0; e0 < ne; e0 += 32) {
-    const uint32_t idx = e0 + lane;
-    const bool active = idx < ne;
-    uint32_t inc = 0, flag = 1, kind = 0, delta = 0, align = 0, j = 0;
-    int row_e = -1;
-    if (active) {
-      const uint4 u = S.units[S.map[idx]];
-      j = idx - (u.x & 0x7ff);
-      kind = (u.x >> 19) & 0xf; align = (u.x >> 24) & 0xf;
-      delta = u.y >> 12;
-      row_e = (int)u.w;
-      flag = 0;
-      if (j == 0) { inc = u.z; flag = (u.x >> 23) & 1; }
-      else if (kind <= K_DELTA64) {   // little-endian fixed-width delta; low 32 bits suffice
-        const uint8_t *b = c + (u.y & 0xfff) + (j - 1) * delta;
-        inc = b[0];
-        if (delta >= 2) inc |= (uint32_t)b[1] << 8;
-        if (delta >= 4) inc |= ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
-      } else if (kind == K_HORIZ) inc = delta;
+  for (uint32_t e0 = 0; e0 < ne; e0 += 64) {
+    uint32_t cur[2], flag[2], kind[2], delta[2], align[2], jj[2];
+    int row_e[2];
+    bool active[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t idx = e0 + h * 32 + lane;
+      active[h] = idx < ne;
+      uint32_t inc = 0;
+      flag[h] = 1; kind[h] = 0; delta[h] = 0; align[h] = 1; jj[h] = 0; row_e[h] = -1 - h;
+      if (active[h]) {
+        const uint4 u = S.units[S.map[idx]];
+        const uint32_t j = idx - (u.x & 0x7ff);
+        jj[h] = j;
+        kind[h] = (u.x >> 19) & 0xf; align[h] = (u.x >> 24) & 0xf;
+        delta[h] = u.y >> 12;
+        row_e[h] = (int)u.w;
+        flag[h] = 0;
+        if (j == 0) { inc = u.z; flag[h] = (u.x >> 23) & 1; }
+        else if (kind[h] <= K_DELTA64) {   // little-endian fixed-width delta; low 32 bits suffice
+          const uint8_t *b = c + (u.y & 0xfff) + (j - 1) * delta[h];
+          inc = b[0];
+          if (delta[h] >= 2) inc |= (uint32_t)b[1] << 8;
+          if (delta[h] >= 4) inc |= ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+        } else if (kind[h] == K_HORIZ) inc = delta[h];
+      }
+      cur[h] = inc;
     }
-    // segmented inclusive prefix sum of the cursor increments (segments start where the cursor restarts)
-    uint32_t cur = inc;
+    // segmented inclusive prefix sums of the cursor increments (segments start where the cursor restarts)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t tv = __shfl_up_sync(FULL, cur, o), tf = __shfl_up_sync(FULL, flag, o);
-      if (lane >= o) { if (!flag) cur += tv; flag |= tf; }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint32_t tv = __shfl_up_sync(FULL, cur[h], o), tf = __shfl_up_sync(FULL, flag[h], o);
+        if (lane >= o) { if (!flag[h]) cur[h] += tv; flag[h] |= tf; }
+      }
     }
-    if (!flag) cur += carry;
-    carry = __shfl_sync(FULL, cur, 31);
+    if (!flag[0]) cur[0] += carry;
+    carry = __shfl_sync(FULL, cur[0], 31);
+    if (!flag[1]) cur[1] += carry;
+    carry = __shfl_sync(FULL, cur[1], 31);
     // element coordinates from the unit geometry (cursor = unit start for substructures)
-    uint32_t col_e = cur;
-    if (kind == K_VERT) row_e += (int)(j * delta);
-    else if (kind == K_DIAG) { row_e += (int)(j * delta); col_e += j * delta; }
-    else if (kind == K_ADIAG) { row_e += (int)(j * delta); col_e -= j * delta; }
-    else if (kind == K_BROW) { row_e += (int)(j % align); col_e += j / align; }   // column-major values
-    else if (kind == K_BCOL) { row_e += (int)(j / align); col_e += j % align; }   // row-major values
-    f.round(active, ce.val_off + idx, row_e, col_e);
+    uint32_t col_e[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t j = jj[h];
+      col_e[h] = cur[h];
+      if (kind[h] == K_VERT) row_e[h] += (int)(j * delta[h]);
+      else if (kind[h] == K_DIAG) { row_e[h] += (int)(j * delta[h]); col_e[h] += j * delta[h]; }
+      else if (kind[h] == K_ADIAG) { row_e[h] += (int)(j * delta[h]); col_e[h] -= j * delta[h]; }
+      else if (kind[h] == K_BROW) { row_e[h] += (int)(j % align[h]); col_e[h] += j / align[h]; }   // column-major values
+      else if (kind[h] == K_BCOL) { row_e[h] += (int)(j / align[h]); col_e[h] += j % align[h]; }   // row-major values
+    }
+    const double p0 = f.fetch(active[0], ce.val_off + e0 + lane, row_e[0], col_e[0]);
+    const double p1 = f.fetch(active[1], ce.val_off + e0 + 32 + lane, row_e[1], col_e[1]);
+    f.reduce(active[0], row_e[0], p0);
+    if (e0 + 32 < ne) f.reduce(active[1], row_e[1], p1);
   }
   f.finish();
 }
@@ -385,13 +415,16 @@ struct SpmvChunkOp {
     }
     run_row = -1; run_acc = 0.0;
   }
-  __device__ __forceinline__ void round(bool active, uint32_t vi, int row, uint32_t col) {
+  __device__ __forceinline__ double fetch(bool active, uint32_t vi, int row, uint32_t col) {
     double p = 0.0;
     if (active) {
       const double v = __ldg(values + vi);
       p = v * __ldg(x + col);
       if (SYM) atomicAdd(y + col, alpha * v * __ldg(x + row_start + row));   // transposed update
     }
+    return p;
+  }
+  __device__ __forceinline__ void reduce(bool active, int row, double p) {
     // whole round in one row (long rows): keep lane-wise partial sums, reduce once per row
     const int row0 = __shfl_sync(FULL, row, 0);
     if (__all_sync(FULL, row == row0)) {
@@ -422,11 +455,11 @@ __global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_chunk_kernel(const __gri
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
   if (ch >= P.nchunks) return;
-  const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(P.chunks + ch));
-  const unsigned long long b = __ldg(reinterpret_cast<const unsigned long long *>(P.chunks + ch) + 2);
+  const unsigned long long *q = reinterpret_cast<const unsigned long long *>(P.chunks + ch);   // 24-byte entries
+  const unsigned long long a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
   ChunkEntry ce;
-  ce.ctl_off = a.x; ce.val_off = (uint32_t)a.y; ce.cursor = (uint32_t)(a.y >> 32);
-  ce.row = (int32_t)(uint32_t)b; ce.pad = (uint32_t)(b >> 32);
+  ce.ctl_off = a0; ce.val_off = (uint32_t)a1; ce.cursor = (uint32_t)(a1 >> 32);
+  ce.row = (int32_t)(uint32_t)a2; ce.pad = (uint32_t)(a2 >> 32);
   SpmvChunkOp<SYM> op{P.values + P.val_base, x, y, P.row_start, alpha, lane, -1, 0.0};
   process_chunk(P, ce, smem[warp], lane, op);
 }
@@ -435,9 +468,11 @@ __global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_chunk_kernel(const __gri
 struct DecodeChunkOp {
   int *rows, *cols;   // partition base applied
   long long row_start;
-  __device__ __forceinline__ void round(bool active, uint32_t vi, int row, uint32_t col) {
+  __device__ __forceinline__ double fetch(bool active, uint32_t vi, int row, uint32_t col) {
     if (active) { rows[vi] = (int)(row_start + row); cols[vi] = (int)col; }
+    return 0.0;
   }
+  __device__ __forceinline__ void reduce(bool, int, double) {}
   __device__ __forceinline__ void finish() {}
 };
 __global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_decode_chunk_kernel(const __grid_constant__ PartDev P, int *rows,

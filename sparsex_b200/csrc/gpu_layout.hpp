@@ -6,7 +6,7 @@
 // built once at tune time by decoding ctl on the host:
 //
 //   * chunk table — the ctl stream is cut at unit boundaries into chunks of
-//     at most 1024 non-zeros / 128 units / 4 KB of ctl ("warp-segmented ctl
+//     at most 512 non-zeros / 64 units / 2 KB of ctl ("warp-segmented ctl
 //     chunks").  An entry holds the byte offset of the chunk's first unit, the
 //     index of its first value, the row it belongs to and the column cursor at
 //     that point, i.e. the decoder state a warp needs to start there.  A warp
@@ -38,9 +38,9 @@ namespace spxb {
 constexpr int CTA_THREADS = 256;      // gather kernel: threads per CTA; a tile has CTA_THREADS * rpt rows
 constexpr int CTL_PAD = 32;           // readable bytes past the end of ctl
 constexpr int XDT_MIN_SIZE = 8;       // linear cross-row units at least this long go to the XDT
-constexpr int CHUNK_MAX_ELEMS = 1024; // chunk limits (chunk kernel shared-memory budget)
-constexpr int CHUNK_MAX_UNITS = 128;
-constexpr int CHUNK_MAX_BYTES = 4096;
+constexpr int CHUNK_MAX_ELEMS = 512;  // chunk limits (chunk kernel shared-memory budget: 3.6 KB per warp)
+constexpr int CHUNK_MAX_UNITS = 64;
+constexpr int CHUNK_MAX_BYTES = 2048;
 
 // unit kinds as the kernels see them
 enum Kind : uint32_t {

@@ -69,5 +69,6 @@ int main(int argc, char **argv)
     spx_mat_destroy(A);
     spx_finalize();
     free(rowptr); free(colind); free(values); free(ybuf);
-    return (maxerr < 1e-12 && maxerr2 < 1e-12 && maxmix == 0.0 && rc_bad == SPX_FAILURE) ? 0 : 1;
+    /* CSX-Sym adds with fp64 red operations: summation order, hence the last bits, may differ between calls */
+    return (maxerr < 1e-12 && maxerr2 < 1e-12 && maxmix < 1e-12 && rc_bad == SPX_FAILURE) ? 0 : 1;
 }
