@@ -15,7 +15,10 @@
 //   CSX-Sym              SparsePartition.hpp:965-1074, CsxBuild.hpp:204-288, 400-581
 // Non-NUMA semantics (SPX_USE_NUMA == 0) throughout.
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -27,6 +30,16 @@
 
 namespace spxb {
 namespace {
+
+// SPXB_TUNE_TRACE=1 prints phase timings of spx_mat_tune to stderr
+struct Trace {
+  const char *what; std::chrono::steady_clock::time_point t0;
+  explicit Trace(const char *w) : what(w), t0(std::chrono::steady_clock::now()) {}
+  ~Trace() {
+    static const bool on = getenv("SPXB_TUNE_TRACE") != nullptr;
+    if (on && what) fprintf(stderr, "[tune] %-22s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
 
 struct TuneError : std::runtime_error {
   explicit TuneError(const std::string &m) : std::runtime_error(m) {}
@@ -80,25 +93,49 @@ inline RC retarget(int from, int to, RC p, int32_t R, int32_t C) {
 }
 
 // ------------------------------------------------------------- radix sort --
+// Slices [0, n) over worker threads (the sorts dominate spx_mat_tune on large partitions).
+int g_sort_threads = 1;
+template <class Fn>
+void parallel_slices(size_t n, Fn fn) {
+  int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
+  if (T <= 1) { fn(0, size_t(0), n); return; }
+  std::vector<std::thread> th;
+  size_t per = (n + T - 1) / T;
+  for (int t = 0; t < T; t++) {
+    size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
+    th.emplace_back([=]() { fn(t, b, e); });
+  }
+  for (auto &x : th) x.join();
+}
+
 // Stable LSD radix sort of (key, index) pairs; only the populated bit ranges
-// of the packed (row << 32 | col) key are visited.
+// of the packed (row << 32 | col) key are visited.  Each pass: per-thread
+// histograms, one exclusive scan over (digit, thread), per-thread stable scatter.
 void radix_sort_pairs(std::vector<uint64_t> &key, std::vector<uint32_t> &idx, int bits_lo, int bits_hi) {
   size_t n = key.size();
   std::vector<uint64_t> key2(n);
   std::vector<uint32_t> idx2(n);
   const int RB = 11;
   const size_t NB = size_t(1) << RB;
-  std::vector<size_t> hist(NB);
+  int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
+  std::vector<size_t> hist((size_t)T * NB);
   auto pass = [&](int shift, int nbits) {
     uint64_t mask = (uint64_t(1) << nbits) - 1;
     std::fill(hist.begin(), hist.end(), 0);
-    for (size_t i = 0; i < n; i++) hist[(key[i] >> shift) & mask]++;
+    parallel_slices(n, [&](int t, size_t b, size_t e) {
+      size_t *h = hist.data() + (size_t)t * NB;
+      for (size_t i = b; i < e; i++) h[(key[i] >> shift) & mask]++;
+    });
     size_t sum = 0;
-    for (size_t b = 0; b <= mask; b++) { size_t h = hist[b]; hist[b] = sum; sum += h; }
-    for (size_t i = 0; i < n; i++) {
-      size_t d = hist[(key[i] >> shift) & mask]++;
-      key2[d] = key[i]; idx2[d] = idx[i];
-    }
+    for (size_t d = 0; d <= mask; d++)
+      for (int t = 0; t < T; t++) { size_t &h = hist[(size_t)t * NB + d]; size_t c = h; h = sum; sum += c; }
+    parallel_slices(n, [&](int t, size_t b, size_t e) {
+      size_t *h = hist.data() + (size_t)t * NB;
+      for (size_t i = b; i < e; i++) {
+        size_t d = h[(key[i] >> shift) & mask]++;
+        key2[d] = key[i]; idx2[d] = idx[i];
+      }
+    });
     key.swap(key2); idx.swap(idx2);
   };
   for (int s = 0; s < bits_lo; s += RB) pass(s, std::min(RB, bits_lo - s));
@@ -115,13 +152,18 @@ struct Part {
   std::vector<int64_t> rowptr;   // rowptr[j] = #records with row <= j ; size = last row + 1
   std::vector<double> *pool = nullptr;
 
-  size_t nrowptr() const { return rowptr.size(); }
+  // The reference rebuilds a full rowptr after every reordering (SparsePartition.hpp:543-563, 852-891) — up to
+  // nr_rows + nr_cols entries in the diagonal orders.  Only its length is ever used outside the Horizontal
+  // order, so the array is materialised for Horizontal only; other orders are walked by runs of equal row.
+  size_t nrowptr_ = 1;
+  size_t nrowptr() const { return nrowptr_; }
 
-  // SparsePartition.hpp:543-563 + Builder :852-891
   void build_rowptr() {
     rowptr.clear();
-    if (e.empty()) { rowptr.push_back(0); return; }
+    if (e.empty()) { rowptr.push_back(0); nrowptr_ = 1; return; }
     int32_t last = e.back().r;
+    nrowptr_ = (size_t)last + 1;
+    if (type != T_HORIZ) return;
     rowptr.assign((size_t)last + 1, 0);
     for (const Rec &x : e) rowptr[x.r]++;
     int64_t s = 0;
@@ -131,30 +173,50 @@ struct Part {
   // SparsePartition.hpp:680-744: re-coordinate, sort lexicographically, rebuild rowptr.
   void transform(int t) {
     if (type == t) return;
+    Trace tr(e.size() >= (size_t(1) << 20) ? "transform" : nullptr);
+    const int t2type = t;
     size_t n = e.size();
     if (n) {
       std::vector<uint64_t> key(n);
       std::vector<uint32_t> idx(n);
-      uint32_t maxr = 0, maxc = 0;
-      for (size_t i = 0; i < n; i++) {
-        RC p = retarget(type, t, RC{e[i].r, e[i].c}, (int32_t)nr_rows, (int32_t)nr_cols);
-        e[i].r = p.r; e[i].c = p.c;
-        key[i] = (uint64_t(uint32_t(p.r)) << 32) | uint32_t(p.c);
-        idx[i] = (uint32_t)i;
-        maxr = std::max(maxr, uint32_t(p.r)); maxc = std::max(maxc, uint32_t(p.c));
-      }
+      const int from = type;
+      const int32_t R = (int32_t)nr_rows, C = (int32_t)nr_cols;
+      std::vector<uint32_t> mr(64, 0), mc(64, 0);
+      std::vector<char> unsorted(64, 0);
+      parallel_slices(n, [&](int t, size_t b, size_t en) {
+        uint32_t maxr = 0, maxc = 0;
+        uint64_t prev = 0;
+        bool uns = false;
+        for (size_t i = b; i < en; i++) {
+          RC p = retarget(from, t2type, RC{e[i].r, e[i].c}, R, C);
+          e[i].r = p.r; e[i].c = p.c;
+          uint64_t k = (uint64_t(uint32_t(p.r)) << 32) | uint32_t(p.c);
+          key[i] = k; idx[i] = (uint32_t)i;
+          maxr = std::max(maxr, uint32_t(p.r)); maxc = std::max(maxc, uint32_t(p.c));
+          if (i > b && k < prev) uns = true;
+          prev = k;
+        }
+        mr[t] = maxr; mc[t] = maxc; unsorted[t] = uns;
+      });
+      uint32_t maxr = *std::max_element(mr.begin(), mr.end()), maxc = *std::max_element(mc.begin(), mc.end());
       bool sorted = true;
-      for (size_t i = 1; i < n && sorted; i++) sorted = key[i - 1] <= key[i];
+      for (char u : unsorted) if (u) sorted = false;
+      if (sorted) {  // slices are sorted inside; check the seams
+        int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
+        size_t per = (n + T - 1) / T;
+        for (int t = 1; t < T && sorted; t++) { size_t b = std::min(n, per * t); if (b > 0 && b < n && key[b - 1] > key[b]) sorted = false; }
+      }
       if (!sorted) {
-        if (n < 2048) {
+        if (n < 32768) {
           std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
         } else {
           radix_sort_pairs(key, idx, bit_width32(maxc), bit_width32(maxr));
         }
         std::vector<Rec> out(n);
-        for (size_t i = 0; i < n; i++) out[i] = e[idx[i]];
+        parallel_slices(n, [&](int, size_t b, size_t en) { for (size_t i = b; i < en; i++) out[i] = e[idx[i]]; });
         e.swap(out);
       }
+      type = t;
       build_rowptr();  // reference rebuilds only when elems_size_ != 0 (:741-742)
     }
     type = t;
@@ -469,11 +531,15 @@ class Miner {
   }
   // GenerateStats, :621-645: every record of a row (substructure or not) is a point.
   void stats_of(Part &p, Stats &st) {
-    size_t nr = p.nrowptr() - 1;
-    for (size_t i = 0; i < nr; i++) {
-      scan_runs(p.e.data(), p.rowptr[i], p.rowptr[i + 1], runs_);
-      if (runs_.empty()) continue;
-      if (is_blk(p.type)) stats_block(p.type, runs_, st); else stats_linear(p.type, runs_, st);
+    const Rec *recs = p.e.data();
+    size_t n = p.e.size(), b = 0;
+    bool blk = is_blk(p.type);
+    while (b < n) {
+      size_t e = b + 1;
+      while (e < n && recs[e].r == recs[b].r) e++;
+      scan_runs(recs, b, e, runs_);
+      if (blk) stats_block(p.type, runs_, st); else stats_linear(p.type, runs_, st);
+      b = e;
     }
   }
 
@@ -495,6 +561,7 @@ class Miner {
 
   // GenAllStats, :707-813
   void gather_stats(Stats &st) {
+    Trace tr("gather_stats");
     chosen_.clear();
     if (sampling_ && spm_->nrowptr() - 1 > samples_) {
       size_t sampled = 0;
@@ -668,14 +735,16 @@ class Miner {
   void encode(int t) {
     if (t == T_NONE) return;
     spm_->transform(t);
+    Trace tr("encode rows");
     std::vector<Rec> out;
     out.reserve(spm_->e.size());
     const Rec *recs = spm_->e.data();
-    size_t nr = spm_->nrowptr() - 1;
+    const size_t n = spm_->e.size();
     bool blk = is_blk(t);
-    for (size_t i = 0; i < nr; i++) {
-      size_t b = spm_->rowptr[i], e = spm_->rowptr[i + 1];
-      if (b == e) continue;
+    size_t b = 0;
+    while (b < n) {
+      size_t e = b + 1;
+      while (e < n && recs[e].r == recs[b].r) e++;
       int32_t row = recs[b].r;
       size_t k = b;
       while (k < e) {
@@ -685,6 +754,7 @@ class Miner {
         if (blk) encode_block(row, recs + k, m - k, out); else encode_linear(row, recs + k, m - k, out);
         k = m;
       }
+      b = e;
     }
     spm_->e.swap(out);
     spm_->build_rowptr();
@@ -718,6 +788,7 @@ class CtlWriter {
 
   // MakeCsx, CsxManager.hpp:300-437
   void run(bool sym, CsxPartition &out) {
+    Trace tr("ctl emission");
     size_t nrows = (size_t)spm_->nr_rows;
     out.nnz = spm_->nr_nzeros; out.nrows = spm_->nr_rows; out.ncols = spm_->nr_cols;
     out.row_start = spm_->row_start;
@@ -860,9 +931,15 @@ struct Cursor {
 struct SplitResult { int64_t taken = 0; int64_t rows = 0; int64_t diag = 0; int32_t cmin = INT32_MAX, cmax = 0; };
 SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sym, bool keep, Part &p,
                            std::vector<double> &pool, std::vector<double> &diag) {
+  Trace tr("take_partition");
   SplitResult res;
   int32_t row_prev = 1, last_row = 0;
   size_t cnt = 0, dcnt = 0;
+  if (keep) {
+    size_t guess = limit ? std::min<size_t>(limit + (limit >> 6) + 1024, (size_t)(cur.n - cur.pos)) : (size_t)(cur.n - cur.pos);
+    if (sym) guess = guess / 2 + 1024;
+    p.e.reserve(guess); pool.reserve(guess);
+  }
   for (; !cur.end(); cur.next()) {
     int32_t row = cur.r() - (int32_t)row_start;  // 1-based, partition relative
     int32_t col = cur.c();
@@ -899,6 +976,7 @@ SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sy
 }
 
 void check_sorted_cols(const Part &p) {
+  Trace tr("check_sorted_cols");
   for (size_t i = 1; i < p.e.size(); i++)
     if (p.e[i].r == p.e[i - 1].r && p.e[i].c <= p.e[i - 1].c)
       throw TuneError("column indices must be strictly increasing within each row");
@@ -939,6 +1017,7 @@ void merge_lower(Part &lower, const Part &m1, const Part &m2) {
   }
   lower.e.swap(out);
   lower.rowptr.swap(rp);
+  lower.nrowptr_ = lower.rowptr.size();
   lower.type = T_HORIZ;
 }
 
@@ -1035,8 +1114,9 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
       std::vector<double>().swap(pools[i]);
     };
     // one preprocessing thread per partition like CsxBuild.hpp:290-326, capped by host_threads
-    int nthreads = opt.host_threads > 0 ? opt.host_threads : (int)std::thread::hardware_concurrency();
-    nthreads = std::max(1, std::min(nthreads, part_hi - part_lo));
+    int hw = opt.host_threads > 0 ? opt.host_threads : (int)std::thread::hardware_concurrency();
+    int nthreads = std::max(1, std::min(hw, part_hi - part_lo));
+    g_sort_threads = std::max(1, std::min(32, hw / nthreads));   // workers inside one partition's sorts
     std::vector<std::string> errs(part_hi - part_lo);
     if (nthreads == 1) {
       for (int i = part_lo; i < part_hi; i++) work(i);

@@ -55,64 +55,31 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Phase B.  Op::add(device-wide value index, x index) for every element of
-// descriptor d that contributes to `myrow` (global row).
+// Table units are vertical / diagonal / anti-diagonal runs (gpu_layout.hpp: goes_to_xdt).
+// Op::add(device-wide value index, x index) for every element of descriptor d that contributes to `myrow`.
 template <bool SYM, class Op>
 __device__ __forceinline__ void gather_desc(const uint4 d, const KindEntry *__restrict__ ktab, int myrow, Op &op) {
   const uint32_t meta = d.w, kind = (meta >> 24) & 0xf, size = (meta >> 16) & 0xff;
   const int r = (int)d.y, c = (int)d.z;
   const uint32_t voff = d.x;
-  if (!SYM || !(meta & XD_TRANSPOSED)) {
-    int t = myrow - r;
+  const uint32_t delta = (meta & XD_DELTA1) ? 1u : __ldg(&ktab[meta & 0xffff].delta);
+  if (!SYM || !(meta & XD_TRANSPOSED)) {  // vert_tmpl.c, diag_tmpl.c, rdiag_tmpl.c
+    const int t = myrow - r;
     if (t < 0) return;
-    if (kind <= K_ADIAG) {  // vert_tmpl.c, diag_tmpl.c, rdiag_tmpl.c
-      uint32_t k = (uint32_t)t;
-      if (!(meta & XD_DELTA1)) {
-        uint32_t delta = __ldg(&ktab[meta & 0xffff].delta);
-        k = (uint32_t)t / delta;
-        if (k * delta != (uint32_t)t) return;
-      }
-      if (k >= size) return;
-      int col = kind == K_VERT ? c : (kind == K_DIAG ? c + t : c - t);
-      op.add(voff + k, col);
-    } else if (kind == K_BROW) {  // block_row_tmpl.c: R rows x C cols, column-major values
-      uint32_t R = (meta >> 29) + 1;
-      if ((uint32_t)t >= R) return;
-      uint32_t C = size / R;
-      for (uint32_t m = 0; m < C; m++) op.add(voff + t + R * m, c + (int)m);
-    } else {  // block_col_tmpl.c: rr rows x C cols, row-major values
-      uint32_t C = (meta >> 29) + 1, rr = size / C;
-      if ((uint32_t)t >= rr) return;
-      for (uint32_t m = 0; m < C; m++) op.add(voff + t * C + m, c + (int)m);
-    }
-  } else {
-    // transposed image (CSX-Sym): element (r+a, c+b, v) adds v * x[r+a] to y[c+b]
-    if (kind == K_VERT) {  // vert_sym_tmpl.c: cur[x_indx] += sum v_k x[y_indx + k*delta]
-      if (myrow != c) return;
-      uint32_t delta = (meta & XD_DELTA1) ? 1u : __ldg(&ktab[meta & 0xffff].delta);
-      for (uint32_t k = 0; k < size; k++) op.add(voff + k, r + (int)(k * delta));
-    } else if (kind == K_DIAG || kind == K_ADIAG) {  // diag_sym_tmpl.c, rdiag_sym_tmpl.c
-      int u = kind == K_DIAG ? myrow - c : c - myrow;
-      if (u < 0) return;
-      uint32_t k = (uint32_t)u;
-      if (!(meta & XD_DELTA1)) {
-        uint32_t delta = __ldg(&ktab[meta & 0xffff].delta);
-        k = (uint32_t)u / delta;
-        if (k * delta != (uint32_t)u) return;
-      }
-      if (k >= size) return;
-      op.add(voff + k, r + u);
-    } else if (kind == K_BROW) {  // block_row_sym_tmpl.c
-      uint32_t R = (meta >> 29) + 1, C = size / R;
-      int u = myrow - c;
-      if (u < 0 || (uint32_t)u >= C) return;
-      for (uint32_t j = 0; j < R; j++) op.add(voff + j + R * u, r + (int)j);
-    } else {  // block_col_sym_tmpl.c
-      uint32_t C = (meta >> 29) + 1, rr = size / C;
-      int u = myrow - c;
-      if (u < 0 || (uint32_t)u >= C) return;
-      for (uint32_t j = 0; j < rr; j++) op.add(voff + j * C + u, r + (int)j);
-    }
+    const uint32_t k = (uint32_t)t / delta;
+    if (k * delta != (uint32_t)t || k >= size) return;
+    op.add(voff + k, kind == K_VERT ? c : (kind == K_DIAG ? c + t : c - t));
+  } else if (kind == K_VERT) {
+    // transposed image (CSX-Sym): element (r+a, c+b, v) adds v * x[r+a] to y[c+b];
+    // vert_sym_tmpl.c: cur[x_indx] += sum v_k x[y_indx + k*delta]
+    if (myrow != c) return;
+    for (uint32_t k = 0; k < size; k++) op.add(voff + k, r + (int)(k * delta));
+  } else {  // diag_sym_tmpl.c, rdiag_sym_tmpl.c
+    const int u = kind == K_DIAG ? myrow - c : c - myrow;
+    if (u < 0) return;
+    const uint32_t k = (uint32_t)u / delta;
+    if (k * delta != (uint32_t)u || k >= size) return;
+    op.add(voff + k, r + u);
   }
 }
 
@@ -121,20 +88,13 @@ template <bool SYM>
 __device__ __forceinline__ bool desc_touches(const uint4 d, const KindEntry *__restrict__ ktab, int row_lo, int row_hi) {
   const uint32_t meta = d.w, kind = (meta >> 24) & 0xf, size = (meta >> 16) & 0xff;
   const int r = (int)d.y, c = (int)d.z;
+  const uint32_t delta = (meta & XD_DELTA1) ? 1u : __ldg(&ktab[meta & 0xffff].delta);
+  const int span = (int)((size - 1) * delta);
   int lo, hi;
-  if (kind <= K_ADIAG) {
-    uint32_t delta = (meta & XD_DELTA1) ? 1u : __ldg(&ktab[meta & 0xffff].delta);
-    int span = (int)((size - 1) * delta);
-    if (!SYM || !(meta & XD_TRANSPOSED)) { lo = r; hi = r + span; }
-    else if (kind == K_VERT) { lo = hi = c; }
-    else if (kind == K_DIAG) { lo = c; hi = c + span; }
-    else { lo = c - span; hi = c; }
-  } else {
-    uint32_t a = (meta >> 29) + 1, other = size / a;   // BROW: a rows x other cols ; BCOL: other rows x a cols
-    int rows = kind == K_BROW ? (int)a : (int)other, cols = kind == K_BROW ? (int)other : (int)a;
-    if (!SYM || !(meta & XD_TRANSPOSED)) { lo = r; hi = r + rows - 1; }
-    else { lo = c; hi = c + cols - 1; }
-  }
+  if (!SYM || !(meta & XD_TRANSPOSED)) { lo = r; hi = r + span; }
+  else if (kind == K_VERT) { lo = hi = c; }
+  else if (kind == K_DIAG) { lo = c; hi = c + span; }
+  else { lo = c - span; hi = c; }
   return lo <= row_hi && hi >= row_lo;
 }
 
