@@ -227,6 +227,7 @@ constexpr int CHUNK_WARPS = 4;
 struct ChunkSmem {
   uint4 raw[(CHUNK_MAX_BYTES + 32) / 16];   // staged ctl bytes (16-byte aligned copy window)
   uint4 units[CHUNK_MAX_UNITS];             // parsed unit heads
+  uint16_t upos[CHUNK_MAX_UNITS + 2];       // byte offset of every unit head
   uint8_t map[CHUNK_MAX_ELEMS];             // element -> unit
 };
 
@@ -255,43 +256,69 @@ __device__ __forceinline__ void process_chunk(const PartDev &P, const ChunkEntry
   __syncwarp();
   const uint8_t *c = reinterpret_cast<const uint8_t *>(S.raw) + mis;
 
-  // 2. parse the unit heads (every lane runs the same scalar code; lane 0 records)
-  uint32_t pos = 0, ne = 0, nu = 0;
-  int row = ce.row;
-  bool firstu = true;
+  // 2a. unit boundaries: the only serial part (a unit's length is known only after its head is read).
+  //     Every lane runs the same scalar code; a 4-byte window covers flags, size and the common 1-2 byte column varint.
   const uint32_t *cw = reinterpret_cast<const uint32_t *>(S.raw);   // word view for 4-byte unaligned reads
+  uint32_t pos = 0, nu = 0;
   while (pos < nbytes) {
-    // four head bytes at once: flags, size and (the common case) a one- or two-byte column varint
+    if (lane == 0) S.upos[nu] = (uint16_t)pos;
     const uint32_t bp = mis + pos;
     const uint32_t w4 = __funnelshift_r(cw[bp >> 2], cw[(bp >> 2) + 1], (bp & 3) * 8);
     const uint32_t flags = w4 & 0xff, size = (w4 >> 8) & 0xff;
-    const bool nr = (flags & 0x80) != 0;
-    uint32_t ucol;
-    if (!(flags & 0x40) && !P.full_colind && (w4 & 0x80800000u) != 0x80800000u) {
-      const uint32_t b2 = (w4 >> 16) & 0xff, b3 = w4 >> 24;
-      if (b2 < 0x80) { ucol = b2; pos += 3; } else { ucol = (b2 & 0x7f) | (b3 << 7); pos += 4; }
-      if (nr && !firstu) row += 1;
-    } else {
-      pos += 2;
-      if (nr) {  // csx_spmv_tmpl.c:86-91; the entry unit's row comes from the table
-        uint32_t jmp = 1;
-        if (flags & 0x40) jmp = (uint32_t)smem_varint(c, pos);
-        if (!firstu) row += (int)jmp;
-      }
-      if (P.full_colind) { ucol = c[pos] | (c[pos + 1] << 8) | (c[pos + 2] << 16) | ((uint32_t)c[pos + 3] << 24); pos += 4; }
-      else ucol = (uint32_t)smem_varint(c, pos);   // modulo 2^32 == modulo 2^64 truncated (negative ucol)
+    uint32_t q = pos + 2;
+    if (!(flags & 0x40) && !P.full_colind && (w4 & 0x80800000u) != 0x80800000u) q += 1 + ((w4 >> 23) & 1);
+    else {
+      if (flags & 0x40) smem_varint(c, q);
+      if (P.full_colind) q += 4; else smem_varint(c, q);
     }
     const KindEntry ke = P.idtab[flags & 0x3f];
-    const uint32_t kind = ke.kind_align & 0xff, align = (ke.kind_align >> 8) & 0xff;
-    const bool reset = firstu || nr || P.full_colind;    // column cursor restarts at this unit
-    const uint32_t inc0 = (firstu && !P.full_colind) ? ce.cursor + ucol : ucol;
-    if (lane == 0)
-      S.units[nu] = make_uint4(ne | (size << 11) | (kind << 19) | ((uint32_t)reset << 23) | (align << 24),
-                               pos | (ke.delta << 12), inc0, (uint32_t)row);
-    for (uint32_t k = lane; k < size; k += 32) S.map[ne + k] = (uint8_t)nu;
-    if (kind <= K_DELTA64) pos += (size - 1) * ke.delta;
-    ne += size; nu++;
-    firstu = false;
+    if ((ke.kind_align & 0xff) <= K_DELTA64) q += (size - 1) * ke.delta;   // fixed-width delta body
+    pos = q;
+    nu++;
+  }
+  __syncwarp();
+
+  // 2b. unit records, one unit per lane: full head decode, rows and element offsets by warp prefix sums
+  uint32_t ne = 0;
+  int row_base = ce.row;
+  for (uint32_t u0 = 0; u0 < nu; u0 += 32) {
+    const uint32_t u = u0 + lane;
+    uint32_t size = 0, rowinc = 0, rec_x = 0, rec_y = 0, inc0 = 0;
+    if (u < nu) {
+      uint32_t p = S.upos[u];
+      const uint32_t flags = c[p];
+      size = c[p + 1];
+      p += 2;
+      const bool nr = (flags & 0x80) != 0;
+      if (nr) {  // csx_spmv_tmpl.c:86-91; the entry unit's row comes from the table
+        uint32_t jmp = 1;
+        if (flags & 0x40) jmp = (uint32_t)smem_varint(c, p);
+        if (u != 0) rowinc = jmp;
+      }
+      uint32_t ucol;
+      if (P.full_colind) { ucol = c[p] | (c[p + 1] << 8) | (c[p + 2] << 16) | ((uint32_t)c[p + 3] << 24); p += 4; }
+      else ucol = (uint32_t)smem_varint(c, p);   // modulo 2^32 == modulo 2^64 truncated (negative ucol)
+      const KindEntry ke = P.idtab[flags & 0x3f];
+      const uint32_t kind = ke.kind_align & 0xff, align = (ke.kind_align >> 8) & 0xff;
+      const bool reset = u == 0 || nr || P.full_colind;    // column cursor restarts at this unit
+      inc0 = (u == 0 && !P.full_colind) ? ce.cursor + ucol : ucol;
+      rec_x = (size << 11) | (kind << 19) | ((uint32_t)reset << 23) | (align << 24);
+      rec_y = p | (ke.delta << 12);
+    }
+    // inclusive scans over the 32 units: element offsets and row numbers
+    uint32_t es = size, rs = rowinc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a = __shfl_up_sync(FULL, es, o), b = __shfl_up_sync(FULL, rs, o);
+      if (lane >= o) { es += a; rs += b; }
+    }
+    if (u < nu) {
+      const uint32_t estart = ne + es - size;
+      S.units[u] = make_uint4(rec_x | estart, rec_y, inc0, (uint32_t)(row_base + (int)rs));
+      for (uint32_t k = 0; k < size; k++) S.map[estart + k] = (uint8_t)u;
+    }
+    ne += __shfl_sync(FULL, es, 31);
+    row_base += (int)__shfl_sync(FULL, rs, 31);
   }
   __syncwarp();
 

@@ -110,6 +110,13 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     uint64_t p = 0, end = cp.ctl.size();
     int64_t row = 0, col = 0, v = 0;
     bool first = true;
+    // A partition whose chunk-kernel share is tiny (stencil matrices: a few boundary elements next to
+    // millions of diagonal units) gets those elements as one-element table units instead; that saves the
+    // second kernel launch.  Coordinates are collected while the share stays under the cap.
+    struct Single { int64_t row, col, v; };
+    std::vector<Single> singles;
+    const size_t single_cap = (size_t)(cp.nnz / 256);
+    bool singles_ok = true;
     // open chunk of consecutive chunk-kernel units
     bool open = false;
     int64_t ch_elems = 0, ch_units = 0;
@@ -178,6 +185,25 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         ch_elems += size; ch_units += 1;
         L.has_flat = true;
         L.flat_elems += size;
+        if (singles_ok && singles.size() + size <= single_cap) {
+          // element coordinates of this unit (same geometry as the chunk kernel)
+          int64_t cc = start_col;
+          for (int k = 0; k < size; k++) {
+            int64_t er = row, ec = start_col;
+            if (kind <= K_DELTA64) {
+              if (k) { uint64_t d = 0; memcpy(&d, ctl + (p - body) + (uint64_t)(k - 1) * delta, delta); cc += (int64_t)d; }
+              ec = cc;
+            } else if (kind == K_HORIZ) ec = start_col + (int64_t)k * delta;
+            else if (kind == K_VERT) er = row + (int64_t)k * delta;
+            else if (kind == K_DIAG) { er = row + (int64_t)k * delta; ec = start_col + (int64_t)k * delta; }
+            else if (kind == K_ADIAG) { er = row + (int64_t)k * delta; ec = start_col - (int64_t)k * delta; }
+            else if (kind == K_BROW) { er = row + k % (int)align; ec = start_col + k / (int)align; }
+            else { er = row + k / (int)align; ec = start_col + k % (int)align; }
+            singles.push_back(Single{er, ec, v + k});
+          }
+        } else {
+          singles_ok = false;
+        }
       } else {
         close_chunk(unit_off);   // the chunk kernel never sees table units
         XDesc d;
@@ -206,6 +232,32 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     }
     close_chunk(end);
     if (v != cp.nnz) return "ctl stream covers " + std::to_string(v) + " values, expected " + std::to_string(cp.nnz);
+    if (L.has_flat && singles_ok && (int64_t)singles.size() == L.flat_elems) {
+      // fold the few chunk-kernel elements into the table as diagonal units of one element
+      KindEntry ke{K_DIAG, 1};
+      auto key = std::make_pair(ke.kind_align, ke.delta);
+      auto it = kindex.find(key);
+      if (it == kindex.end()) { it = kindex.insert(std::make_pair(key, (uint32_t)out.ktab.size())).first; out.ktab.push_back(ke); }
+      for (const Single &sg : singles) {
+        XDesc d;
+        d.voff = (uint32_t)(L.val_base + (uint64_t)sg.v);
+        d.row = (int32_t)(cp.row_start + sg.row);
+        d.col = (int32_t)sg.col;
+        d.meta = it->second | (1u << 16) | ((uint32_t)K_DIAG << 24) | XD_DELTA1;
+        pend.push_back(Pending{(int64_t)pi, sg.row / TILE_ROWS, d});
+        if (m.symmetric) {
+          XDesc td = d;
+          td.meta |= XD_TRANSPOSED;
+          int64_t q = owner_of(sg.col);
+          if (q < 0) return "symmetric update targets a row that is not on this device";
+          const int64_t qt = (int64_t)CTA_THREADS * tile_rpt(m.parts[q].nrows, m.rows_per_thread);
+          pend.push_back(Pending{q, (sg.col - m.parts[q].row_start) / qt, td});
+        }
+      }
+      L.chunks.clear();
+      L.has_flat = false;
+      L.flat_elems = 0;
+    }
   }
   out.total_values = vbase;
   out.total_ctl = cbase;
