@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <string>
@@ -134,9 +135,11 @@ struct SpmvGatherOp {
 //   KSET_ANY    vertical / diagonal / anti-diagonal units of any stride, CSX-Sym images included
 //   KSET_DIAG1  only diagonal units of stride 1 (what the stencil matrices of the baseline configs encode to)
 // The kernel is bandwidth-bound and latency-sensitive: compiled for 8 resident CTAs per SM (32 registers).
+// VAR = 1 (4-rows-per-thread diagonal instantiation) issues the eight loads of a unit as one inline-PTX block so
+// that all of them are in flight before the first FMA; ptxas otherwise interleaves loads and FMAs at 32 registers.
 enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
-template <bool XD, bool SYM, int RPT, int KSET>
-__global__ void __launch_bounds__(CTA_THREADS, 8) csx_spmv_kernel(const __grid_constant__ PartDev P,
+template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __grid_constant__ PartDev P,
                                                                   const double *__restrict__ x,
                                                                   double *__restrict__ y, double alpha, double beta,
                                                                   int overwrite) {
@@ -172,6 +175,26 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) csx_spmv_kernel(const __grid_c
           // one base pointer per stream; the RPT rows of this lane sit at fixed 256-byte strides from it
           const double *__restrict__ vp = values + ((long long)d.x + t0);
           const double *__restrict__ xp = x + ((long long)(int)d.z + t0);
+          if (VAR == 1 && RPT == 4) {
+            // the eight loads of a unit as one block, so that all of them are in flight before the first FMA
+            double v0, v1, v2, v3, x0, x1, x2, x3;
+            asm volatile(
+                "{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                "setp.lt.u32 p0, %8, %12;\n\tsetp.lt.u32 p1, %9, %12;\n\tsetp.lt.u32 p2, %10, %12;\n\tsetp.lt.u32 p3, %11, %12;\n\t"
+                "mov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+                "mov.f64 %2, 0d0000000000000000;\n\tmov.f64 %3, 0d0000000000000000;\n\t"
+                "mov.f64 %4, 0d0000000000000000;\n\tmov.f64 %5, 0d0000000000000000;\n\t"
+                "mov.f64 %6, 0d0000000000000000;\n\tmov.f64 %7, 0d0000000000000000;\n\t"
+                "@p0 ld.global.nc.f64 %0, [%13];\n\t@p0 ld.global.nc.f64 %4, [%14];\n\t"
+                "@p1 ld.global.nc.f64 %1, [%13+256];\n\t@p1 ld.global.nc.f64 %5, [%14+256];\n\t"
+                "@p2 ld.global.nc.f64 %2, [%13+512];\n\t@p2 ld.global.nc.f64 %6, [%14+512];\n\t"
+                "@p3 ld.global.nc.f64 %3, [%13+768];\n\t@p3 ld.global.nc.f64 %7, [%14+768];\n\t}"
+                : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3), "=d"(x0), "=d"(x1), "=d"(x2), "=d"(x3)
+                : "r"((uint32_t)t0), "r"((uint32_t)(t0 + 32)), "r"((uint32_t)(t0 + 64)), "r"((uint32_t)(t0 + 96)), "r"(size),
+                  "l"(vp), "l"(xp));
+            acc[0] += v0 * x0; acc[1 % RPT] += v1 * x1; acc[2 % RPT] += v2 * x2; acc[3 % RPT] += v3 * x3;
+            continue;
+          }
           double v[RPT], xv[RPT];
 #pragma unroll
           for (int k = 0; k < RPT; k++) {
@@ -766,7 +789,10 @@ static void launch_gather(const PartDev &P, const PartLayout &pl, const double *
   // kernels are pre-compiled per (tile shape, unit-kind set) — the counterpart of the per-partition JIT (CsxJit.hpp)
   const bool diag1 = !SYM && pl.xd_diag1_only && !pl.xdesc.empty();
   if (pl.rpt == 4) {
-    if (diag1) launch_gather_k<SYM, 4, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
+    if (diag1) {  // the instantiation the stencil configs run: loads of a unit issued as one PTX block
+      dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
+      csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 1><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+    }
     else launch_gather_k<SYM, 4, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
   } else {
     if (diag1) launch_gather_k<SYM, 1, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
