@@ -45,7 +45,11 @@ void csxb_destroy(csxb_matrix_t *m);
 
 /* Matrix-level queries (spx_mat_get_nrows/ncols/nnz, src/api/matvec.c:447-476). */
 enum { CSXB_NROWS = 0, CSXB_NCOLS = 1, CSXB_NNZ = 2, CSXB_SYMMETRIC = 3, CSXB_NPARTS = 4,
-       CSXB_NPARTS_TOTAL = 5, CSXB_PART_LO = 6, CSXB_FULL_COLIND = 7 };
+       CSXB_NPARTS_TOTAL = 5, CSXB_PART_LO = 6, CSXB_FULL_COLIND = 7,
+       /* CSX-Sym with only some partitions local (valid after csxb_upload): rows [LO, HI) of y belong to
+        * other devices; csxb_spmv zeroes them and adds this device's transposed contributions there, the
+        * caller sends them to their owners and adds (sparsex_b200/dist.py: SymHaloReduce). */
+       CSXB_SYM_HALO_LO = 8, CSXB_SYM_HALO_HI = 9 };
 int64_t csxb_info(const csxb_matrix_t *m, int what);
 
 /* Per-partition CSX arrays == csx_matrix_t / csx_sym_matrix_t / map_t
@@ -89,7 +93,7 @@ int64_t csxb_traffic(const csxb_matrix_t *m, int what);
  *   overwrite != 0 : spx_matvec_mult semantics (y := alpha*A*x, beta ignored, CsxKernels.cpp:93)
  *   overwrite == 0 : spx_matvec_kernel semantics (y := alpha*A*x + beta*y, CsxSpmv.cpp:52-65)
  *   stream : cudaStream_t (NULL = default stream).  Asynchronous.
- * CSX-Sym matrices need every partition local (single GPU) in this version. */
+ * CSX-Sym with a partition range: see CSXB_SYM_HALO_LO/HI. */
 int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, double *d_y,
               int overwrite, void *stream);
 

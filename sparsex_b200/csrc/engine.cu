@@ -535,6 +535,7 @@ struct csxb_matrix {
   double *d_values = nullptr;
   double *d_x = nullptr, *d_y = nullptr;   // staging for csxb_spmv_host
   int64_t covered_rows_end = 0;
+  int64_t sym_halo_lo = 0, sym_halo_hi = 0;   // CSX-Sym, partial device: rows of other devices this one adds into
   int64_t bytes[7] = {0, 0, 0, 0, 0, 0, 0};
   std::vector<std::string> logs;
   ~csxb_matrix() {
@@ -621,6 +622,8 @@ int64_t csxb_info(const csxb_matrix_t *m, int what) {
     case CSXB_NPARTS_TOTAL: return m->host.nparts_total;
     case CSXB_PART_LO: return m->host.part_lo;
     case CSXB_FULL_COLIND: return m->host.full_colind;
+    case CSXB_SYM_HALO_LO: return m->sym_halo_lo;
+    case CSXB_SYM_HALO_HI: return m->sym_halo_hi;
   }
   return -1;
 }
@@ -693,8 +696,6 @@ extern "C" {
 
 int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
   if (m->uploaded) return fail("matrix already uploaded");
-  if (m->host.symmetric && (int)m->host.parts.size() != m->host.nparts_total)
-    return fail("CSX-Sym needs all partitions on one device in this version");
   // CSX-Sym: a partition owns dvalues.size() rows (SparsePartitionSym::GetNrRows, SparsePartition.hpp:420-423)
   CsxMatrix &H = m->host;
   std::vector<int64_t> saved_nrows;
@@ -752,6 +753,12 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
     if (free_host) std::vector<double>().swap(hp.values);
   }
+  if (H.symmetric && (int)H.parts.size() != H.nparts_total && !H.parts.empty()) {
+    // transposed updates of the local lower triangle reach rows [col_min, first local row) of lower ranks
+    int64_t first_row = H.parts.front().row_start, lo = first_row;
+    for (auto &p : H.parts) if (p.col_max >= p.col_min) lo = std::min(lo, p.col_min);
+    m->sym_halo_lo = lo; m->sym_halo_hi = first_row;
+  }
   m->bytes[CSXB_B_VALUES] = nnz_stored * 8;
   m->bytes[CSXB_B_CTL] = ctl_bytes;
   m->bytes[CSXB_B_TABLES] = tables;
@@ -806,6 +813,8 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
   cudaStream_t s = (cudaStream_t)stream;
   const bool sym = m->host.symmetric;
+  if (m->sym_halo_hi > m->sym_halo_lo)   // halo rows owned by other devices: start from zero, the caller reduces them
+    CUDA_TRY(cudaMemsetAsync(d_y + m->sym_halo_lo, 0, (size_t)(m->sym_halo_hi - m->sym_halo_lo) * 8, s));
   // kernel 1 of every partition first: it initialises y, and under CSX-Sym the chunk kernel of one
   // partition adds into rows that another partition owns
   for (size_t i = 0; i < m->pdev.size(); i++) {

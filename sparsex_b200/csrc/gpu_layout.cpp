@@ -169,7 +169,11 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       if (row + span >= cp.nrows) return "cross-row unit leaves its partition";
       if (cmin < 0 || cmax >= cp.ncols) return "unit leaves the column range";
 
-      if (!goes_to_xdt(kind, size)) {
+      // CSX-Sym with only some partitions on this device: a unit whose transposed image reaches rows of
+      // another device cannot be gathered by a local owner; the chunk kernel adds it to those rows of the
+      // local y instead and the caller reduces the halo across devices.
+      const bool image_local = !m.symmetric || (owner_of(cmin) >= 0 && owner_of(cmax) >= 0);
+      if (!goes_to_xdt(kind, size) || !image_local) {
         // chunk kernel: extend the open chunk or start a new one at this unit
         uint64_t ubytes = p - unit_off;
         if (open && (ch_elems + size > CHUNK_MAX_ELEMS || ch_units + 1 > CHUNK_MAX_UNITS ||
@@ -185,7 +189,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         ch_elems += size; ch_units += 1;
         L.has_flat = true;
         L.flat_elems += size;
-        if (singles_ok && singles.size() + size <= single_cap) {
+        if (singles_ok && image_local && singles.size() + size <= single_cap) {
           // element coordinates of this unit (same geometry as the chunk kernel)
           int64_t cc = start_col;
           for (int k = 0; k < size; k++) {

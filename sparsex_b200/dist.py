@@ -89,3 +89,34 @@ class WindowExchange(object):
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         return buf
+
+
+class SymHaloReduce(object):
+    """CSX-Sym across devices: rank r's lower triangle also updates rows [halo_lo_r, halo_hi_r) that lower ranks
+    own (csxb_info CSXB_SYM_HALO_LO/HI).  After the local SpMV every rank sends those slices of its y to their
+    owners, which add them to their own rows — the cross-device form of the reference's local-buffer + map
+    reduction (CsxSpmv.cpp:37-50, Vector.cpp:291-299).  One grouped NCCL launch plus one add per neighbour."""
+
+    def __init__(self, ranges, halos, rank, like):
+        self.rank, self.send, self.recv = rank, [], []
+        for r, (hlo, hhi) in enumerate(halos):       # sender r
+            for q, (qlo, qn) in enumerate(ranges):   # owner q
+                if q == r or qn == 0:
+                    continue
+                lo, hi = max(hlo, qlo), min(hhi, qlo + qn)
+                if hi <= lo:
+                    continue
+                if r == rank:
+                    self.send.append((q, lo, hi))
+                if q == rank:
+                    self.recv.append((r, lo, hi, torch.zeros(hi - lo, dtype=like.dtype, device=like.device)))
+
+    def __call__(self, y):
+        ops = [dist.P2POp(dist.isend, y[lo:hi], peer) for peer, lo, hi in self.send]
+        ops += [dist.P2POp(dist.irecv, tmp, peer) for peer, lo, hi, tmp in self.recv]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for _, lo, hi, tmp in self.recv:
+            y[lo:hi] += tmp
+        return y

@@ -64,3 +64,63 @@ def test_partition_per_rank_and_piece_exchange(world, sym):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _sym_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sparsex_b200 import CsxMatrix
+        from sparsex_b200.dist import SymHaloReduce, gather_row_ranges
+        from tests.matrices import sym_block_banded
+        rp, ci, va, n = sym_block_banded(600, b=12)
+        opts = {"spx.rt.nr_threads": world, "spx.matrix.symmetric": "true"}
+        A = CsxMatrix.tune_csr(rp, ci, va, n, n, opts, part_lo=rank, part_hi=rank + 1)
+        P = A.partition(0)
+        lo, cnt = P.row_start, len(P.dvalues)
+        ranges = gather_row_ranges(lo, cnt, "cpu")
+        # what the device kernels produce for this rank, computed here from the lower triangle of its rows:
+        # own rows get a_ij x_j (j <= i), every column j < i gets the transposed a_ij x_i
+        x = np.random.default_rng(3).uniform(-1, 1, n)
+        y = np.zeros(n)
+        col_min = lo
+        for i in range(lo, lo + cnt):
+            for k in range(rp[i], rp[i + 1]):
+                j = ci[k]
+                if j > i:
+                    continue
+                y[i] += va[k] * x[j]
+                if j < i:
+                    y[j] += va[k] * x[i]
+                    col_min = min(col_min, j)
+        halo = torch.tensor([col_min, lo], dtype=torch.int64)
+        allh = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allh, halo)
+        halos = [(int(t[0]), int(t[1])) for t in allh]
+        yt = torch.from_numpy(y)
+        SymHaloReduce(ranges, halos, rank, yt)(yt)
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        yref = np.zeros(n)
+        np.add.at(yref, rows, va * x[ci])
+        assert np.abs(yt.numpy()[lo:lo + cnt] - yref[lo:lo + cnt]).max() < 1e-12
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL %r" % (e,)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_symmetric_halo_reduce(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world * 11 + os.getpid() % 200
+    procs = [ctx.Process(target=_sym_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

@@ -229,3 +229,39 @@ def test_sym_block_banded(opts):
 def test_rmat(opts):
     rp, ci, va, n = rmat(14)
     check_matrix(rp, ci, va, n, n, opts)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_symmetric_partition_per_device(world):
+    """CSX-Sym with one partition per device (all on cuda:0 here): every logical rank computes its own rows plus
+    its transposed contributions to the halo rows of lower ranks; summing the halos reproduces y = A x."""
+    torch = _torch()
+    from oracle.pyoracle import OracleMatrix
+    from sparsex_b200 import CsxMatrix, lib
+    rng = np.random.default_rng(world)
+    cases = [sym_block_banded(3000, b=40)[:3] + (9000,), random_structured(rng, 1500, 1500, symmetric=True) + (1500,)]
+    for rp, ci, va, n in cases:
+        for xf in ("all", "none", "d,v,ad", "br,bc"):
+            opts = {"spx.matrix.symmetric": "true", "spx.rt.nr_threads": world, "spx.preproc.xform": xf}
+            O = OracleMatrix.from_csr(rp, ci, va, n, n).tune(dict(opts, **{"oracle.undefined_sampling": "break"}))
+            x = rng.uniform(-1, 1, n)
+            yref = O.spmv(0.5, x)
+            dx = torch.from_numpy(x).cuda()
+            total = np.zeros(n)
+            for r in range(world):
+                A = CsxMatrix.tune_csr(rp, ci, va, n, n, opts, part_lo=r, part_hi=r + 1)
+                assert np.array_equal(A.partition(0).ctl, O.parts[r].ctl)
+                A.upload(0)
+                P = A.partition(0)
+                lo, cnt = P.row_start, len(P.dvalues)
+                hlo, hhi = lib().csxb_info(A._h, 8), lib().csxb_info(A._h, 9)
+                assert hhi == lo or hlo == hhi == 0 or r == 0
+                dy = torch.full((n,), 7.0, dtype=torch.float64, device="cuda")   # stale content must not leak
+                A.spmv(0.5, dx, dy, overwrite=True)
+                y = dy.cpu().numpy()
+                total[lo:lo + cnt] += y[lo:lo + cnt]
+                if hhi > hlo:
+                    total[hlo:hhi] += y[hlo:hhi]
+                A.close()
+            bound = _abs_bound(rp, ci, va, x, n) + 1e-300
+            assert np.max(np.abs(total - yref) / (0.5 * bound)) <= TOL, (world, xf, O.log)
