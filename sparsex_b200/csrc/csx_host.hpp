@@ -45,6 +45,7 @@ struct TuneOptions {
   bool build_rows_info = true;     // spx.b200.rows_info : keep the per-row table of Csx.hpp:29-35
   int host_threads = 0;            // spx.b200.host_threads : 0 = hardware concurrency
   int rows_per_thread = 0;         // spx.b200.rows_per_thread : GPU tile shape, 0 = by partition size, else 1 or 4
+  int slice_elems = 0;             // spx.b200.slice : elements one lane of the chunk kernel handles, 0 = from the unit mix
   // Returns "" or an error message.  Unknown mnemonics are an error
   // (Runtime.hpp:108-134 logs and ignores; the C API layer downgrades this to a warning).
   std::string set(const std::string &mnemonic, const std::string &value);
@@ -71,6 +72,7 @@ struct CsxMatrix {
   int64_t nrows = 0, ncols = 0, nnz = 0;   // nnz = input non-zeros (full matrix also when symmetric)
   bool symmetric = false, full_colind = false;
   int rows_per_thread = 0;                 // requested GPU tile shape (0 = automatic)
+  int slice_elems = 0;                     // requested chunk-kernel slice length (0 = automatic)
   int nparts_total = 0;                    // partitions the matrix was split into
   int part_lo = 0;                         // parts[k] is global partition part_lo + k
   std::vector<CsxPartition> parts;

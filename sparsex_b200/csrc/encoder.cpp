@@ -1064,6 +1064,7 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
     out.symmetric = opt.symmetric; out.full_colind = opt.full_colind;
     out.nparts_total = np; out.part_lo = part_lo;
     out.rows_per_thread = opt.rows_per_thread;
+    out.slice_elems = opt.slice_elems;
     out.parts.resize(part_hi - part_lo);
     bool sym = opt.symmetric;
     if (sym && nrows != ncols) throw TuneError("spx.matrix.symmetric requires a square matrix");
@@ -1166,6 +1167,10 @@ std::string TuneOptions::set(const std::string &k, const std::string &v) {
     else if (k == "spx.b200.rows_per_thread") {
       rows_per_thread = std::stoi(v);
       if (rows_per_thread != 0 && rows_per_thread != 1 && rows_per_thread != 4) return "spx.b200.rows_per_thread must be 0, 1 or 4";
+    }
+    else if (k == "spx.b200.slice") {
+      slice_elems = std::stoi(v);
+      if (slice_elems != 0 && (slice_elems < 4 || slice_elems > 32)) return "spx.b200.slice must be 0 or 4..32";
     }
     else return "unknown option \"" + k + "\"";
   } catch (std::exception &) {

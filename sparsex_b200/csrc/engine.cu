@@ -28,33 +28,7 @@
 #include "../../include/csx_b200.h"
 #include "csx_host.hpp"
 #include "gpu_layout.hpp"
-
-using namespace spxb;
-
-// ------------------------------------------------------------ device side --
-struct PartDev {
-  const uint8_t *ctl;          // this partition's ctl bytes (16-byte aligned, CTL_PAD readable bytes behind)
-  const double *values;        // device-wide values array
-  const ChunkEntry *chunks;    // chunk kernel entry points
-  const uint32_t *tile_xoff;
-  const uint4 *xdesc;
-  const KindEntry *ktab;
-  const double *dvalues;       // CSX-Sym: diagonal of the owned rows
-  long long nrows, row_start;  // owned rows
-  uint32_t val_base;
-  uint32_t nchunks;
-  int full_colind;
-  int rpt;                     // rows per thread: a tile has CTA_THREADS * rpt rows
-  KindEntry idtab[64];
-};
-
-constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
-}
+#include "chunk_kernel.cuh"
 
 // Table units are vertical / diagonal / anti-diagonal runs (gpu_layout.hpp: goes_to_xdt).
 // Op::add(device-wide value index, x index) for every element of descriptor d that contributes to `myrow`.
@@ -241,259 +215,27 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __gri
   }
 }
 
-// ---- kernel 2: chunk kernel ------------------------------------------------------------------------
-// One warp = one chunk of the ctl stream (gpu_layout.hpp).  Handles every unit that is not in the table:
-// delta8/16/32/64 and horizontal units (delta_tmpl.c, horiz_tmpl.c), block-row / block-column units
-// (block_row_tmpl.c, block_col_tmpl.c) and short vertical / diagonal / anti-diagonal units, plus their
-// CSX-Sym transposed updates (*_sym_tmpl.c).  Runs after kernel 1 on the same stream and adds into y.
-constexpr int CHUNK_WARPS = 4;
-struct ChunkSmem {
-  uint4 raw[(CHUNK_MAX_BYTES + 32) / 16];   // staged ctl bytes (16-byte aligned copy window)
-  uint4 units[CHUNK_MAX_UNITS];             // parsed unit heads
-  uint16_t upos[CHUNK_MAX_UNITS + 2];       // byte offset of every unit head
-  uint8_t map[CHUNK_MAX_ELEMS];             // element -> unit
-};
-
-__device__ __forceinline__ uint64_t smem_varint(const uint8_t *c, uint32_t &pos) {  // CtlUtil.hpp:110-133
-  uint64_t v = 0;
-  unsigned shift = 0;
-  for (;;) {
-    uint32_t b = c[pos++];
-    v |= (uint64_t)(b & 0x7f) << shift;
-    if (!(b & 0x80)) break;
-    shift += 7;
-  }
-  return v;
-}
-
-// F::fetch(active, value index within the partition, partition-relative row, column) returns the lane's product,
-// F::reduce(active, row, product) folds a 32-element round into y (both warp-uniform calls), F::finish() ends the chunk.
-template <class F>
-__device__ __forceinline__ void process_chunk(const PartDev &P, const ChunkEntry ce, ChunkSmem &S, int lane, F &f) {
-  // 1. stage the chunk's ctl bytes: 16-byte coalesced copies of the aligned window that contains them
-  const uint8_t *g = P.ctl + ce.ctl_off;
-  const uint32_t nbytes = ce.pad;
-  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
-  const uint4 *src = reinterpret_cast<const uint4 *>(g - mis);
-  for (uint32_t i = lane; i * 16 < mis + nbytes; i += 32) S.raw[i] = __ldg(src + i);
-  __syncwarp();
-  const uint8_t *c = reinterpret_cast<const uint8_t *>(S.raw) + mis;
-
-  // 2a. unit boundaries: the only serial part (a unit's length is known only after its head is read).
-  //     Every lane runs the same scalar code; a 4-byte window covers flags, size and the common 1-2 byte column varint.
-  const uint32_t *cw = reinterpret_cast<const uint32_t *>(S.raw);   // word view for 4-byte unaligned reads
-  uint32_t pos = 0, nu = 0;
-  while (pos < nbytes) {
-    if (lane == 0) S.upos[nu] = (uint16_t)pos;
-    const uint32_t bp = mis + pos;
-    const uint32_t w4 = __funnelshift_r(cw[bp >> 2], cw[(bp >> 2) + 1], (bp & 3) * 8);
-    const uint32_t flags = w4 & 0xff, size = (w4 >> 8) & 0xff;
-    uint32_t q = pos + 2;
-    if (!(flags & 0x40) && !P.full_colind && (w4 & 0x80800000u) != 0x80800000u) q += 1 + ((w4 >> 23) & 1);
-    else {
-      if (flags & 0x40) smem_varint(c, q);
-      if (P.full_colind) q += 4; else smem_varint(c, q);
-    }
-    const KindEntry ke = P.idtab[flags & 0x3f];
-    if ((ke.kind_align & 0xff) <= K_DELTA64) q += (size - 1) * ke.delta;   // fixed-width delta body
-    pos = q;
-    nu++;
-  }
-  __syncwarp();
-
-  // 2b. unit records, one unit per lane: full head decode, rows and element offsets by warp prefix sums
-  uint32_t ne = 0;
-  int row_base = ce.row;
-  for (uint32_t u0 = 0; u0 < nu; u0 += 32) {
-    const uint32_t u = u0 + lane;
-    uint32_t size = 0, rowinc = 0, rec_x = 0, rec_y = 0, inc0 = 0;
-    if (u < nu) {
-      uint32_t p = S.upos[u];
-      const uint32_t flags = c[p];
-      size = c[p + 1];
-      p += 2;
-      const bool nr = (flags & 0x80) != 0;
-      if (nr) {  // csx_spmv_tmpl.c:86-91; the entry unit's row comes from the table
-        uint32_t jmp = 1;
-        if (flags & 0x40) jmp = (uint32_t)smem_varint(c, p);
-        if (u != 0) rowinc = jmp;
-      }
-      uint32_t ucol;
-      if (P.full_colind) { ucol = c[p] | (c[p + 1] << 8) | (c[p + 2] << 16) | ((uint32_t)c[p + 3] << 24); p += 4; }
-      else ucol = (uint32_t)smem_varint(c, p);   // modulo 2^32 == modulo 2^64 truncated (negative ucol)
-      const KindEntry ke = P.idtab[flags & 0x3f];
-      const uint32_t kind = ke.kind_align & 0xff, align = (ke.kind_align >> 8) & 0xff;
-      const bool reset = u == 0 || nr || P.full_colind;    // column cursor restarts at this unit
-      inc0 = (u == 0 && !P.full_colind) ? ce.cursor + ucol : ucol;
-      rec_x = (size << 11) | (kind << 19) | ((uint32_t)reset << 23) | (align << 24);
-      rec_y = p | (ke.delta << 12);
-    }
-    // inclusive scans over the 32 units: element offsets and row numbers
-    uint32_t es = size, rs = rowinc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t a = __shfl_up_sync(FULL, es, o), b = __shfl_up_sync(FULL, rs, o);
-      if (lane >= o) { es += a; rs += b; }
-    }
-    if (u < nu) {
-      const uint32_t estart = ne + es - size;
-      S.units[u] = make_uint4(rec_x | estart, rec_y, inc0, (uint32_t)(row_base + (int)rs));
-      for (uint32_t k = 0; k < size; k++) S.map[estart + k] = (uint8_t)u;
-    }
-    ne += __shfl_sync(FULL, es, 31);
-    row_base += (int)__shfl_sync(FULL, rs, 31);
-  }
-  __syncwarp();
-
-  // 3. decode 64 elements per iteration (two independent 32-element rounds: their loads overlap)
-  uint32_t carry = 0;
-  for (uint32_t e0 = 0; e0 < ne; e0 += 64) {
-    uint32_t cur[2], flag[2], kind[2], delta[2], align[2], jj[2];
-    int row_e[2];
-    bool active[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const uint32_t idx = e0 + h * 32 + lane;
-      active[h] = idx < ne;
-      uint32_t inc = 0;
-      flag[h] = 1; kind[h] = 0; delta[h] = 0; align[h] = 1; jj[h] = 0; row_e[h] = -1 - h;
-      if (active[h]) {
-        const uint4 u = S.units[S.map[idx]];
-        const uint32_t j = idx - (u.x & 0x7ff);
-        jj[h] = j;
-        kind[h] = (u.x >> 19) & 0xf; align[h] = (u.x >> 24) & 0xf;
-        delta[h] = u.y >> 12;
-        row_e[h] = (int)u.w;
-        flag[h] = 0;
-        if (j == 0) { inc = u.z; flag[h] = (u.x >> 23) & 1; }
-        else if (kind[h] <= K_DELTA64) {   // little-endian fixed-width delta; low 32 bits suffice
-          const uint8_t *b = c + (u.y & 0xfff) + (j - 1) * delta[h];
-          inc = b[0];
-          if (delta[h] >= 2) inc |= (uint32_t)b[1] << 8;
-          if (delta[h] >= 4) inc |= ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
-        } else if (kind[h] == K_HORIZ) inc = delta[h];
-      }
-      cur[h] = inc;
-    }
-    // segmented inclusive prefix sums of the cursor increments (segments start where the cursor restarts)
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const uint32_t tv = __shfl_up_sync(FULL, cur[h], o), tf = __shfl_up_sync(FULL, flag[h], o);
-        if (lane >= o) { if (!flag[h]) cur[h] += tv; flag[h] |= tf; }
-      }
-    }
-    if (!flag[0]) cur[0] += carry;
-    carry = __shfl_sync(FULL, cur[0], 31);
-    if (!flag[1]) cur[1] += carry;
-    carry = __shfl_sync(FULL, cur[1], 31);
-    // element coordinates from the unit geometry (cursor = unit start for substructures)
-    uint32_t col_e[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const uint32_t j = jj[h];
-      col_e[h] = cur[h];
-      if (kind[h] == K_VERT) row_e[h] += (int)(j * delta[h]);
-      else if (kind[h] == K_DIAG) { row_e[h] += (int)(j * delta[h]); col_e[h] += j * delta[h]; }
-      else if (kind[h] == K_ADIAG) { row_e[h] += (int)(j * delta[h]); col_e[h] -= j * delta[h]; }
-      else if (kind[h] == K_BROW) { row_e[h] += (int)(j % align[h]); col_e[h] += j / align[h]; }   // column-major values
-      else if (kind[h] == K_BCOL) { row_e[h] += (int)(j / align[h]); col_e[h] += j % align[h]; }   // row-major values
-    }
-    const double p0 = f.fetch(active[0], ce.val_off + e0 + lane, row_e[0], col_e[0]);
-    const double p1 = f.fetch(active[1], ce.val_off + e0 + 32 + lane, row_e[1], col_e[1]);
-    f.reduce(active[0], row_e[0], p0);
-    if (e0 + 32 < ne) f.reduce(active[1], row_e[1], p1);
-  }
-  f.finish();
-}
-
 template <bool SYM>
-struct SpmvChunkOp {
-  const double *__restrict__ values;  // partition base applied
-  const double *__restrict__ x;
-  double *__restrict__ y;
-  long long row_start;
-  double alpha;
-  int lane;
-  int run_row;      // row whose products are being accumulated lane-wise (-1: none)
-  double run_acc;
-  __device__ __forceinline__ void flush() {
-    if (run_row >= 0) {
-      const double s = warp_sum(run_acc);
-      if (lane == 0) atomicAdd(y + row_start + run_row, alpha * s);
-    }
-    run_row = -1; run_acc = 0.0;
-  }
-  __device__ __forceinline__ double fetch(bool active, uint32_t vi, int row, uint32_t col) {
-    double p = 0.0;
-    if (active) {
-      const double v = __ldg(values + vi);
-      p = v * __ldg(x + col);
-      if (SYM) atomicAdd(y + col, alpha * v * __ldg(x + row_start + row));   // transposed update
-    }
-    return p;
-  }
-  __device__ __forceinline__ void reduce(bool active, int row, double p) {
-    // whole round in one row (long rows): keep lane-wise partial sums, reduce once per row
-    const int row0 = __shfl_sync(FULL, row, 0);
-    if (__all_sync(FULL, row == row0)) {
-      if (row0 != run_row) { flush(); run_row = row0; }
-      run_acc += p;
-      return;
-    }
-    flush();
-    // segmented sum over runs of equal rows; the last lane of a run adds it to y
-    const int prev = __shfl_up_sync(FULL, row, 1), next = __shfl_down_sync(FULL, row, 1);
-    uint32_t flag = (lane == 0) || (prev != row);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double tv = __shfl_up_sync(FULL, p, o);
-      const uint32_t tf = __shfl_up_sync(FULL, flag, o);
-      if (lane >= o) { if (!flag) p += tv; flag |= tf; }
-    }
-    if (active && (lane == 31 || next != row)) atomicAdd(y + row_start + row, alpha * p);
-  }
-  __device__ __forceinline__ void finish() { flush(); }
-};
-
-template <bool SYM>
-__global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_chunk_kernel(const __grid_constant__ PartDev P,
+__global__ void __launch_bounds__(CHUNK_WARPS * 32, 9) csx_chunk_kernel(const __grid_constant__ PartDev P,
                                                                      const double *__restrict__ x,
                                                                      double *__restrict__ y, double alpha) {
   __shared__ ChunkSmem smem[CHUNK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
   if (ch >= P.nchunks) return;
-  const unsigned long long *q = reinterpret_cast<const unsigned long long *>(P.chunks + ch);   // 24-byte entries
-  const unsigned long long a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
-  ChunkEntry ce;
-  ce.ctl_off = a0; ce.val_off = (uint32_t)a1; ce.cursor = (uint32_t)(a1 >> 32);
-  ce.row = (int32_t)(uint32_t)a2; ce.pad = (uint32_t)(a2 >> 32);
-  SpmvChunkOp<SYM> op{P.values + P.val_base, x, y, P.row_start, alpha, lane, -1, 0.0};
-  process_chunk(P, ce, smem[warp], lane, op);
+  SpmvChunkOp<SYM> op;
+  op.x = x; op.y = y; op.vals = smem[warp].vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
+  process_chunk(P, ch, smem[warp], lane, op);
 }
 
-// Parity aid: the same traversals, storing the decoded coordinates per value (csxb_decode_coords).
-struct DecodeChunkOp {
-  int *rows, *cols;   // partition base applied
-  long long row_start;
-  __device__ __forceinline__ double fetch(bool active, uint32_t vi, int row, uint32_t col) {
-    if (active) { rows[vi] = (int)(row_start + row); cols[vi] = (int)col; }
-    return 0.0;
-  }
-  __device__ __forceinline__ void reduce(bool, int, double) {}
-  __device__ __forceinline__ void finish() {}
-};
 __global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_decode_chunk_kernel(const __grid_constant__ PartDev P, int *rows,
                                                                             int *cols) {
   __shared__ ChunkSmem smem[CHUNK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
   if (ch >= P.nchunks) return;
-  const ChunkEntry ce = P.chunks[ch];
-  DecodeChunkOp op{rows + P.val_base, cols + P.val_base, P.row_start};
-  process_chunk(P, ce, smem[warp], lane, op);
+  DecodeChunkOp op{rows + P.val_base, cols + P.val_base, P.row_start, 0};
+  process_chunk(P, ch, smem[warp], lane, op);
 }
 struct DecodeGatherOp {
   int *rows, *cols;   // device-wide
@@ -730,8 +472,10 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     if (!hp.ctl.empty()) CUDA_TRY(cudaMemcpy((uint8_t *)dc + pl.ctl_base, hp.ctl.data(), hp.ctl.size(), cudaMemcpyHostToDevice));
     P.ctl = (const uint8_t *)dc + pl.ctl_base;
     P.values = m->d_values;
-    uint32_t *tx = nullptr; XDesc *xd = nullptr; ChunkEntry *ch = nullptr;
+    uint32_t *tx = nullptr; XDesc *xd = nullptr; ChunkEntry *ch = nullptr; uint16_t *uo = nullptr;
     if (dev_copy(m, pl.chunks.data(), pl.chunks.size(), &ch)) return -1;
+    if (dev_copy(m, pl.uoffs.data(), pl.uoffs.size(), &uo)) return -1;
+    P.uoffs = uo;
     if (dev_copy(m, pl.tile_xoff.data(), pl.tile_xoff.size(), &tx)) return -1;
     if (dev_copy(m, pl.xdesc.data(), pl.xdesc.size(), &xd)) return -1;
     P.chunks = ch; P.nchunks = (uint32_t)pl.chunks.size();
@@ -748,7 +492,7 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
     nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
-    tables += (int64_t)pl.chunks.size() * (int64_t)sizeof(ChunkEntry);
+    tables += (int64_t)pl.chunks.size() * (int64_t)sizeof(ChunkEntry) + (int64_t)pl.uoffs.size() * 2;
     if (pl.nrows) launches += 1 + (pl.chunks.empty() ? 0 : 1);
     m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
     if (free_host) std::vector<double>().swap(hp.values);

@@ -57,6 +57,76 @@ struct Pending { int64_t part; int64_t tile; XDesc d; };
 // rows per thread of a partition's tiles (a later partition's value is needed while an earlier one is decoded)
 inline int tile_rpt(int64_t nrows, int forced) { return forced ? forced : (nrows >= (int64_t(1) << 20) ? 4 : 1); }
 
+// Walks the unit heads once and picks the slice length of the chunk kernel for this partition: every lane of
+// a warp handles one slice per round, a round lasts as long as its longest slice, and every slice carries a
+// fixed cost (setup, cursor scan, row reduction) of about C0 loop iterations.
+std::string choose_slice(const CsxPartition &cp, const CsxMatrix &m, size_t nid, PartLayout &L) {
+  std::vector<uint64_t> hist(64 * 256, 0);
+  const uint8_t *ctl = cp.ctl.data();
+  uint64_t p = 0, end = cp.ctl.size();
+  while (p < end) {
+    if (p + 2 > end) return "ctl stream truncated";
+    const uint8_t flags = ctl[p++], size = ctl[p++];
+    if ((flags & 0x80) && (flags & 0x40)) get_varint(ctl, p);
+    if (m.full_colind) p += 4; else get_varint(ctl, p);
+    const uint32_t id = flags & 0x3f;
+    if (id >= nid) return "ctl stream uses an unmapped unit id";
+    const uint32_t kind = L.idtab[id].kind_align & 0xff;
+    if (size == 0) return "ctl unit of size 0";
+    if (kind <= K_DELTA64) p += (uint64_t)(size - 1) * L.idtab[id].delta;
+    if (p > end) return "ctl stream truncated";
+    if (!goes_to_xdt(kind, size)) hist[id * 256 + size]++;
+  }
+  static const int cand[] = {4, 8, 12, 16, 24, 32};
+  const double C0 = 12.0;
+  int best = 16;
+  double best_cost = -1.0;
+  for (int S : cand) {
+    if (m.slice_elems && S != cand[0]) break;
+    if (m.slice_elems) S = m.slice_elems;
+    IdEntry tab[64];
+    for (size_t id = 0; id < nid; id++) {
+      tab[id] = L.idtab[id];
+      const uint32_t kind = tab[id].kind_align & 0xff, align = (tab[id].kind_align >> 8) & 0xff;
+      uint32_t sl = (kind == K_BROW || kind == K_BCOL) ? std::max<uint32_t>(1, (uint32_t)S / align) : (uint32_t)S;
+      tab[id].sl = sl;
+      tab[id].recip = (65536 + sl - 1) / sl;
+    }
+    double slices = 0.0;
+    std::vector<std::pair<uint32_t, double>> lens;   // (slice length, number of such slices)
+    for (size_t id = 0; id < nid; id++) {
+      const uint32_t kind = tab[id].kind_align & 0xff, align = (tab[id].kind_align >> 8) & 0xff;
+      for (uint32_t size = 1; size < 256; size++) {
+        const uint64_t n = hist[id * 256 + size];
+        if (!n) continue;
+        const uint32_t nsl = unit_slices(kind, size, tab[id].delta, tab[id]);
+        const uint32_t len = (kind == K_BROW || kind == K_BCOL) ? std::min<uint32_t>(size, tab[id].sl * align)
+                                                               : std::min<uint32_t>(size, tab[id].sl);
+        slices += (double)n * nsl;
+        lens.push_back(std::make_pair(len, (double)n * nsl));
+      }
+    }
+    // longest slice among those that are not rare (a round is as long as its longest slice)
+    std::sort(lens.begin(), lens.end());
+    double tail = 0.0;
+    uint32_t lmax = 1;
+    for (size_t i = lens.size(); i-- > 0;) {
+      tail += lens[i].second;
+      if (tail >= 0.02 * slices) { lmax = lens[i].first; break; }
+    }
+    const double cost = slices * (C0 + (double)((lmax + 3) / 4 * 4));
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = S; }
+  }
+  L.slice = best;
+  for (size_t id = 0; id < nid; id++) {
+    const uint32_t kind = L.idtab[id].kind_align & 0xff, align = (L.idtab[id].kind_align >> 8) & 0xff;
+    const uint32_t sl = (kind == K_BROW || kind == K_BCOL) ? std::max<uint32_t>(1, (uint32_t)best / align) : (uint32_t)best;
+    L.idtab[id].sl = sl;
+    L.idtab[id].recip = (65536 + sl - 1) / sl;
+  }
+  return "";
+}
+
 }  // namespace
 
 std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
@@ -95,7 +165,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       if (nid >= 64) return "too many unit kinds";
       KindEntry ke;
       if (!classify(cp.id_map[nid], ke)) return "unsupported pattern id " + std::to_string(cp.id_map[nid]);
-      L.idtab[nid] = ke;
+      L.idtab[nid] = IdEntry{ke.kind_align, ke.delta, 1, 65536};
       auto key = std::make_pair(ke.kind_align, ke.delta);
       auto it = kindex.find(key);
       if (it == kindex.end()) {
@@ -110,6 +180,8 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     uint64_t p = 0, end = cp.ctl.size();
     int64_t row = 0, col = 0, v = 0;
     bool first = true;
+    std::string serr = choose_slice(cp, m, nid, L);
+    if (!serr.empty()) return serr;
     // A partition whose chunk-kernel share is tiny (stencil matrices: a few boundary elements next to
     // millions of diagonal units) gets those elements as one-element table units instead; that saves the
     // second kernel launch.  Coordinates are collected while the share stays under the cap.
@@ -119,10 +191,13 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     bool singles_ok = true;
     // open chunk of consecutive chunk-kernel units
     bool open = false;
-    int64_t ch_elems = 0, ch_units = 0;
+    int64_t ch_elems = 0, ch_units = 0, ch_slices = 0;
     uint64_t ch_start = 0;
     auto close_chunk = [&](uint64_t at) {
-      if (open) { L.chunks.back().pad = (uint32_t)(at - ch_start); open = false; }
+      if (open) {
+        L.chunks.back().counts = (uint32_t)(at - ch_start) | ((uint32_t)ch_elems << 12) | ((uint32_t)ch_units << 22);
+        open = false;
+      }
     };
     while (p < end) {
       uint64_t unit_off = p;
@@ -176,17 +251,22 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       if (!goes_to_xdt(kind, size) || !image_local) {
         // chunk kernel: extend the open chunk or start a new one at this unit
         uint64_t ubytes = p - unit_off;
+        const int64_t nsl = unit_slices(kind, size, delta, L.idtab[id]);
         if (open && (ch_elems + size > CHUNK_MAX_ELEMS || ch_units + 1 > CHUNK_MAX_UNITS ||
+                     ch_slices + nsl > CHUNK_MAX_SLICES ||
                      (unit_off - ch_start) + ubytes > (uint64_t)CHUNK_MAX_BYTES))
           close_chunk(unit_off);
         if (!open) {
+          if (ubytes > (uint64_t)CHUNK_MAX_BYTES || nsl > CHUNK_MAX_SLICES) return "ctl unit exceeds the chunk limits";
+          if (L.uoffs.size() >= 0xffffffffull) return "unit-offset table too large";
           ChunkEntry ce;
           ce.ctl_off = unit_off; ce.val_off = (uint32_t)v; ce.cursor = (uint32_t)cursor_before;
-          ce.row = (int32_t)row; ce.pad = 0;
+          ce.row = (int32_t)row; ce.counts = 0; ce.uoff = (uint32_t)L.uoffs.size(); ce.pad = 0;
           L.chunks.push_back(ce);
-          open = true; ch_elems = 0; ch_units = 0; ch_start = unit_off;
+          open = true; ch_elems = 0; ch_units = 0; ch_slices = 0; ch_start = unit_off;
         }
-        ch_elems += size; ch_units += 1;
+        L.uoffs.push_back((uint16_t)(unit_off - ch_start));
+        ch_elems += size; ch_units += 1; ch_slices += nsl;
         L.has_flat = true;
         L.flat_elems += size;
         if (singles_ok && image_local && singles.size() + size <= single_cap) {
@@ -259,6 +339,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         }
       }
       L.chunks.clear();
+      L.uoffs.clear();
       L.has_flat = false;
       L.flat_elems = 0;
     }

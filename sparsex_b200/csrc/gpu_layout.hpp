@@ -6,16 +6,21 @@
 // built once at tune time by decoding ctl on the host:
 //
 //   * chunk table — the ctl stream is cut at unit boundaries into chunks of
-//     at most 512 non-zeros / 64 units / 2 KB of ctl ("warp-segmented ctl
+//     at most 512 non-zeros / 128 units / 2 KB of ctl ("warp-segmented ctl
 //     chunks").  An entry holds the byte offset of the chunk's first unit, the
 //     index of its first value, the row it belongs to and the column cursor at
-//     that point, i.e. the decoder state a warp needs to start there.  A warp
-//     stages the chunk's ctl bytes in shared memory, parses the unit heads
-//     (flags, size, varints), then decodes all elements of the chunk 32 at a
-//     time: delta bodies become columns through a segmented warp prefix sum,
-//     substructure elements get (row, column) from their unit's geometry.
-//     Rows are reduced inside the warp with a segmented shuffle reduction and
-//     added to y with fp64 red operations (a row may span chunks).
+//     that point (the decoder state a warp needs to start there), plus its
+//     byte / element / unit counts.  A second table holds the 16-bit offset of
+//     every unit head inside its chunk, so no warp has to walk the heads
+//     serially.  A warp copies the chunk's ctl bytes and values into shared
+//     memory (asynchronous copies), parses one unit head per lane, cuts the
+//     units into slices of at most `slice` elements and then gives every lane
+//     one slice: delta bodies are summed per slice, a segmented warp prefix sum
+//     over the slice totals yields each slice's column cursor, and the lane
+//     walks its slice (columns from the deltas or from the unit geometry).
+//     Row sums of row-local units are combined across lanes with a segmented
+//     shuffle reduction and added to y with fp64 red operations (a row may
+//     span chunks); block and short cross-row units add once per block row.
 //
 //   * cross-row unit table (XDT) — long vertical / diagonal / anti-diagonal
 //     units (>= XDT_MIN_SIZE elements) are better served by a gather: each gets
@@ -33,14 +38,21 @@
 
 #include "csx_host.hpp"
 
+#ifdef __CUDACC__
+#define SPXB_HD __host__ __device__
+#else
+#define SPXB_HD
+#endif
+
 namespace spxb {
 
 constexpr int CTA_THREADS = 256;      // gather kernel: threads per CTA; a tile has CTA_THREADS * rpt rows
 constexpr int CTL_PAD = 32;           // readable bytes past the end of ctl
 constexpr int XDT_MIN_SIZE = 8;       // linear cross-row units at least this long go to the XDT
-constexpr int CHUNK_MAX_ELEMS = 512;  // chunk limits (chunk kernel shared-memory budget: 3.6 KB per warp)
+constexpr int CHUNK_MAX_ELEMS = 256;  // chunk limits (chunk kernel shared-memory budget: 5.7 KB per warp)
 constexpr int CHUNK_MAX_UNITS = 64;
 constexpr int CHUNK_MAX_BYTES = 2048;
+constexpr int CHUNK_MAX_SLICES = 128;
 
 // unit kinds as the kernels see them
 enum Kind : uint32_t {
@@ -61,13 +73,24 @@ constexpr uint32_t XD_TRANSPOSED = 1u << 28;
 constexpr uint32_t XD_DELTA1 = 1u << 29;
 
 struct KindEntry { uint32_t kind_align; uint32_t delta; };  // kind | align << 8 ; stride or free block dim
+// ctl unit id -> kind as the chunk kernel sees it.  `sl` is the slice parameter of this kind: elements per
+// slice for row-local and linear units, columns per slice for block-row units, rows per slice for block-column
+// units; `recip` = ceil(2^16 / sl), so that n / sl == (n * recip) >> 16 for n < 256.
+struct IdEntry { uint32_t kind_align; uint32_t delta; uint32_t sl; uint32_t recip; };
+// number of slices a unit of `size` elements is cut into (same arithmetic on host and device)
+SPXB_HD inline uint32_t unit_slices(uint32_t kind, uint32_t size, uint32_t delta, const IdEntry &ie) {
+  const uint32_t n = (kind == K_BROW || kind == K_BCOL) ? delta : size;   // columns / rows / elements to distribute
+  return ((n + ie.sl - 1) * ie.recip) >> 16;
+}
 
-// 24-byte chunk entry (device layout: 3 x u64)
+// 32-byte chunk entry (device layout: 2 x uint4)
 struct ChunkEntry {
   uint64_t ctl_off;   // byte offset of the chunk's first unit head (partition relative)
   uint32_t val_off;   // index of its first value (partition relative, XDT units included)
   uint32_t cursor;    // column cursor before that unit (0 when the unit starts a row)
   int32_t row;        // partition-relative row of that unit
+  uint32_t counts;    // ctl bytes [0:12) | elements [12:22) | units [22:30)
+  uint32_t uoff;      // index of the chunk's first entry in the unit-offset table
   uint32_t pad;
 };
 
@@ -79,8 +102,10 @@ struct PartLayout {
   int64_t ntiles = 0;
   int rpt = 1;                           // rows per thread (1 or 4): tile_rows = CTA_THREADS * rpt
   int64_t tile_rows() const { return (int64_t)CTA_THREADS * rpt; }
-  KindEntry idtab[64];                   // ctl unit id -> kind
-  std::vector<ChunkEntry> chunks;        // nchunks + 1 (the last entry marks the end of the stream)
+  IdEntry idtab[64];                     // ctl unit id -> kind and slice parameter
+  int slice = 0;                         // elements per slice the chunk kernel was laid out for
+  std::vector<ChunkEntry> chunks;
+  std::vector<uint16_t> uoffs;           // offset of every chunk-kernel unit head inside its chunk
   std::vector<uint32_t> tile_xoff;       // ntiles + 1
   std::vector<XDesc> xdesc;
   int64_t flat_elems = 0;                // non-zeros handled by the chunk kernel

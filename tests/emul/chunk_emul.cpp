@@ -1,0 +1,119 @@
+// Host emulation of the chunk kernel (test infrastructure): tunes a CSR matrix with the product encoder,
+// builds the product's GPU layout and then executes sparsex_b200/csrc/chunk_kernel.cuh — the same text nvcc
+// compiles — warp by warp on the fibre emulation of warp_emul.hpp.  The cross-row unit table is applied with
+// a plain loop (that kernel is covered on the GPU).  Lets the CPU test suite check the decode logic of the
+// chunk kernel against the CSR input without a GPU.
+#include "warp_emul.hpp"
+
+#include <sstream>
+#include <string>
+#include <vector>
+
+#define CSXB_EMUL 1
+#include "../../sparsex_b200/csrc/csx_host.hpp"
+#include "../../sparsex_b200/csrc/chunk_kernel.cuh"
+
+namespace {
+void put_err(char *err, size_t n, const std::string &m) {
+  if (err && n) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
+}
+}  // namespace
+
+extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const double *values, int64_t nrows, int64_t ncols,
+                         const char *options, double alpha, const double *x, double *y, int32_t *dec_rows,
+                         int32_t *dec_cols, int64_t *stats, char *err, size_t errlen) {
+  TuneOptions o;
+  if (options) {
+    std::stringstream ss(options);
+    std::string kv;
+    while (std::getline(ss, kv, ';')) {
+      if (kv.empty()) continue;
+      size_t eq = kv.find('=');
+      std::string e = eq == std::string::npos ? "malformed option" : o.set(kv.substr(0, eq), kv.substr(eq + 1));
+      if (!e.empty()) { put_err(err, errlen, e); return -1; }
+    }
+  }
+  CsxMatrix M;
+  CsrView v{rowptr, colind, values, nrows, ncols};
+  std::string e = tune_csr(v, o, 0, o.nr_threads, M);
+  if (!e.empty()) { put_err(err, errlen, e); return -1; }
+  std::vector<int64_t> saved;
+  for (auto &p : M.parts) { saved.push_back(p.nrows); if (M.symmetric) p.nrows = (int64_t)p.dvalues.size(); }
+  DeviceLayout L;
+  e = build_layout(M, L);
+  if (!e.empty()) { put_err(err, errlen, "layout: " + e); return -1; }
+  // device-wide arrays as the upload would lay them out
+  std::vector<double> vals((size_t)L.total_values + 2, 0.0);
+  std::vector<uint8_t> ctl((size_t)L.total_ctl + 64, 0);
+  for (size_t i = 0; i < L.parts.size(); i++) {
+    memcpy(vals.data() + L.parts[i].val_base, M.parts[i].values.data(), M.parts[i].values.size() * 8);
+    memcpy(ctl.data() + L.parts[i].ctl_base, M.parts[i].ctl.data(), M.parts[i].ctl.size());
+  }
+  for (int64_t i = 0; i < nrows; i++) y[i] = 0.0;
+  for (int64_t i = 0; i < (int64_t)L.total_values; i++) { dec_rows[i] = -1; dec_cols[i] = -1; }
+  int64_t nchunks = 0, nunits = 0, nxd = 0;
+  static ChunkSmem smem;
+  for (size_t i = 0; i < L.parts.size(); i++) {
+    const PartLayout &pl = L.parts[i];
+    const CsxPartition &hp = M.parts[i];
+    // kernel 1 stand-in: diagonal (CSX-Sym) and the table units, each unit once (under the tile of its first row)
+    if (M.symmetric)
+      for (int64_t r = 0; r < pl.nrows; r++) y[pl.row_start + r] += alpha * hp.dvalues[r] * x[pl.row_start + r];
+    for (int64_t t = 0; t < pl.ntiles; t++)
+      for (uint32_t j = pl.tile_xoff[t]; j < pl.tile_xoff[t + 1]; j++) {
+        const XDesc &d = pl.xdesc[j];
+        if (d.meta & XD_TRANSPOSED) continue;
+        if (((int64_t)d.row - pl.row_start) / pl.tile_rows() != t) continue;
+        nxd++;
+        const uint32_t kind = (d.meta >> 24) & 0xf, size = (d.meta >> 16) & 0xff;
+        const uint32_t delta = (d.meta & XD_DELTA1) ? 1u : L.ktab[d.meta & 0xffff].delta;
+        for (uint32_t k = 0; k < size; k++) {
+          const int64_t r = d.row + (int64_t)k * delta;
+          const int64_t c = kind == K_VERT ? d.col : (kind == K_DIAG ? d.col + (int64_t)k * delta : d.col - (int64_t)k * delta);
+          const double val = vals[d.voff + k];
+          y[r] += alpha * val * x[c];
+          if (M.symmetric) y[c] += alpha * val * x[r];
+          dec_rows[d.voff + k] = (int32_t)r; dec_cols[d.voff + k] = (int32_t)c;
+        }
+      }
+    PartDev P;
+    memset(&P, 0, sizeof(P));
+    P.ctl = ctl.data() + pl.ctl_base;
+    P.values = vals.data();
+    P.chunks = pl.chunks.data();
+    P.uoffs = pl.uoffs.data();
+    P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
+    P.nchunks = (uint32_t)pl.chunks.size();
+    P.full_colind = L.full_colind;
+    P.rpt = pl.rpt;
+    memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
+    nchunks += (int64_t)pl.chunks.size();
+    nunits += (int64_t)pl.uoffs.size();
+    for (uint32_t ch = 0; ch < P.nchunks; ch++) {
+      for (int pass = 0; pass < 2; pass++) {
+        if (pass == 0) {
+          warp_emul::run_warp([&](int lane) {
+            DecodeChunkOp op{dec_rows + P.val_base, dec_cols + P.val_base, P.row_start, 0};
+            process_chunk(P, ch, smem, lane, op);
+          });
+        } else if (M.symmetric) {
+          warp_emul::run_warp([&](int lane) {
+            SpmvChunkOp<true> op;
+            op.x = x; op.y = y; op.vals = smem.vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
+            process_chunk(P, ch, smem, lane, op);
+          });
+        } else {
+          warp_emul::run_warp([&](int lane) {
+            SpmvChunkOp<false> op;
+            op.x = x; op.y = y; op.vals = smem.vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
+            process_chunk(P, ch, smem, lane, op);
+          });
+        }
+      }
+    }
+    if (stats) stats[3] = pl.slice;
+  }
+  for (size_t i = 0; i < M.parts.size(); i++) M.parts[i].nrows = saved[i];
+  if (stats) { stats[0] = nchunks; stats[1] = nunits; stats[2] = nxd; }
+  return 0;
+}

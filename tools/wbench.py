@@ -35,9 +35,22 @@ def timeit(fn, reps=30):
     return e0.elapsed_time(e1) / reps
 
 
+_cache = {}
 for name in (sys.argv[1:] or list(CASES)):
+    name, _, forced = name.partition(":")   # "c3b:4" forces spx.b200.slice=4
     gen, opts = CASES[name]
-    rp, ci, va, n = gen()
+    if forced:
+        opts = dict(opts, **{"spx.b200.slice": forced})
+    if name not in _cache:
+        _cache.clear()
+        rp, ci, va, n = gen()
+        xh = np.random.default_rng(0).uniform(-1, 1, n)
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        _cache[name] = (rp, ci, va, n, xh, np.bincount(rows, weights=va * xh[ci], minlength=n))
+        del rows
+    rp, ci, va, n, xh, yref = _cache[name]
+    if forced:
+        name += ":" + forced
     nnz = int(rp[-1])
     t0 = time.time()
     A = CsxMatrix.tune_csr(rp, ci, va, n, n, dict(opts, **{"spx.b200.rows_info": "false"}))
@@ -46,16 +59,13 @@ for name in (sys.argv[1:] or list(CASES)):
     A.upload(0, free_host=True)
     t2 = time.time()
     tr = A.traffic()
-    x = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, n)).cuda()
+    x = torch.from_numpy(xh).cuda()
     y = torch.zeros(n, dtype=torch.float64, device="cuda")
-    rows = np.repeat(np.arange(n), np.diff(rp))
     A.spmv(1.0, x, y)
     torch.cuda.synchronize()
-    yref = np.zeros(n)
-    np.add.at(yref, rows, va * x.cpu().numpy()[ci])
     err = np.abs(y.cpu().numpy() - yref).max() / np.abs(yref).max()
     ms = timeit(lambda: A.spmv(1.0, x, y))
-    print("%-4s rows %9d nnz %10d  tune %.1fs upload %.1fs  [%s]  %.1f us  %.0f GB/s (%.0f%% of 6552)  %.0f GFLOP/s  bytes/nnz %.2f (ctl %.2f tables %.2f)  relerr %.1e"
+    print("%-6s rows %9d nnz %10d  tune %.1fs upload %.1fs  [%s]  %.1f us  %.0f GB/s (%.0f%% of 6552)  %.0f GFLOP/s  bytes/nnz %.2f (ctl %.2f tables %.2f)  relerr %.1e"
           % (name, n, nnz, t1 - t0, t2 - t1, log.strip(), ms * 1e3, tr["total"] / ms / 1e6, tr["total"] / ms / 1e6 / 65.517,
              2 * nnz / ms / 1e6, tr["total"] / nnz, tr["ctl"] / nnz, tr["tables"] / nnz, err), flush=True)
     A.close()
