@@ -159,6 +159,9 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: exchange fused into the SpMV kernel over peer memory (default) or NCCL after it")
+    ap.add_argument("--graph-steps", type=int, default=16, help="N > 1, peer exchange: steps per captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,7 +232,15 @@ def main():
     y = torch.zeros(n, dtype=torch.float64, device="cuda")
     exchange = None
     xbuf = [x, y]   # ping-pong: the SpMV writes the own rows of the other buffer, the exchange fills the halo
-    if world > 1:
+    peer = None
+    sym = str(opts.get("spx.matrix.symmetric", "false")) == "true"
+    if world > 1 and args.exchange == "peer" and not sym:
+        # the engine's own exchange: halo rows are stored into the neighbours' vectors by the SpMV kernel itself
+        from sparsex_b200.dist import connect_peer_exchange
+        peer, ranges, windows = connect_peer_exchange(eng, rank, world, "cuda")
+        peer.vector(0).copy_(x)
+        exchange_kind = "fused into the SpMV kernel: rows other ranks read are stored into their vectors over NVLink (peer memory), device-side flags order the steps"
+    elif world > 1:
         from sparsex_b200.dist import PieceExchange, WindowExchange, gather_row_ranges
         L = sparsex_b200.lib()
         ranges = gather_row_ranges(row_lo, row_n, "cuda")
@@ -248,6 +259,9 @@ def main():
     state = {"cur": 0}
 
     def step():
+        if peer is not None:
+            peer.spmv(alpha)
+            return
         src, dst = xbuf[state["cur"]], xbuf[1 - state["cur"]]
         eng.spmv(alpha, src, dst, overwrite=True)
         if world > 1:
@@ -262,36 +276,67 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1 with the peer exchange: a step is kernel launches only, so G steps are captured into one CUDA graph
+    # (the step counter and the buffer parity live on the device, the graph is replayable)
+    graph, G = None, 1
+    if peer is not None and args.graph_steps > 1:
+        G = args.graph_steps
+        while G > 1 and (args.steps % G or G % 2):
+            G -= 1
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if G > 1:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(G):
+                    step()
+        torch.cuda.current_stream().wait_stream(side)
+        barrier()
+        graph.replay()   # one untimed replay
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        src, dst = xbuf[state["cur"]], xbuf[1 - state["cur"]]
-        kev[i][0].record()
-        eng.spmv(alpha, src, dst, overwrite=True)
-        kev[i][1].record()
-        if world > 1:
-            if exchange is not None:
-                exchange(dst)
-            else:
-                pieces[1 - state["cur"]](dst[row_lo:row_lo + row_n])
-            state["cur"] = 1 - state["cur"]
+    if graph is not None:
+        for i in range(args.steps // G):
+            graph.replay()
+    else:
+        for i in range(args.steps):
+            kev[i][0].record()
+            step()
+            kev[i][1].record()
     e1.record()
     barrier()
     clocks = sampler.finish()
     ms = e0.elapsed_time(e1)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    kernel_ms = ms / args.steps if graph is not None else sum(a.elapsed_time(b) for a, b in kev) / args.steps
     t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, kernel_ms = float(t[0]), float(t[1])
     value = 2.0 * nnz * args.steps / (ms * 1e-3) / 1e9
+    if peer is not None and peer.error():
+        raise SystemExit("peer exchange: a wait for a neighbour timed out")
+    kernel_only_ms = None
+    if world > 1:   # this rank's SpMV kernel alone (no exchange, no neighbour): what the step time is made of
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            eng.spmv(alpha, x, y, overwrite=True)
+        ka.record()
+        for _ in range(32):
+            eng.spmv(alpha, x, y, overwrite=True)
+        kb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ka.elapsed_time(kb) / 32], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_only_ms = float(t[0])
 
     # ---- end to end through spx_matvec_mult with host buffers ---------------------
     xh = torch.from_numpy(rng.uniform(-1, 1, n)).pin_memory()
@@ -311,10 +356,19 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
-    e2e = {"value": 2.0 * nnz * args.e2e_steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n * world,
-           "d2h_bytes_per_step": 8 * n, "steps": args.e2e_steps,
-           "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory)"}
+    L_ = sparsex_b200.lib()
+    cw_lo, cw_hi = L_.csxb_part_info(eng._h, 0, 11), L_.csxb_part_info(eng._h, 0, 12)
+    hb = torch.tensor([8.0 * max(0, cw_hi - cw_lo + 1), 8.0 * row_n], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(hb)
+    e2e = {"value": 2.0 * nnz * args.e2e_steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(hb[0]),
+           "d2h_bytes_per_step": int(hb[1]), "steps": args.e2e_steps,
+           "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory); every rank uploads the "
+                  "columns its partition reads and downloads its rows, slab-pipelined (H2D, kernels, D2H overlap)"}
     # check the device-resident result against the host-buffer path on the same x
+    if peer is not None:
+        barrier()
+        peer.close()
     x.copy_(xh, non_blocking=False)
     y.zero_()
     eng.spmv(alpha, x, y, overwrite=True)
@@ -339,7 +393,9 @@ def main():
                            "self_check_rel": self_check},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu_traffic(name), "peak_source": peak_src,
-                             "kernel": "csx_spmv_kernel (rank 0 partition)", "kernel_ms": kernel_ms,
+                             "kernel": "csx_spmv_kernel (rank 0 partition)" + (
+                                 "; N > 1: step time of the captured graph (SpMV kernel incl. fused exchange + flag kernel)"
+                                 if graph is not None else ""), "kernel_ms": kernel_ms, "kernel_only_ms": kernel_only_ms,
                              "algorithmic_bytes": traffic["total"],
                              "bytes": {k: traffic[k] for k in ("values", "ctl", "tables", "x", "y")},
                              "frac_of_8TBs_nominal": achieved / 8000.0},

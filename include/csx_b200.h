@@ -103,6 +103,38 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
 int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double beta, double *h_y,
                    int overwrite);
 
+/* ---- repeated SpMV across GPUs, exchange over peer memory -------------------
+ * Replaces the shared-memory x vector of the reference's thread pool
+ * (CsxKernels.cpp:35-129: all threads read one x) for one process per GPU.
+ * Every rank owns one partition (csxb_tune_* with part_lo = rank) and holds two
+ * full-length vectors in a block the other ranks map through CUDA IPC.  Step k
+ * computes vec[(k+1)&1][own rows] = alpha * A_local * vec[k&1]; the kernel
+ * stores the rows that other ranks read (their column windows,
+ * CSXB_P_COL_MIN/MAX) directly into their vectors over NVLink, and device-side
+ * flags order the steps, so a step is kernel launches only (no host
+ * synchronisation, CUDA-graph capturable).  CSX-Sym is not covered here.
+ *   create  : after csxb_upload; allocates the block on the matrix's device
+ *   handle  : 64-byte CUDA IPC handle of the block, to be all-gathered by the caller
+ *   connect : handles = world * 64 bytes in rank order; row_lo/row_n = row range of every rank;
+ *             win_lo/win_hi = first/last column every rank reads
+ *   vector  : device pointer of vec[which]; fill vec[0] with the initial x (all columns the rank reads)
+ *   spmv    : one step (asynchronous on `stream`)
+ *   status  : what = 0 steps finished, 1 error word (non-zero: a wait for a neighbour timed out) */
+typedef struct csxb_xchg csxb_xchg_t;
+csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world);
+int csxb_xchg_handle(csxb_xchg_t *x, void *handle64);
+int csxb_xchg_connect(csxb_xchg_t *x, const void *handles, const int64_t *row_lo, const int64_t *row_n,
+                      const int64_t *win_lo, const int64_t *win_hi);
+/* Same plan for ranks that live in one process (peer access enabled by the caller, or one device): bases[q] =
+ * csxb_xchg_base of rank q. */
+int csxb_xchg_connect_ptr(csxb_xchg_t *x, void *const *bases, const int64_t *row_lo, const int64_t *row_n,
+                          const int64_t *win_lo, const int64_t *win_hi);
+void *csxb_xchg_base(csxb_xchg_t *x);
+double *csxb_xchg_vector(csxb_xchg_t *x, int which);
+int csxb_xchg_spmv(csxb_xchg_t *x, double alpha, void *stream);
+int64_t csxb_xchg_status(csxb_xchg_t *x, int what);
+void csxb_xchg_destroy(csxb_xchg_t *x);
+
 /* Debug/parity aid: decode the device-side tables back into (row, col) pairs
  * in values order for partition `part` (0-based global coordinates), running
  * the same ctl walk the kernels use but on the host copy of the tables. */

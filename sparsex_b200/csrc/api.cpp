@@ -372,6 +372,13 @@ static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx
   const double *dx = x->elements;
   double *dy = y->elements;
   bool x_host = !is_managed(x), y_host = !is_managed(y);
+  if (x_host && y_host) {   // user buffers on both sides: the pipelined host-buffer path of the engine
+    if (csxb_spmv_host(A->csx, alpha, x->elements, beta, y->elements, overwrite) != 0) {
+      spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+      return SPX_FAILURE;
+    }
+    return SPX_SUCCESS;
+  }
   if (x_host) {
     if (!A->stage_x && cudaMalloc((void **)&A->stage_x, (size_t)(A->ncols ? A->ncols : 1) * 8) != cudaSuccess) {
       SETERROR_1(SPX_ERR_VEC, "device allocation failed");

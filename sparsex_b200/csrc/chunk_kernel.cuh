@@ -22,6 +22,7 @@ struct PartDev {
   uint32_t nchunks;
   int full_colind;
   int rpt;                     // rows per thread: a tile has CTA_THREADS * rpt rows
+  uint32_t tile0, chunk0;      // first tile / chunk of this launch (a launch may cover a sub-range)
   IdEntry idtab[64];
 };
 

@@ -1065,6 +1065,7 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
     out.nparts_total = np; out.part_lo = part_lo;
     out.rows_per_thread = opt.rows_per_thread;
     out.slice_elems = opt.slice_elems;
+    out.slab_rows = opt.slab_rows;
     out.parts.resize(part_hi - part_lo);
     bool sym = opt.symmetric;
     if (sym && nrows != ncols) throw TuneError("spx.matrix.symmetric requires a square matrix");
@@ -1167,6 +1168,10 @@ std::string TuneOptions::set(const std::string &k, const std::string &v) {
     else if (k == "spx.b200.rows_per_thread") {
       rows_per_thread = std::stoi(v);
       if (rows_per_thread != 0 && rows_per_thread != 1 && rows_per_thread != 4) return "spx.b200.rows_per_thread must be 0, 1 or 4";
+    }
+    else if (k == "spx.b200.slab_rows") {
+      slab_rows = std::stoll(v);
+      if (slab_rows < 1) return "spx.b200.slab_rows must be positive";
     }
     else if (k == "spx.b200.slice") {
       slice_elems = std::stoi(v);

@@ -18,11 +18,13 @@
 // y handling of CsxKernels.cpp:35-129 / CsxSpmv.cpp:28-86.
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/csx_b200.h"
@@ -100,6 +102,38 @@ struct SpmvGatherOp {
   __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * __ldg(x + xi); }
 };
 
+// ---- multi-GPU exchange over peer memory ---------------------------------------------------------------
+// One process per GPU.  Every rank holds two full-length vectors (ping-pong) in one cudaMalloc'ed block that
+// the other ranks map through CUDA IPC.  Step k reads vec[k & 1] and writes vec[(k + 1) & 1]: the SpMV kernel
+// stores the rows it owns locally and, where another rank's partition reads them (its column window), also
+// straight into that rank's copy over NVLink — the exchange is part of the kernel's epilogue, there is no
+// separate collective.  Flags in the same block order the steps: after its own kernels of step k a rank
+// stores k + 1 into its slot of every neighbour's flag array and then waits (one warp, csx_xchg_sync_kernel)
+// until every neighbour has done the same — the halo of the next step has arrived, and no neighbour still
+// reads the buffer that the next step overwrites.  The step counter lives on the device, so a captured CUDA
+// graph can be replayed.
+constexpr int XCHG_MAX_PEERS = 15;
+struct XchgDev {
+  double *vec[2];                          // local ping-pong vectors
+  unsigned long long *step;                // local: number of steps this rank has finished
+  unsigned long long *flags;               // local: flags[q] = number of steps rank q has finished
+  unsigned long long *error;               // local: set when a wait timed out
+  int rank, nwait, npush;
+  int wait_rank[XCHG_MAX_PEERS];
+  unsigned long long *peer_flags[XCHG_MAX_PEERS];   // neighbours' flag arrays (peer memory), same order as wait_rank
+  long long push_lo[XCHG_MAX_PEERS], push_hi[XCHG_MAX_PEERS];   // global rows [lo, hi) of mine that peer p reads
+  double *push_vec[XCHG_MAX_PEERS][2];     // that peer's ping-pong vectors (peer memory)
+};
+struct NoXchg {};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // ---- kernel 1: gather over the cross-row unit table + y initialisation --------------------------
 // One CTA = one tile of CTA_THREADS * RPT rows; warp w owns RPT consecutive 32-row groups and lane L owns
 // rows  tile0 + (w*RPT + k)*32 + L,  k < RPT  (RPT independent accumulators per thread).  Warps never
@@ -112,15 +146,21 @@ struct SpmvGatherOp {
 // VAR = 1 (4-rows-per-thread diagonal instantiation) issues the eight loads of a unit as one inline-PTX block so
 // that all of them are in flight before the first FMA; ptxas otherwise interleaves loads and FMAs at 32 registers.
 enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
-template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0>
+template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0, class XP = NoXchg>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __grid_constant__ PartDev P,
                                                                   const double *__restrict__ x,
                                                                   double *__restrict__ y, double alpha, double beta,
-                                                                  int overwrite) {
+                                                                  int overwrite, const __grid_constant__ XP X) {
+  constexpr bool XCHG = !std::is_same<XP, NoXchg>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = blockIdx.x;
+  const long long tile = (long long)blockIdx.x + P.tile0;
   const long long lrow0 = ((tile * (CTA_THREADS / 32) + warp) * RPT) * 32;   // first row of this warp (partition relative)
   if (lrow0 >= P.nrows) return;
+  unsigned long long xk = 0;
+  if constexpr (XCHG) {   // vectors by step parity (the sync kernel that ended the previous step has seen the halo arrive)
+    xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+    x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
+  }
   double acc[RPT];
 #pragma unroll
   for (int k = 0; k < RPT; k++) acc[k] = 0.0;
@@ -210,18 +250,68 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __gri
       const long long g = P.row_start + lrow;
       double a = acc[k];
       if (SYM) a += __ldg(P.dvalues + lrow) * __ldg(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
-      y[g] = overwrite ? alpha * a : alpha * a + beta * y[g];
+      const double r = overwrite ? alpha * a : alpha * a + beta * y[g];
+      y[g] = r;
+      if constexpr (XCHG) {   // the exchange: rows another rank's partition reads go straight into its next x.
+        // No fence here (a system fence per store would wait for every NVLink acknowledgement in turn): the
+        // sync kernel that ends the step runs after this kernel on the same stream and issues the system-scope
+        // fence and release before the neighbours are told that the step is complete.
+        for (int p = 0; p < X.npush; p++)
+          if (g >= X.push_lo[p] && g < X.push_hi[p]) X.push_vec[p][(xk & 1) ^ 1][g] = r;
+      }
     }
   }
 }
 
-template <bool SYM>
+// Exchange for partitions whose rows are only final after the chunk kernel: copies the rows the peers read.
+__global__ void __launch_bounds__(256) csx_xchg_push_kernel(const __grid_constant__ XchgDev X) {
+  const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+  const double *src = X.vec[(k & 1) ^ 1];
+  for (int p = 0; p < X.npush; p++) {
+    double *dst = X.push_vec[p][(k & 1) ^ 1];
+    for (long long g = X.push_lo[p] + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < X.push_hi[p];
+         g += (long long)gridDim.x * blockDim.x)
+      dst[g] = src[g];
+  }
+}
+// Rows past the last partition's rows belong to nobody: zero in every step's result (VecInit(y, 0), CsxKernels.cpp:93).
+__global__ void __launch_bounds__(256) csx_xchg_zero_tail_kernel(const __grid_constant__ XchgDev X, long long lo, long long hi) {
+  const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+  double *dst = X.vec[(k & 1) ^ 1];
+  for (long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < hi; g += (long long)gridDim.x * blockDim.x) dst[g] = 0.0;
+}
+// End of a step (one warp): publish "rank finished step k" to every neighbour, advance the local step counter,
+// then wait until every neighbour has finished step k as well — its halo rows for the next step have arrived
+// and it no longer reads the buffer the next step overwrites.  Runs after the step's kernels on the same stream,
+// so their stores (local and peer) are complete; the next step's kernels start after it.  The wait is bounded:
+// a lost peer sets the error word instead of hanging the device.
+__global__ void csx_xchg_sync_kernel(const __grid_constant__ XchgDev X, int dbg) {
+  const int lane = threadIdx.x;
+  const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+  if (!(dbg & 2)) __threadfence_system();
+  if (lane < X.nwait) st_release_sys(X.peer_flags[lane] + X.rank, k + 1);
+  if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(X.step) = k + 1;
+  if (lane < X.nwait) {
+    const unsigned long long *f = X.flags + X.wait_rank[lane];
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < k + 1) {
+      if (clock64() - t0 > 6000000000ll) { atomicExch(X.error, 1ull); break; }
+    }
+  }
+}
+
+template <bool SYM, class XP = NoXchg>
 __global__ void __launch_bounds__(CHUNK_WARPS * 32, 9) csx_chunk_kernel(const __grid_constant__ PartDev P,
                                                                      const double *__restrict__ x,
-                                                                     double *__restrict__ y, double alpha) {
+                                                                     double *__restrict__ y, double alpha,
+                                                                     const __grid_constant__ XP X) {
   __shared__ ChunkSmem smem[CHUNK_WARPS];
+  if constexpr (!std::is_same<XP, NoXchg>::value) {   // vectors by step parity (kernel 1 of this step has waited)
+    const unsigned long long xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+    x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
+  const uint32_t ch = P.chunk0 + blockIdx.x * CHUNK_WARPS + warp;
   if (ch >= P.nchunks) return;
   SpmvChunkOp<SYM> op;
   op.x = x; op.y = y; op.vals = smem[warp].vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
@@ -278,16 +368,24 @@ struct csxb_matrix {
   double *d_x = nullptr, *d_y = nullptr;   // staging for csxb_spmv_host
   int64_t covered_rows_end = 0;
   int64_t sym_halo_lo = 0, sym_halo_hi = 0;   // CSX-Sym, partial device: rows of other devices this one adds into
+  // pipelined host-buffer path (csxb_spmv_host): row slabs with the x columns they need and the y rows that are
+  // final once they have run
+  struct Slab { int part; int64_t tile0, tile1; uint32_t chunk0, chunk1; int64_t x_lo, x_hi, row_lo, row_hi, y_lo, y_hi; };
+  std::vector<Slab> slabs;
+  std::vector<cudaEvent_t> slab_ev;
+  cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
   int64_t bytes[7] = {0, 0, 0, 0, 0, 0, 0};
   std::vector<std::string> logs;
   ~csxb_matrix() {
-    if (!allocs.empty() || d_x || d_y) {
+    if (!allocs.empty() || d_x || d_y || s_h2d) {
       int cur = -1;
       cudaGetDevice(&cur);
       if (device >= 0) cudaSetDevice(device);
       for (void *p : allocs) cudaFree(p);
       if (d_x) cudaFree(d_x);
       if (d_y) cudaFree(d_y);
+      for (cudaEvent_t e : slab_ev) cudaEventDestroy(e);
+      if (s_h2d) { cudaStreamDestroy(s_h2d); cudaStreamDestroy(s_run); cudaStreamDestroy(s_d2h); }
       if (cur >= 0) cudaSetDevice(cur);
     }
   }
@@ -434,6 +532,52 @@ static int dev_copy(csxb_matrix *m, const T *src, size_t n, T **dst, size_t extr
   return 0;
 }
 
+// Row slabs of the pipelined host-buffer path: about 4 MB of y per slab.  A chunk runs with the slab that
+// holds the last row it touches (kernel 1 must have initialised every row a chunk adds into), and a slab's y
+// rows travel back only up to the first row of the first chunk that runs later.
+static void build_slabs(csxb_matrix *m) {
+  m->slabs.clear();
+  const int64_t SLAB_ROWS = m->host.slab_rows;
+  for (size_t i = 0; i < m->layout.parts.size(); i++) {
+    const PartLayout &pl = m->layout.parts[i];
+    if (!pl.ntiles) continue;
+    const int64_t tr = pl.tile_rows(), tiles_per = std::max<int64_t>(1, SLAB_ROWS / tr);
+    uint32_t c = 0;
+    const uint32_t nc = (uint32_t)pl.chunks.size();
+    int64_t y_done = pl.row_start, xmax = -1, xmin = INT32_MAX;
+    for (int64_t t0 = 0; t0 < pl.ntiles; t0 += tiles_per) {
+      csxb_matrix::Slab sl;
+      sl.part = (int)i; sl.tile0 = t0; sl.tile1 = std::min(pl.ntiles, t0 + tiles_per);
+      const int64_t r1 = std::min(pl.nrows, sl.tile1 * tr);   // partition-relative end row
+      sl.row_lo = pl.row_start + t0 * tr; sl.row_hi = pl.row_start + r1;
+      for (int64_t t = sl.tile0; t < sl.tile1; t++)
+        if (pl.tile_cmax[t] >= pl.tile_cmin[t]) { xmax = std::max<int64_t>(xmax, pl.tile_cmax[t]); xmin = std::min<int64_t>(xmin, pl.tile_cmin[t]); }
+      sl.chunk0 = c;
+      int32_t last = -1;
+      while (c < nc) {   // chunks in stream order; running maximum of the last rows they touch
+        last = std::max(last, pl.chunk_last_row[c]);
+        if (last >= r1) break;
+        c++;
+      }
+      sl.chunk1 = c;
+      sl.x_lo = 0; sl.x_hi = xmax + 1;
+      sl.y_lo = y_done;
+      sl.y_hi = c < nc ? std::min<int64_t>(sl.row_hi, pl.row_start + pl.chunks[c].row) : sl.row_hi;
+      sl.y_hi = std::max(sl.y_hi, sl.y_lo);
+      y_done = sl.y_hi;
+      m->slabs.push_back(sl);
+    }
+    (void)xmin;
+  }
+  // x travels in ascending column order starting at the smallest column any local slab reads
+  int64_t lo = INT64_MAX;
+  for (size_t i = 0; i < m->layout.parts.size(); i++)
+    for (int32_t v : m->layout.parts[i].tile_cmin) if (v != INT32_MAX) lo = std::min<int64_t>(lo, v);
+  if (lo == INT64_MAX) lo = 0;
+  int64_t run = lo;
+  for (auto &sl : m->slabs) { sl.x_lo = lo; run = std::max(run, sl.x_hi); sl.x_hi = run; }
+}
+
 extern "C" {
 
 int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
@@ -503,6 +647,7 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     for (auto &p : H.parts) if (p.col_max >= p.col_min) lo = std::min(lo, p.col_min);
     m->sym_halo_lo = lo; m->sym_halo_hi = first_row;
   }
+  if (!H.symmetric) build_slabs(m);
   m->bytes[CSXB_B_VALUES] = nnz_stored * 8;
   m->bytes[CSXB_B_CTL] = ctl_bytes;
   m->bytes[CSXB_B_TABLES] = tables;
@@ -526,29 +671,45 @@ int64_t csxb_traffic(const csxb_matrix_t *m, int what) {
 
 }  // extern "C"
 
-template <bool SYM, int RPT, int KSET>
-static void launch_gather_k(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
-                            int overwrite, cudaStream_t s) {
-  dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
+// Launches kernel 1 over tiles [t0, t1) of one partition.  XP = XchgDev fuses the multi-GPU exchange into it.
+template <bool SYM, int RPT, int KSET, class XP>
+static void launch_gather_k(const PartDev &P, const PartLayout &pl, unsigned nt, const double *x, double *y, double alpha,
+                            double beta, int overwrite, cudaStream_t s, const XP &X) {
+  dim3 grid(nt), block(CTA_THREADS);
   // descriptors can also come from other partitions (transposed images under CSX-Sym)
-  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
-  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET, 8, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, 8, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
 }
-template <bool SYM>
-static void launch_gather(const PartDev &P, const PartLayout &pl, const double *x, double *y, double alpha, double beta,
-                          int overwrite, cudaStream_t s) {
+template <bool SYM, class XP>
+static void launch_gather(const PartDev &P0, const PartLayout &pl, int64_t t0, int64_t t1, const double *x, double *y,
+                          double alpha, double beta, int overwrite, cudaStream_t s, const XP &X) {
+  if (t1 <= t0) return;
+  PartDev P = P0;
+  P.tile0 = (uint32_t)t0;
+  const unsigned nt = (unsigned)(t1 - t0);
   // kernels are pre-compiled per (tile shape, unit-kind set) — the counterpart of the per-partition JIT (CsxJit.hpp)
   const bool diag1 = !SYM && pl.xd_diag1_only && !pl.xdesc.empty();
   if (pl.rpt == 4) {
     if (diag1) {  // the instantiation the stencil configs run: loads of a unit issued as one PTX block
-      dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
-      csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 1><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite);
+      dim3 grid(nt), block(CTA_THREADS);
+      csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 1, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
     }
-    else launch_gather_k<SYM, 4, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
+    else launch_gather_k<SYM, 4, KSET_ANY>(P, pl, nt, x, y, alpha, beta, overwrite, s, X);
   } else {
-    if (diag1) launch_gather_k<SYM, 1, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, x, y, alpha, beta, overwrite, s);
-    else launch_gather_k<SYM, 1, KSET_ANY>(P, pl, x, y, alpha, beta, overwrite, s);
+    if (diag1) launch_gather_k<SYM, 1, SYM ? KSET_ANY : KSET_DIAG1>(P, pl, nt, x, y, alpha, beta, overwrite, s, X);
+    else launch_gather_k<SYM, 1, KSET_ANY>(P, pl, nt, x, y, alpha, beta, overwrite, s, X);
   }
+}
+// Launches kernel 2 over chunks [c0, c1) of one partition.
+template <class XP>
+static void launch_chunks(const PartDev &P0, bool sym, uint32_t c0, uint32_t c1, const double *x, double *y, double alpha,
+                          cudaStream_t s, const XP &X) {
+  if (c1 <= c0) return;
+  PartDev P = P0;
+  P.chunk0 = c0; P.nchunks = c1;
+  const unsigned grid = (unsigned)((c1 - c0 + CHUNK_WARPS - 1) / CHUNK_WARPS);
+  if (sym) csx_chunk_kernel<true, XP><<<grid, CHUNK_WARPS * 32, 0, s>>>(P, x, y, alpha, X);
+  else csx_chunk_kernel<false, XP><<<grid, CHUNK_WARPS * 32, 0, s>>>(P, x, y, alpha, X);
 }
 
 extern "C" {
@@ -563,17 +724,11 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   // partition adds into rows that another partition owns
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
-    if (!pl.ntiles) continue;
-    if (sym) launch_gather<true>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
-    else launch_gather<false>(m->pdev[i], pl, d_x, d_y, alpha, beta, overwrite, s);
+    if (sym) launch_gather<true>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, beta, overwrite, s, NoXchg());
+    else launch_gather<false>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, beta, overwrite, s, NoXchg());
   }
-  for (size_t i = 0; i < m->pdev.size(); i++) {
-    const PartLayout &pl = m->layout.parts[i];
-    if (pl.chunks.empty()) continue;
-    const unsigned grid = (unsigned)((pl.chunks.size() + CHUNK_WARPS - 1) / CHUNK_WARPS);
-    if (sym) csx_chunk_kernel<true><<<grid, CHUNK_WARPS * 32, 0, s>>>(m->pdev[i], d_x, d_y, alpha);
-    else csx_chunk_kernel<false><<<grid, CHUNK_WARPS * 32, 0, s>>>(m->pdev[i], d_x, d_y, alpha);
-  }
+  for (size_t i = 0; i < m->pdev.size(); i++)
+    launch_chunks(m->pdev[i], sym, 0, (uint32_t)m->layout.parts[i].chunks.size(), d_x, d_y, alpha, s, NoXchg());
   // rows after the last partition's last non-empty row belong to nobody; VecInit(y,0) clears them (CsxKernels.cpp:93)
   if (overwrite && m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total && m->covered_rows_end < m->host.nrows)
     CUDA_TRY(cudaMemsetAsync(d_y + m->covered_rows_end, 0, (size_t)(m->host.nrows - m->covered_rows_end) * 8, s));
@@ -581,6 +736,11 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   return 0;
 }
 
+// Host-buffer SpMV, pipelined: the rows are cut into slabs; x travels to the device in ascending column order
+// on one stream, a slab's kernels start as soon as the columns its rows read have arrived, and its y rows go
+// back on a third stream while the next slabs compute — host-to-device, compute and device-to-host overlap
+// (PCIe is full duplex).  Banded matrices overlap all three; a matrix whose first rows read the whole x only
+// overlaps compute with the way back.  CSX-Sym scatters into rows of earlier slabs, so it runs unpipelined.
 int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double beta, double *h_y, int overwrite) {
   if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
   int cur = -1;
@@ -589,17 +749,208 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
   size_t nx = (size_t)std::max<int64_t>(m->host.ncols, 1), ny = (size_t)std::max<int64_t>(m->host.nrows, 1);
   if (!m->d_x) CUDA_TRY(cudaMalloc((void **)&m->d_x, nx * 8));
   if (!m->d_y) CUDA_TRY(cudaMalloc((void **)&m->d_y, ny * 8));
-  CUDA_TRY(cudaMemcpyAsync(m->d_x, h_x, (size_t)m->host.ncols * 8, cudaMemcpyHostToDevice, 0));
-  if (!overwrite) CUDA_TRY(cudaMemcpyAsync(m->d_y, h_y, (size_t)m->host.nrows * 8, cudaMemcpyHostToDevice, 0));
-  if (csxb_spmv(m, alpha, m->d_x, beta, m->d_y, overwrite, nullptr)) return -1;
-  // only the rows this handle computes travel back (one process per GPU owns one row range)
-  int64_t lo = m->layout.parts.empty() ? 0 : m->layout.parts.front().row_start;
-  int64_t hi = (m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total) ? m->host.nrows : m->covered_rows_end;
-  if (!overwrite) { lo = 0; hi = m->host.nrows; }
-  if (hi > lo) CUDA_TRY(cudaMemcpyAsync(h_y + lo, m->d_y + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  if (!m->s_h2d) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->s_run, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+  }
+  const bool last_local = m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total;
+  if (m->slabs.empty()) {   // CSX-Sym or nothing to pipeline: upload, run, download
+    CUDA_TRY(cudaMemcpyAsync(m->d_x, h_x, (size_t)m->host.ncols * 8, cudaMemcpyHostToDevice, m->s_run));
+    if (!overwrite) CUDA_TRY(cudaMemcpyAsync(m->d_y, h_y, (size_t)m->host.nrows * 8, cudaMemcpyHostToDevice, m->s_run));
+    if (csxb_spmv(m, alpha, m->d_x, beta, m->d_y, overwrite, m->s_run)) return -1;
+    // only the rows this handle computes travel back (one process per GPU owns one row range)
+    int64_t lo = m->layout.parts.empty() ? 0 : m->layout.parts.front().row_start;
+    int64_t hi = last_local ? m->host.nrows : m->covered_rows_end;
+    if (!overwrite) { lo = 0; hi = m->host.nrows; }
+    if (hi > lo) CUDA_TRY(cudaMemcpyAsync(h_y + lo, m->d_y + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, m->s_run));
+    CUDA_TRY(cudaStreamSynchronize(m->s_run));
+  } else {
+    if (m->slab_ev.size() < 2 * m->slabs.size()) {
+      size_t old = m->slab_ev.size();
+      m->slab_ev.resize(2 * m->slabs.size());
+      for (size_t i = old; i < m->slab_ev.size(); i++) CUDA_TRY(cudaEventCreateWithFlags(&m->slab_ev[i], cudaEventDisableTiming));
+    }
+    int64_t x_done = m->slabs.front().x_lo;   // columns [x_lo of the first slab, x_done) are on the device
+    for (size_t k = 0; k < m->slabs.size(); k++) {
+      const csxb_matrix::Slab &sl = m->slabs[k];
+      const PartLayout &pl = m->layout.parts[sl.part];
+      if (sl.x_hi > x_done) {
+        CUDA_TRY(cudaMemcpyAsync(m->d_x + x_done, h_x + x_done, (size_t)(sl.x_hi - x_done) * 8, cudaMemcpyHostToDevice, m->s_h2d));
+        x_done = sl.x_hi;
+      }
+      if (!overwrite && sl.row_hi > sl.row_lo)
+        CUDA_TRY(cudaMemcpyAsync(m->d_y + sl.row_lo, h_y + sl.row_lo, (size_t)(sl.row_hi - sl.row_lo) * 8, cudaMemcpyHostToDevice, m->s_h2d));
+      CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k], m->s_h2d));
+      CUDA_TRY(cudaStreamWaitEvent(m->s_run, m->slab_ev[2 * k], 0));
+      launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, beta, overwrite, m->s_run, NoXchg());
+      launch_chunks(m->pdev[sl.part], false, sl.chunk0, sl.chunk1, m->d_x, m->d_y, alpha, m->s_run, NoXchg());
+      CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k + 1], m->s_run));
+      if (sl.y_hi > sl.y_lo) {
+        CUDA_TRY(cudaStreamWaitEvent(m->s_d2h, m->slab_ev[2 * k + 1], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_y + sl.y_lo, m->d_y + sl.y_lo, (size_t)(sl.y_hi - sl.y_lo) * 8, cudaMemcpyDeviceToHost, m->s_d2h));
+      }
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(m->s_run));
+    CUDA_TRY(cudaStreamSynchronize(m->s_d2h));
+    // rows after the last partition's last non-empty row belong to nobody: zero under spx_matvec_mult
+    // semantics (CsxKernels.cpp:93), beta*y under spx_matvec_kernel semantics
+    if (last_local && m->covered_rows_end < m->host.nrows)
+      for (int64_t r = m->covered_rows_end; r < m->host.nrows; r++) h_y[r] = overwrite ? 0.0 : beta * h_y[r];
+  }
   if (cur != m->device && cur >= 0) CUDA_TRY(cudaSetDevice(cur));
   return 0;
+}
+
+// ---- csxb_xchg_*: exchange over peer memory (see XchgDev) ------------------------------------------------
+struct csxb_xchg {
+  csxb_matrix *m = nullptr;
+  int rank = 0, world = 1;
+  void *base = nullptr;              // [vec0 | vec1 | ctrl] on m's device
+  size_t n = 0;
+  std::vector<void *> peer_base;     // other ranks' blocks (CUDA IPC mappings; own slot = base)
+  XchgDev dev;
+  bool connected = false, fused_push = true;
+  int64_t tail_lo = 0, tail_hi = 0;   // rows no rank owns (after the last partition's rows)
+};
+static size_t xchg_vec_bytes(size_t n) { return ((n * 8 + 255) / 256) * 256; }
+
+csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world) {
+  if (!m || !m->uploaded) { fail("matrix not uploaded (csxb_upload)"); return nullptr; }
+  if (m->host.symmetric) { fail("the peer-memory exchange covers non-symmetric CSX (CSX-Sym: SymHaloReduce)"); return nullptr; }
+  if (world < 1 || rank < 0 || rank >= world || world - 1 > XCHG_MAX_PEERS) { fail("invalid rank / world size"); return nullptr; }
+  if (m->host.nrows != m->host.ncols) { fail("repeated SpMV with exchange needs a square matrix"); return nullptr; }
+  if (cudaSetDevice(m->device) != cudaSuccess) { fail("cudaSetDevice failed"); return nullptr; }
+  csxb_xchg *h = new csxb_xchg;
+  h->m = m; h->rank = rank; h->world = world; h->n = (size_t)m->host.nrows;
+  const size_t vb = xchg_vec_bytes(h->n), total = 2 * vb + 4096;
+  if (cudaMalloc(&h->base, total) != cudaSuccess || cudaMemset(h->base, 0, total) != cudaSuccess) {
+    fail("device allocation for the exchange vectors failed");
+    delete h;
+    return nullptr;
+  }
+  memset(&h->dev, 0, sizeof(h->dev));
+  h->dev.vec[0] = (double *)h->base;
+  h->dev.vec[1] = (double *)((char *)h->base + vb);
+  unsigned long long *ctrl = (unsigned long long *)((char *)h->base + 2 * vb);
+  h->dev.step = ctrl; h->dev.error = ctrl + 1; h->dev.flags = ctrl + 16;
+  h->dev.rank = rank;
+  for (auto &pl : m->layout.parts) if (!pl.chunks.empty()) h->fused_push = false;
+  if (world == 1) {
+    h->connected = true;
+    if (m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total) { h->tail_lo = m->covered_rows_end; h->tail_hi = (int64_t)h->n; }
+  }
+  return h;
+}
+
+int csxb_xchg_handle(csxb_xchg_t *h, void *handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t ih;
+  CUDA_TRY(cudaSetDevice(h->m->device));
+  CUDA_TRY(cudaIpcGetMemHandle(&ih, h->base));
+  memcpy(handle64, &ih, 64);
+  return 0;
+}
+
+// bases[q] = rank q's block as seen from this device (IPC mapping, or the pointer itself inside one process)
+static int xchg_plan(csxb_xchg *h, const std::vector<void *> &bases, const int64_t *row_lo, const int64_t *row_n,
+                     const int64_t *win_lo, const int64_t *win_hi) {
+  const size_t vb = xchg_vec_bytes(h->n);
+  XchgDev &D = h->dev;
+  D.nwait = 0; D.npush = 0;
+  auto overlap = [&](int owner, int reader, int64_t &lo, int64_t &hi) {   // rows of `owner` that `reader` reads
+    lo = std::max(row_lo[owner], win_lo[reader]);
+    hi = std::min(row_lo[owner] + row_n[owner], win_hi[reader] + 1);
+    return hi > lo;
+  };
+  for (int q = 0; q < h->world; q++) {
+    if (q == h->rank) continue;
+    int64_t lo, hi, lo2, hi2;
+    const bool i_push = overlap(h->rank, q, lo, hi), q_pushes = overlap(q, h->rank, lo2, hi2);
+    if (!i_push && !q_pushes) continue;
+    void *pb = bases[q];
+    if (!pb) return fail("missing peer block");
+    D.wait_rank[D.nwait] = q;
+    D.peer_flags[D.nwait] = (unsigned long long *)((char *)pb + 2 * vb) + 16;
+    D.nwait++;
+    if (i_push) {
+      D.push_lo[D.npush] = lo; D.push_hi[D.npush] = hi;
+      D.push_vec[D.npush][0] = (double *)pb;
+      D.push_vec[D.npush][1] = (double *)((char *)pb + vb);
+      D.npush++;
+    }
+  }
+  int64_t cov = 0;
+  for (int q = 0; q < h->world; q++) cov = std::max(cov, row_lo[q] + row_n[q]);
+  h->tail_lo = cov; h->tail_hi = (int64_t)h->n;
+  h->connected = true;
+  return 0;
+}
+
+int csxb_xchg_connect(csxb_xchg_t *h, const void *handles, const int64_t *row_lo, const int64_t *row_n,
+                      const int64_t *win_lo, const int64_t *win_hi) {
+  if (h->connected) return fail("exchange already connected");
+  CUDA_TRY(cudaSetDevice(h->m->device));
+  h->peer_base.assign(h->world, nullptr);
+  for (int q = 0; q < h->world; q++) {
+    if (q == h->rank) continue;
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, (const char *)handles + (size_t)q * 64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(&h->peer_base[q], ih, cudaIpcMemLazyEnablePeerAccess));
+  }
+  std::vector<void *> bases = h->peer_base;
+  bases[h->rank] = h->base;
+  return xchg_plan(h, bases, row_lo, row_n, win_lo, win_hi);
+}
+
+int csxb_xchg_connect_ptr(csxb_xchg_t *h, void *const *bases, const int64_t *row_lo, const int64_t *row_n,
+                          const int64_t *win_lo, const int64_t *win_hi) {
+  if (h->connected) return fail("exchange already connected");
+  std::vector<void *> b(bases, bases + h->world);
+  return xchg_plan(h, b, row_lo, row_n, win_lo, win_hi);
+}
+
+void *csxb_xchg_base(csxb_xchg_t *h) { return h->base; }
+
+double *csxb_xchg_vector(csxb_xchg_t *h, int which) { return h->dev.vec[which & 1]; }
+
+int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
+  if (!h->connected) return fail("exchange not connected (csxb_xchg_connect)");
+  csxb_matrix *m = h->m;
+  cudaStream_t s = (cudaStream_t)stream;
+  static const int dbg = getenv("CSXB_XCHG_DEBUG") ? atoi(getenv("CSXB_XCHG_DEBUG")) : 0;   // tuning aid
+  XchgDev X = h->dev;
+  if (!h->fused_push || (dbg & 4)) X.npush = 0;   // rows are final only after the chunk kernel: pushed by a copy kernel below
+  for (size_t i = 0; i < m->pdev.size(); i++) {
+    const PartLayout &pl = m->layout.parts[i];
+    launch_gather<false>(m->pdev[i], pl, 0, pl.ntiles, nullptr, nullptr, alpha, 0.0, 1, s, X);
+  }
+  for (size_t i = 0; i < m->pdev.size(); i++)
+    launch_chunks(m->pdev[i], false, 0, (uint32_t)m->layout.parts[i].chunks.size(), nullptr, nullptr, alpha, s, X);
+  if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 4, 256, 0, s>>>(h->dev);
+  if (h->tail_hi > h->tail_lo)
+    csx_xchg_zero_tail_kernel<<<(unsigned)std::min<int64_t>(148, (h->tail_hi - h->tail_lo + 255) / 256), 256, 0, s>>>(h->dev, h->tail_lo, h->tail_hi);
+  if (!(dbg & 1)) csx_xchg_sync_kernel<<<1, 32, 0, s>>>(h->dev, dbg);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int64_t csxb_xchg_status(csxb_xchg_t *h, int what) {
+  unsigned long long v[2] = {0, 0};
+  if (cudaSetDevice(h->m->device) != cudaSuccess) return -1;
+  if (cudaMemcpy(v, h->dev.step, 16, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return what == 0 ? (int64_t)v[0] : (int64_t)v[1];
+}
+
+void csxb_xchg_destroy(csxb_xchg_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->m->device);
+  cudaDeviceSynchronize();
+  for (int q = 0; q < (int)h->peer_base.size(); q++)
+    if (q != h->rank && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
+  if (h->base) cudaFree(h->base);
+  delete h;
 }
 
 int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t *cols) {

@@ -4,6 +4,7 @@
 // templates (csx_spmv_tmpl.c:83-98; Element.hpp:657-666 for where a unit
 // leaves the column cursor).
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <map>
 
@@ -158,6 +159,13 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     const int64_t TILE_ROWS = L.tile_rows();
     L.ntiles = (cp.nrows + TILE_ROWS - 1) / TILE_ROWS;
     L.tile_xoff.assign((size_t)L.ntiles + 1, 0);
+    L.tile_cmin.assign((size_t)L.ntiles, INT32_MAX);
+    L.tile_cmax.assign((size_t)L.ntiles, -1);
+    if (m.symmetric)   // the diagonal term reads x at the row itself
+      for (int64_t t = 0; t < L.ntiles; t++) {
+        L.tile_cmin[t] = (int32_t)(cp.row_start + t * TILE_ROWS);
+        L.tile_cmax[t] = (int32_t)(cp.row_start + std::min<int64_t>(cp.nrows, (t + 1) * TILE_ROWS) - 1);
+      }
     memset(L.idtab, 0, sizeof(L.idtab));
     uint32_t id2k[64];
     size_t nid = 0;
@@ -243,6 +251,14 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       }
       if (row + span >= cp.nrows) return "cross-row unit leaves its partition";
       if (cmin < 0 || cmax >= cp.ncols) return "unit leaves the column range";
+      {
+        int64_t wlo = cmin, whi = cmax;
+        if (m.symmetric) { wlo = std::min(wlo, cp.row_start + row); whi = std::max(whi, cp.row_start + row + span); }
+        for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) {
+          L.tile_cmin[t] = std::min<int32_t>(L.tile_cmin[t], (int32_t)wlo);
+          L.tile_cmax[t] = std::max<int32_t>(L.tile_cmax[t], (int32_t)whi);
+        }
+      }
 
       // CSX-Sym with only some partitions on this device: a unit whose transposed image reaches rows of
       // another device cannot be gathered by a local owner; the chunk kernel adds it to those rows of the
@@ -263,8 +279,10 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
           ce.ctl_off = unit_off; ce.val_off = (uint32_t)v; ce.cursor = (uint32_t)cursor_before;
           ce.row = (int32_t)row; ce.counts = 0; ce.uoff = (uint32_t)L.uoffs.size(); ce.pad = 0;
           L.chunks.push_back(ce);
+          L.chunk_last_row.push_back((int32_t)row);
           open = true; ch_elems = 0; ch_units = 0; ch_slices = 0; ch_start = unit_off;
         }
+        L.chunk_last_row.back() = std::max<int32_t>(L.chunk_last_row.back(), (int32_t)(row + span));
         L.uoffs.push_back((uint16_t)(unit_off - ch_start));
         ch_elems += size; ch_units += 1; ch_slices += nsl;
         L.has_flat = true;
@@ -339,6 +357,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         }
       }
       L.chunks.clear();
+      L.chunk_last_row.clear();
       L.uoffs.clear();
       L.has_flat = false;
       L.flat_elems = 0;

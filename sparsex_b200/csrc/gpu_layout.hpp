@@ -106,6 +106,10 @@ struct PartLayout {
   int slice = 0;                         // elements per slice the chunk kernel was laid out for
   std::vector<ChunkEntry> chunks;
   std::vector<uint16_t> uoffs;           // offset of every chunk-kernel unit head inside its chunk
+  // host-side only (pipelined host-buffer SpMV, csxb_spmv_host): last row a chunk touches, and per tile the
+  // global column window its units read (CSX-Sym: the rows themselves included, x[row] is read too)
+  std::vector<int32_t> chunk_last_row;
+  std::vector<int32_t> tile_cmin, tile_cmax;
   std::vector<uint32_t> tile_xoff;       // ntiles + 1
   std::vector<XDesc> xdesc;
   int64_t flat_elems = 0;                // non-zeros handled by the chunk kernel

@@ -120,3 +120,26 @@ class SymHaloReduce(object):
         for _, lo, hi, tmp in self.recv:
             y[lo:hi] += tmp
         return y
+
+
+def connect_peer_exchange(matrix, rank, world, device):
+    """One process per GPU: creates the engine's peer-memory exchange for `matrix` (csxb_xchg_*, include/csx_b200.h),
+    all-gathers the CUDA IPC handles, row ranges and column windows over torch.distributed (plumbing only) and
+    connects.  Afterwards a step is `ex.spmv(alpha)`: kernel launches only, the halo rows travel inside the SpMV
+    kernel over NVLink."""
+    import numpy as np
+    from .engine import PeerExchange, lib
+    L = lib()
+    ex = PeerExchange(matrix, rank, world)
+    mine = torch.from_numpy(ex.handle()).to(device)
+    allh = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    info = torch.tensor([L.csxb_part_info(matrix._h, 0, 3), L.csxb_part_info(matrix._h, 0, 1),
+                         L.csxb_part_info(matrix._h, 0, 11), L.csxb_part_info(matrix._h, 0, 12)], dtype=torch.int64, device=device)
+    alli = [torch.zeros(4, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(alli, info)
+    ranges = [(int(t[0]), int(t[1])) for t in alli]
+    windows = [(int(t[2]), int(t[3])) for t in alli]
+    ex.connect(np.stack([t.cpu().numpy() for t in allh]), ranges, windows)
+    dist.barrier()
+    return ex, ranges, windows

@@ -60,6 +60,23 @@ def lib():
     L.csxb_spmv_host.argtypes = [vp, dbl, vp, dbl, vp, i32]
     L.csxb_decode_coords.restype = i32
     L.csxb_decode_coords.argtypes = [vp, i32, vp, vp]
+    L.csxb_xchg_create.restype = vp
+    L.csxb_xchg_create.argtypes = [vp, i32, i32]
+    L.csxb_xchg_handle.restype = i32
+    L.csxb_xchg_handle.argtypes = [vp, vp]
+    L.csxb_xchg_connect.restype = i32
+    L.csxb_xchg_connect.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.csxb_xchg_connect_ptr.restype = i32
+    L.csxb_xchg_connect_ptr.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.csxb_xchg_base.restype = vp
+    L.csxb_xchg_base.argtypes = [vp]
+    L.csxb_xchg_vector.restype = vp
+    L.csxb_xchg_vector.argtypes = [vp, i32]
+    L.csxb_xchg_spmv.restype = i32
+    L.csxb_xchg_spmv.argtypes = [vp, dbl, vp]
+    L.csxb_xchg_status.restype = i64
+    L.csxb_xchg_status.argtypes = [vp, i32]
+    L.csxb_xchg_destroy.argtypes = [vp]
     _LIB = L
     return L
 
@@ -184,6 +201,72 @@ class CsxMatrix(object):
             self.close()
         except Exception:
             pass
+
+
+class _DevArray(object):
+    """Device memory owned by the engine, exposed through __cuda_array_interface__ (float64 vector)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class PeerExchange(object):
+    """csxb_xchg_* (include/csx_b200.h): repeated SpMV across GPUs with the exchange fused into the kernel."""
+
+    def __init__(self, matrix, rank, world):
+        self.A, self.rank, self.world = matrix, rank, world
+        self._h = lib().csxb_xchg_create(matrix._h, rank, world)
+        if not self._h:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    def handle(self):
+        buf = np.zeros(64, np.uint8)
+        if lib().csxb_xchg_handle(self._h, buf.ctypes.data) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return buf
+
+    def base(self):
+        return lib().csxb_xchg_base(self._h)
+
+    def _ranges(self, ranges, windows):
+        a = [np.ascontiguousarray(v, np.int64) for v in ([r[0] for r in ranges], [r[1] for r in ranges],
+                                                         [w[0] for w in windows], [w[1] for w in windows])]
+        return a
+
+    def connect(self, handles, ranges, windows):
+        """handles: (world, 64) uint8 array of every rank's handle(); ranges: (row_lo, row_n); windows: (col_min, col_max)."""
+        hb = np.ascontiguousarray(handles, np.uint8)
+        a = self._ranges(ranges, windows)
+        if lib().csxb_xchg_connect(self._h, hb.ctypes.data, *[v.ctypes.data for v in a]) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    def connect_ptr(self, bases, ranges, windows):
+        pb = (C.c_void_p * self.world)(*bases)
+        a = self._ranges(ranges, windows)
+        if lib().csxb_xchg_connect_ptr(self._h, pb, *[v.ctypes.data for v in a]) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    def vector(self, which):
+        """torch view of ping-pong vector `which` (0: the initial x)."""
+        import torch
+        return torch.as_tensor(_DevArray(lib().csxb_xchg_vector(self._h, which), self.A.nrows), device="cuda")
+
+    def spmv(self, alpha, stream=None):
+        import torch
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        if lib().csxb_xchg_spmv(self._h, alpha, s) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    def steps(self):
+        return lib().csxb_xchg_status(self._h, 0)
+
+    def error(self):
+        return lib().csxb_xchg_status(self._h, 1)
+
+    def close(self):
+        if self._h:
+            lib().csxb_xchg_destroy(self._h)
+            self._h = None
 
 
 class SpxVector(C.Structure):

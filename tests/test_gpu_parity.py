@@ -265,3 +265,94 @@ def test_symmetric_partition_per_device(world):
                 A.close()
             bound = _abs_bound(rp, ci, va, x, n) + 1e-300
             assert np.max(np.abs(total - yref) / (0.5 * bound)) <= TOL, (world, xf, O.log)
+
+
+@pytest.mark.parametrize("slab_rows", [256, 1024, 5000])
+def test_pipelined_host_buffer_path(slab_rows):
+    """csxb_spmv_host with many slabs: x uploaded in column order, slabs computed as their windows arrive, y rows
+    downloaded as they become final; chunks that straddle slab boundaries; both y semantics."""
+    _torch()
+    from sparsex_b200 import CsxMatrix
+    rng = np.random.default_rng(slab_rows)
+    cases = [poisson2d(60)[:3] + (3600, 3600, {}), stencil27(14)[:3] + (2744, 2744, {"spx.preproc.xform": "br,bc", "spx.preproc.sampling": "none"}),
+             rmat(12)[:3] + (4096, 4096, {"spx.preproc.xform": "none"}),
+             random_structured(rng, 3000, 2500) + (3000, 2500, {"spx.preproc.sampling": "none"})]
+    for rp, ci, va, n, m, opts in cases:
+        for nt in (1, 3):
+            o = dict(opts, **{"spx.b200.slab_rows": slab_rows, "spx.rt.nr_threads": nt})
+            A = CsxMatrix.tune_csr(rp, ci, va, n, m, o).upload(0)
+            x = rng.uniform(-1, 1, m)
+            y0 = rng.uniform(-1, 1, n)
+            bound = _abs_bound(rp, ci, va, x, n) + 1e-300
+            ref = _csr_spmv(rp, ci, va, x, n)
+            y = y0.copy()
+            A.spmv_host(0.5, x, y)
+            assert np.max(np.abs(y - 0.5 * ref) / (0.5 * bound)) <= TOL
+            y = y0.copy()
+            A.spmv_host(0.75, x, y, beta=-0.3, overwrite=False)
+            assert np.max(np.abs(y - (0.75 * ref - 0.3 * y0)) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300)) <= TOL
+            A.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_exchange_logical_ranks(world):
+    """csxb_xchg_*: repeated SpMV with the exchange fused into the kernel.  All logical ranks live on cuda:0 in
+    this process (csxb_xchg_connect_ptr), every rank issues its steps on its own stream (a step ends with the
+    flag exchange with its neighbours); after every step each rank's next x must hold alpha*A*x on every column
+    its partition reads."""
+    torch = _torch()
+    from sparsex_b200 import CsxMatrix, PeerExchange, lib
+    rng = np.random.default_rng(world)
+    cases = [poisson2d(70)[:3] + (4900, {}), stencil27(12)[:3] + (1728, {"spx.preproc.xform": "br,bc", "spx.preproc.sampling": "none"}),
+             rmat(11)[:3] + (2048, {"spx.preproc.xform": "none"})]
+    for rp, ci, va, n, opts in cases:
+        o = dict(opts, **{"spx.rt.nr_threads": world})
+        mats = [CsxMatrix.tune_csr(rp, ci, va, n, n, o, part_lo=r, part_hi=r + 1).upload(0) for r in range(world)]
+        L = lib()
+        ranges = [(L.csxb_part_info(A._h, 0, 3), L.csxb_part_info(A._h, 0, 1)) for A in mats]
+        windows = [(L.csxb_part_info(A._h, 0, 11), L.csxb_part_info(A._h, 0, 12)) for A in mats]
+        ex = [PeerExchange(A, r, world) for r, A in enumerate(mats)]
+        bases = [e.base() for e in ex]
+        for e in ex:
+            e.connect_ptr(bases, ranges, windows)
+        x = rng.uniform(-1, 1, n)
+        for e in ex:
+            e.vector(0).copy_(torch.from_numpy(x))
+            e.vector(1).fill_(float("nan"))
+        alpha = 0.25
+        cur = x
+        streams = [torch.cuda.Stream() for _ in ex]
+        torch.cuda.synchronize()
+        for step in range(5):
+            for e, st in zip(ex, streams):
+                e.spmv(alpha, stream=st.cuda_stream)
+            torch.cuda.synchronize()
+            ref = alpha * _csr_spmv(rp, ci, va, cur, n)
+            bound = alpha * _abs_bound(rp, ci, va, cur, n) + 1e-300
+            for r, e in enumerate(ex):
+                assert e.error() == 0 and e.steps() == step + 1
+                got = e.vector((step + 1) & 1).cpu().numpy()
+                lo, hi = windows[r]
+                own_lo, own_n = ranges[r]
+                need = np.zeros(n, bool)
+                if hi >= lo:
+                    need[lo:hi + 1] = True
+                need[own_lo:own_lo + own_n] = True
+                covered = np.zeros(n, bool)   # rows some rank owns (trailing empty rows belong to nobody)
+                for a, b in ranges:
+                    covered[a:a + b] = True
+                need &= covered
+                assert np.all(np.abs(got[need] - ref[need]) / bound[need] <= TOL), (step, r)
+            # the next step's reference input is what the engine holds (every rank's own rows are authoritative),
+            # so that rounding differences of earlier steps do not count against the tolerance of this one
+            nxt = np.zeros(n)
+            for r, e in enumerate(ex):
+                a, b = ranges[r]
+                nxt[a:a + b] = e.vector((step + 1) & 1)[a:a + b].cpu().numpy()
+            for e in ex:   # rows nobody owns are zero in every step's result (VecInit(y, 0), CsxKernels.cpp:93)
+                assert np.all(e.vector((step + 1) & 1).cpu().numpy()[~covered] == 0.0)
+            cur = nxt
+        for e in ex:
+            e.close()
+        for A in mats:
+            A.close()
