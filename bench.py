@@ -222,6 +222,8 @@ def main():
     enc_log = sparsex_b200.lib().csxb_part_log(eng._h, 0).decode()
     row_lo = sparsex_b200.lib().csxb_part_info(eng._h, 0, 3)
     row_n = sparsex_b200.lib().csxb_part_info(eng._h, 0, 1)
+    if str(opts.get("spx.matrix.symmetric", "false")) == "true":   # CSX-Sym partitions own dvalues.size() rows
+        row_n = sparsex_b200.lib().csxb_part_info(eng._h, 0, 8)
     traffic = eng.traffic()
     del rp, ci, va
 
@@ -241,6 +243,7 @@ def main():
         peer.vector(0).copy_(x)
         exchange_kind = "fused into the SpMV kernel: rows other ranks read are stored into their vectors over NVLink (peer memory), device-side flags order the steps"
     elif world > 1:
+        symred = None
         from sparsex_b200.dist import PieceExchange, WindowExchange, gather_row_ranges
         L = sparsex_b200.lib()
         ranges = gather_row_ranges(row_lo, row_n, "cuda")
@@ -248,6 +251,13 @@ def main():
         allwin = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(allwin, win)
         windows = [(int(t[0]), int(t[1])) for t in allwin]
+        if sym:   # CSX-Sym: transposed contributions to rows of lower ranks are sent to their owners and added
+            from sparsex_b200.dist import SymHaloReduce
+            hl = torch.tensor([L.csxb_info(eng._h, 8), L.csxb_info(eng._h, 9)], dtype=torch.int64, device="cuda")
+            allh = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, hl)
+            symred = SymHaloReduce(ranges, [(int(t[0]), int(t[1])) for t in allh], rank, y)
+            windows = [(w[0], max(w[1], r[0] + r[1] - 1)) for w, r in zip(windows, ranges)]
         wx = WindowExchange(ranges, windows, rank)
         frac = torch.tensor([wx.fraction], dtype=torch.float64, device="cuda")
         dist.all_reduce(frac, op=dist.ReduceOp.MAX)
@@ -256,6 +266,8 @@ def main():
         else:
             pieces = [PieceExchange(xbuf[0], ranges), PieceExchange(xbuf[1], ranges)]
             exchange_kind = "NCCL all-gather of the y pieces"
+        if sym:
+            exchange_kind = "CSX-Sym halo reduction to the owners (grouped NCCL send/recv + add), then " + exchange_kind
     state = {"cur": 0}
 
     def step():
@@ -265,6 +277,8 @@ def main():
         src, dst = xbuf[state["cur"]], xbuf[1 - state["cur"]]
         eng.spmv(alpha, src, dst, overwrite=True)
         if world > 1:
+            if sym and symred is not None:
+                symred(dst)
             if exchange is not None:
                 exchange(dst)
             else:  # dst's own rows -> every rank's dst

@@ -4,6 +4,10 @@
 // std::set iteration order, std::sort on (row, col)) so that order-dependent
 // behaviour is inherited rather than re-derived.  Non-NUMA branches only
 // (SPX_USE_NUMA == 0).  Citations are file:line into /root/reference/.
+// PINNED TO THE REFERENCE: oracle/build_refenc.py compiles the reference's own encoder (its headers and
+// Encodings/Runtime/Statistics/CtlBuilder/CsxUtil sources, g++ against the stand-in headers of oracle/refshim);
+// this restatement reproduces its ctl / values / id_map / dvalues bit for bit on the 1002 seeded cases of
+// tests/refpin_cases.py (tests/golden/ref_encodings.json, tests/test_cpu_refpin.py).
 #include "csx_oracle.hpp"
 
 #include <algorithm>
