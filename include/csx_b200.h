@@ -103,6 +103,20 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
 int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double beta, double *h_y,
                    int overwrite);
 
+/* ---- tuned-matrix container, single entries -------------------------------------
+ * csxb_save / csxb_load replace SaveTuned / LoadTuned (src/internals/Facade.cpp,
+ * CsxSaveRestore.hpp:77-370, a boost::archive) with a Boost-free container of the
+ * CSX arrays (values, ctl, id_map, rows_info, dvalues, reduction map, options);
+ * a loaded matrix is uploaded with csxb_upload like a freshly tuned one (the GPU
+ * tables are rebuilt from ctl).  csxb_get_entry / csxb_set_entry replace GetValue /
+ * SetValue (CsxGetSet.hpp:84-537): zero-based (row, col); return 0, 1 when the
+ * entry is not stored (or the row is not local), < 0 on error.  set updates the
+ * host copy and the device copy, so the next SpMV sees it without re-tuning. */
+int csxb_save(csxb_matrix_t *m, const char *path);
+csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen);
+int csxb_get_entry(csxb_matrix_t *m, int64_t row, int64_t col, double *value);
+int csxb_set_entry(csxb_matrix_t *m, int64_t row, int64_t col, double value);
+
 /* ---- repeated SpMV across GPUs, exchange over peer memory -------------------
  * Replaces the shared-memory x vector of the reference's thread pool
  * (CsxKernels.cpp:35-129: all threads read one x) for one process per GPU.

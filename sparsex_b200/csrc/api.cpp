@@ -282,26 +282,71 @@ spx_index_t spx_mat_get_nnz(const spx_matrix_t *A) {
   return A->nnz;
 }
 
-// Out of scope for this engine (SURVEY.md section 8b "may stub"): fail through the handler.
-spx_error_t spx_mat_get_entry(const spx_matrix_t *A, spx_index_t, spx_index_t, spx_value_t *, ...) {
-  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
-  SETERROR_1(SPX_ERR_ENTRY_NOT_FOUND, "spx_mat_get_entry is not provided by the B200 engine");
-  return SPX_FAILURE;
+// Single entries (matvec.c:322-403): the optional argument selects the indexing; anything else means zero-based.
+static int entry_indexing(va_list ap) {
+  int indexing = va_arg(ap, int) - SPX_INDEX_ZERO_BASED;
+  return (indexing == 0 || indexing == 1) ? indexing : 0;
 }
-spx_error_t spx_mat_set_entry(spx_matrix_t *A, spx_index_t, spx_index_t, spx_value_t, ...) {
+spx_error_t spx_mat_get_entry(const spx_matrix_t *A, spx_index_t row, spx_index_t column, spx_value_t *value, ...) {
+  va_list ap;
+  va_start(ap, value);
+  const int indexing = entry_indexing(ap);
+  va_end(ap);
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
-  SETERROR_1(SPX_ERR_ENTRY_NOT_FOUND, "spx_mat_set_entry is not provided by the B200 engine");
-  SETWARNING(SPX_WARN_ENTRY_NOT_SET);
-  return SPX_FAILURE;
+  if (row - indexing < 0 || row - indexing >= A->nrows || column - indexing < 0 || column - indexing >= A->ncols) {
+    SETERROR_0(SPX_OUT_OF_BOUNDS);
+    return SPX_FAILURE;
+  }
+  if (!value || csxb_get_entry(A->csx, row - indexing, column - indexing, value) != 0) {
+    SETERROR_0(SPX_ERR_ENTRY_NOT_FOUND);
+    return SPX_FAILURE;
+  }
+  return SPX_SUCCESS;
 }
-spx_error_t spx_mat_save(const spx_matrix_t *A, const char *) {
+spx_error_t spx_mat_set_entry(spx_matrix_t *A, spx_index_t row, spx_index_t column, spx_value_t value, ...) {
+  va_list ap;
+  va_start(ap, value);
+  const int indexing = entry_indexing(ap);
+  va_end(ap);
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
-  SETERROR_1(SPX_ERR_FILE, "spx_mat_save is not provided by the B200 engine");
-  return SPX_FAILURE;
+  if (row - indexing < 0 || row - indexing >= A->nrows || column - indexing < 0 || column - indexing >= A->ncols) {
+    SETERROR_0(SPX_OUT_OF_BOUNDS);
+    return SPX_FAILURE;
+  }
+  if (csxb_set_entry(A->csx, row - indexing, column - indexing, value) != 0) {
+    SETERROR_0(SPX_ERR_ENTRY_NOT_FOUND);
+    return SPX_FAILURE;
+  }
+  return SPX_SUCCESS;
 }
-spx_matrix_t *spx_mat_restore(const char *) {
-  SETERROR_1(SPX_ERR_TUNED_MAT, "spx_mat_restore is not provided by the B200 engine");
-  return SPX_INVALID_MAT;
+// Tuned-matrix container (matvec.c:405-445; the file format is this engine's own, not the reference's boost::archive)
+spx_error_t spx_mat_save(const spx_matrix_t *A, const char *filename) {
+  if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
+  if (!filename) { SETWARNING(SPX_WARN_CSXFILE); filename = "csx_file"; }
+  if (csxb_save(A->csx, filename) != 0) {
+    spx_err_get_handler()(SPX_ERR_FILE, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+    return SPX_FAILURE;
+  }
+  return SPX_SUCCESS;
+}
+spx_matrix_t *spx_mat_restore(const char *filename) {
+  if (!filename || access(filename, F_OK | R_OK) == -1) { SETERROR_0(SPX_ERR_FILE); return SPX_INVALID_MAT; }
+  char err[512] = "";
+  csxb_matrix_t *m = csxb_load(filename, err, sizeof(err));
+  if (!m) { spx_err_get_handler()(SPX_ERR_FILE, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
+  if (csxb_upload(m, g_device, 0) != 0) {
+    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+    csxb_destroy(m);
+    return SPX_INVALID_MAT;
+  }
+  spx_matrix_t *A = spx_malloc(spx_matrix_t, sizeof(spx_matrix_t));
+  A->nrows = (spx_index_t)csxb_info(m, CSXB_NROWS); A->ncols = (spx_index_t)csxb_info(m, CSXB_NCOLS);
+  A->nnz = (spx_index_t)csxb_info(m, CSXB_NNZ);
+  A->symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
+  A->permutation = SPX_INVALID_PERM;
+  A->csx = m;
+  A->stage_x = A->stage_y = nullptr;
+  return A;
 }
 spx_perm_t *spx_mat_get_perm(const spx_matrix_t *A) {
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_INVALID_PERM; }

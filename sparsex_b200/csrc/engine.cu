@@ -376,6 +376,7 @@ struct csxb_matrix {
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
   int64_t bytes[7] = {0, 0, 0, 0, 0, 0, 0};
   std::vector<std::string> logs;
+  std::vector<RowIndex> row_index;   // per partition, built on the first csxb_get/set_entry
   ~csxb_matrix() {
     if (!allocs.empty() || d_x || d_y || s_h2d) {
       int cur = -1;
@@ -951,6 +952,85 @@ void csxb_xchg_destroy(csxb_xchg_t *h) {
     if (q != h->rank && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
   if (h->base) cudaFree(h->base);
   delete h;
+}
+
+// ---- tuned-matrix container and single-entry access ------------------
+int csxb_save(csxb_matrix_t *m, const char *path) {
+  if (!m || !path) return fail("invalid argument");
+  CsxMatrix &H = m->host;
+  for (size_t i = 0; i < H.parts.size(); i++) {   // values released at upload come back from the device
+    CsxPartition &p = H.parts[i];
+    if ((int64_t)p.values.size() == p.nnz) continue;
+    if (!m->uploaded) return fail("partition values are neither on the host nor on a device");
+    CUDA_TRY(cudaSetDevice(m->device));
+    p.values.resize((size_t)p.nnz);
+    CUDA_TRY(cudaMemcpy(p.values.data(), m->d_values + m->layout.parts[i].val_base, (size_t)p.nnz * 8, cudaMemcpyDeviceToHost));
+  }
+  std::string e = save_matrix(H, path);
+  return e.empty() ? 0 : fail(e);
+}
+
+csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen) {
+  if (!path) { put_err(err, errlen, "invalid file name"); return nullptr; }
+  csxb_matrix *m = new csxb_matrix;
+  std::string e = load_matrix(path, m->host);
+  if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
+  return m;
+}
+
+// Locates A(row, col) (zero-based): partition, index into its values (or into dvalues when diag is set).
+static int locate_entry(csxb_matrix *m, int64_t row, int64_t col, size_t &part, int64_t &idx, bool &diag) {
+  CsxMatrix &H = m->host;
+  if (row < 0 || row >= H.nrows || col < 0 || col >= H.ncols) return fail("index out of bounds");
+  diag = false;
+  if (H.symmetric) {
+    if (col > row) std::swap(row, col);   // the lower triangle is what is stored (CsxGetSet.hpp:84-135)
+    diag = row == col;
+  }
+  if (m->row_index.size() != H.parts.size()) m->row_index.assign(H.parts.size(), RowIndex());
+  for (size_t i = 0; i < H.parts.size(); i++) {
+    CsxPartition &p = H.parts[i];
+    const int64_t owned = H.symmetric ? (int64_t)p.dvalues.size() : p.nrows;
+    if (row < p.row_start || row >= p.row_start + owned) continue;
+    part = i;
+    if (diag) { idx = row - p.row_start; return 0; }
+    RowIndex &ri = m->row_index[i];
+    if (ri.ctl_off.empty()) {
+      std::string e = build_row_index(p, H.full_colind, ri);
+      if (!e.empty()) return fail(e);
+    }
+    idx = find_entry(p, H.full_colind, ri, row - p.row_start, col);
+    return idx < 0 ? 1 : 0;
+  }
+  return 1;   // the row belongs to no local partition
+}
+
+int csxb_get_entry(csxb_matrix_t *m, int64_t row, int64_t col, double *value) {
+  size_t part; int64_t idx; bool diag;
+  const int rc = locate_entry(m, row, col, part, idx, diag);
+  if (rc) return rc;
+  CsxPartition &p = m->host.parts[part];
+  if (diag) { *value = p.dvalues[(size_t)idx]; return 0; }
+  if ((int64_t)p.values.size() == p.nnz) { *value = p.values[(size_t)idx]; return 0; }
+  if (!m->uploaded) return fail("partition values are neither on the host nor on a device");
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaMemcpy(value, m->d_values + m->layout.parts[part].val_base + idx, 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int csxb_set_entry(csxb_matrix_t *m, int64_t row, int64_t col, double value) {
+  size_t part; int64_t idx; bool diag;
+  const int rc = locate_entry(m, row, col, part, idx, diag);
+  if (rc) return rc;
+  CsxPartition &p = m->host.parts[part];
+  if (diag) p.dvalues[(size_t)idx] = value;
+  else if ((int64_t)p.values.size() == p.nnz) p.values[(size_t)idx] = value;
+  if (m->uploaded) {   // the device copy is what the kernels read
+    CUDA_TRY(cudaSetDevice(m->device));
+    double *dst = diag ? const_cast<double *>(m->pdev[part].dvalues) + idx : m->d_values + m->layout.parts[part].val_base + idx;
+    CUDA_TRY(cudaMemcpy(dst, &value, 8, cudaMemcpyHostToDevice));
+  }
+  return 0;
 }
 
 int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t *cols) {

@@ -25,6 +25,8 @@ inline uint64_t get_varint(const uint8_t *ctl, uint64_t &p) {
   return v;
 }
 
+}  // namespace
+
 // pattern id (CsxUtil.hpp:58-74, CsxUtil.cpp:27-33) -> kernel kind
 bool classify(long pid, KindEntry &ke) {
   int type = (int)(pid / PATTERN_ID_OFFSET);
@@ -52,6 +54,8 @@ bool classify(long pid, KindEntry &ke) {
   ke.delta = delta;
   return true;
 }
+
+namespace {
 
 struct Pending { int64_t part; int64_t tile; XDesc d; };
 

@@ -124,5 +124,22 @@ struct DeviceLayout {
 
 // Decodes every local partition's ctl stream and fills the tables.
 std::string build_layout(const CsxMatrix &m, DeviceLayout &out);
+// pattern id (CsxUtil.hpp:58-74, CsxUtil.cpp:27-33) -> kernel kind
+bool classify(long pid, KindEntry &ke);
+
+// csx_tools.cpp ------------------------------------------------------------------------------------------------
+// Per-row entry points into the ctl stream (built lazily for spx_mat_get/set_entry).
+struct RowIndex {
+  std::vector<uint64_t> ctl_off;   // offset of the row's first unit head (UINT64_MAX: the row has no unit)
+  std::vector<uint64_t> val_off;   // index of its first value
+  std::vector<int32_t> span;       // rows below this one that its units reach
+  int32_t max_span = 0;
+};
+std::string build_row_index(const CsxPartition &cp, bool full_colind, RowIndex &ri);
+// index (partition relative) of the value stored for (partition-relative row, zero-based column), or -1
+int64_t find_entry(const CsxPartition &cp, bool full_colind, const RowIndex &ri, int64_t prow, int64_t col);
+// tuned matrix <-> file (Boost-free container; the GPU tables are rebuilt from ctl at upload)
+std::string save_matrix(const CsxMatrix &m, const char *path);
+std::string load_matrix(const char *path, CsxMatrix &m);
 
 }  // namespace spxb

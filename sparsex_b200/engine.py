@@ -60,6 +60,14 @@ def lib():
     L.csxb_spmv_host.argtypes = [vp, dbl, vp, dbl, vp, i32]
     L.csxb_decode_coords.restype = i32
     L.csxb_decode_coords.argtypes = [vp, i32, vp, vp]
+    L.csxb_save.restype = i32
+    L.csxb_save.argtypes = [vp, cp]
+    L.csxb_load.restype = vp
+    L.csxb_load.argtypes = [cp, cp, C.c_size_t]
+    L.csxb_get_entry.restype = i32
+    L.csxb_get_entry.argtypes = [vp, i64, i64, C.POINTER(dbl)]
+    L.csxb_set_entry.restype = i32
+    L.csxb_set_entry.argtypes = [vp, i64, i64, dbl]
     L.csxb_xchg_create.restype = vp
     L.csxb_xchg_create.argtypes = [vp, i32, i32]
     L.csxb_xchg_handle.restype = i32
@@ -182,6 +190,32 @@ class CsxMatrix(object):
         if lib().csxb_spmv_host(self._h, alpha, x.ctypes.data, beta, y.ctypes.data, int(overwrite)) != 0:
             raise EngineError(lib().csxb_last_error().decode())
         return y
+
+    def save(self, path):
+        if lib().csxb_save(self._h, path.encode()) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    @classmethod
+    def load(cls, path):
+        err = C.create_string_buffer(1024)
+        h = lib().csxb_load(path.encode(), err, 1024)
+        if not h:
+            raise EngineError(err.value.decode())
+        return cls(h)
+
+    def get_entry(self, row, col):
+        """A(row, col), zero-based; None when the entry is not stored."""
+        v = C.c_double()
+        rc = lib().csxb_get_entry(self._h, row, col, C.byref(v))
+        if rc < 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return v.value if rc == 0 else None
+
+    def set_entry(self, row, col, value):
+        rc = lib().csxb_set_entry(self._h, row, col, value)
+        if rc < 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return rc == 0
 
     def decode_coords(self, p):
         n = lib().csxb_part_info(self._h, p, 0)

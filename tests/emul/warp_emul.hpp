@@ -8,6 +8,7 @@
 #include <ucontext.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 struct uint4 { uint32_t x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 using std::min;
+using std::fma;
 
 namespace warp_emul {
 constexpr int LANES = 32;

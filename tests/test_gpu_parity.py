@@ -356,3 +356,73 @@ def test_peer_exchange_logical_ranks(world):
             e.close()
         for A in mats:
             A.close()
+
+
+def test_set_entry_and_restore_on_device(tmp_path):
+    """SURVEY.md 8f rows 2-3 on the device: csxb_set_entry updates the uploaded values (next SpMV sees it without
+    re-tuning, also when the host copy was released), and a matrix restored from the container multiplies like the
+    tuned one; then the same through spx_mat_set_entry / spx_mat_save / spx_mat_restore."""
+    torch = _torch()
+    import ctypes as C
+    from sparsex_b200 import CsxMatrix, load_spx_api
+    rng = np.random.default_rng(11)
+    n = 900
+    for sym in (False, True):
+        rp, ci, va = random_structured(rng, n, n, symmetric=sym)
+        opts = {"spx.preproc.sampling": "none", "spx.rt.nr_threads": 2}
+        if sym:
+            opts["spx.matrix.symmetric"] = "true"
+        A = CsxMatrix.tune_csr(rp, ci, va, n, n, opts).upload(0, free_host=True)
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        va2 = va.copy()
+        for _ in range(40):
+            k = int(rng.integers(len(va)))
+            r, c = int(rows[k]), int(ci[k])
+            nv = float(rng.standard_normal())
+            assert A.get_entry(r, c) == va2[k]          # read back from the device copy
+            assert A.set_entry(r, c, nv)
+            va2[k] = nv
+            if sym and r != c:                         # the mirrored entry is the same stored value
+                k2 = rp[c] + int(np.searchsorted(ci[rp[c]:rp[c + 1]], r))
+                va2[k2] = nv
+        x = rng.uniform(-1, 1, n)
+        y = np.zeros(n)
+        A.spmv_host(1.0, x, y)
+        ref = _csr_spmv(rp, ci, va2, x, n)
+        bound = _abs_bound(rp, ci, va2, x, n) + 1e-300
+        assert np.max(np.abs(y - ref) / bound) <= TOL
+        path = os.path.join(str(tmp_path), "a.csxb")
+        A.save(path)                                    # values come back from the device for the container
+        B = CsxMatrix.load(path).upload(0)
+        y2 = np.zeros(n)
+        B.spmv_host(1.0, x, y2)
+        assert np.max(np.abs(y2 - ref) / bound) <= TOL
+        A.close()
+        B.close()
+    # drop-in API
+    api = load_spx_api()
+    api.spx_init()
+    rp, ci, va = random_structured(rng, 500, 500)
+    api.spx_option_set(b"spx.preproc.sampling", b"none")
+    api.spx_option_set(b"spx.rt.nr_threads", b"1")
+    api.spx_option_set(b"spx.matrix.symmetric", b"false")
+    inp = api.spx_input_load_csr(rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 500, 500)
+    M = api.spx_mat_tune(inp)
+    assert M
+    v = C.c_double()
+    assert api.spx_mat_get_entry(M, int(0), int(ci[rp[0]]), C.byref(v)) == 0 or rp[1] == rp[0]
+    k = int(rp[250])
+    r = int(np.searchsorted(rp, k, side="right") - 1)
+    api.L.spx_mat_set_entry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+    assert api.L.spx_mat_set_entry(M, r, int(ci[k]), 9.25) == 0
+    path = os.path.join(str(tmp_path), "b.csxb").encode()
+    api.L.spx_mat_save.argtypes = [C.c_void_p, C.c_char_p]
+    api.L.spx_mat_restore.restype = C.c_void_p
+    api.L.spx_mat_restore.argtypes = [C.c_char_p]
+    assert api.L.spx_mat_save(M, path) == 0
+    R = api.L.spx_mat_restore(path)
+    assert R
+    assert api.spx_mat_get_entry(R, r, int(ci[k]), C.byref(v)) == 0 and v.value == 9.25
+    api.spx_mat_destroy(M)
+    api.spx_mat_destroy(R)
+    api.spx_input_destroy(inp)

@@ -9,14 +9,16 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sparsex_b200 import CsxMatrix, PeerExchange  # noqa: E402
-from tests.matrices import poisson2d  # noqa: E402
+from tests.matrices import poisson2d, stencil27  # noqa: E402
 
 g = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 parts = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 rpt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-rp, ci, va, n = poisson2d(g)
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+rp, ci, va, n = stencil27(-g) if g < 0 else poisson2d(g)
 A = CsxMatrix.tune_csr(rp, ci, va, n, n, {"spx.rt.nr_threads": parts, "spx.b200.rows_info": "false", "spx.b200.rows_per_thread": rpt},
-                       part_lo=0, part_hi=1).upload(0)
+                       part_lo=which, part_hi=which + 1).upload(0)
+print("traffic", A.traffic())
 print("grid %d, partition 0 of %d, rows per thread %d" % (g, parts, rpt))
 x = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, n)).cuda()
 y = torch.zeros_like(x)
