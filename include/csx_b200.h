@@ -117,6 +117,15 @@ csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen);
 int csxb_get_entry(csxb_matrix_t *m, int64_t row, int64_t col, double *value);
 int csxb_set_entry(csxb_matrix_t *m, int64_t row, int64_t col, double value);
 
+/* ---- BLAS-1 on device-resident vectors -------------------------------------------
+ * What a solver iteration needs next to the SpMV, so that it stays on the GPU
+ * (VecScale / VecScaleAdd / VecAdd / VecSub / VecMult, src/internals/Vector.cpp:259-377).
+ * Pointers are device-accessible (cudaMalloc or managed memory).
+ *   axpby : out[i] = alpha*a[i] + beta*b[i]   (b may be NULL with beta ignored; out may alias a or b)
+ *   dot   : *result = sum a[i]*b[i]           (synchronises `stream`; fixed reduction order) */
+int csxb_vec_axpby(double *d_out, const double *d_a, const double *d_b, double alpha, double beta, int64_t n, void *stream);
+int csxb_vec_dot(const double *d_a, const double *d_b, int64_t n, double *result, void *stream);
+
 /* ---- repeated SpMV across GPUs, exchange over peer memory -------------------
  * Replaces the shared-memory x vector of the reference's thread pool
  * (CsxKernels.cpp:35-129: all threads read one x) for one process per GPU.

@@ -31,6 +31,7 @@ std::map<std::string, std::string> &props() {
 }
 int g_device = 0;
 bool g_async = false;
+bool g_gpu_ok = false;   // a managed vector was allocated successfully: a usable GPU is present
 int g_part_lo = 0, g_part_hi = -1;   // one process per GPU: encode and own only partitions [lo, hi)
 int g_log_level = 2;  // 0 none, 1 error, 2 warning, 3 info, 4 verbose, 5 debug
 FILE *g_log_file = nullptr;
@@ -516,6 +517,7 @@ static spx_vector_t *vec_alloc(size_t size, bool zero) {
   size_t bytes = (size ? size : 1) * sizeof(spx_value_t);
   if (cudaMallocManaged(&p, bytes, cudaMemAttachGlobal) == cudaSuccess) {
     v->alloc_type = ALLOC_MANAGED;
+    g_gpu_ok = true;
     if (zero) memset(p, 0, bytes);
   } else {
     cudaGetLastError();  // no usable GPU: a plain host vector still works for the BLAS-1 helpers
@@ -574,37 +576,51 @@ spx_error_t spx_vec_set_entry(spx_vector_t *v, spx_index_t idx, spx_value_t val,
   v->elements[idx - 1] = val;
   return SPX_SUCCESS;
 }
-void spx_vec_scale(spx_vector_t *v1, spx_vector_t *v2, spx_value_t num) {
-  for (size_t i = 0; i < v1->size; i++) v2->elements[i] = num * v1->elements[i];
+// BLAS-1 helpers (Vector.cpp:259-377).  Vectors the library allocated live in managed memory and are resident in
+// HBM between SpMVs: for those the operation runs on the GPU (csxb_vec_*), so that a solver iteration does not
+// migrate them back to the host; user buffers take the host loop.
+static bool on_device(const spx_vector_t *a, const spx_vector_t *b, const spx_vector_t *c) {
+  return g_gpu_ok && a && is_managed(a) && (!b || is_managed(b)) && (!c || is_managed(c));
 }
-void spx_vec_scale_add(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_value_t num) {
-  for (size_t i = 0; i < v1->size; i++) v3->elements[i] = v1->elements[i] + num * v2->elements[i];
+static void device_done() { if (!g_async) cudaStreamSynchronize(0); }
+// out[s:e) = alpha*a[s:e) + beta*b[s:e)
+static void axpby(spx_vector_t *out, const spx_vector_t *a, const spx_vector_t *b, double alpha, double beta, size_t s, size_t e) {
+  if (e <= s) return;
+  if (on_device(out, a, b) && csxb_vec_axpby(out->elements + s, a->elements + s, b ? b->elements + s : nullptr, alpha, beta,
+                                             (int64_t)(e - s), nullptr) == 0) {
+    device_done();
+    return;
+  }
+  cudaDeviceSynchronize();   // pending device work on managed vectors must finish before the host touches them
+  if (b) for (size_t i = s; i < e; i++) out->elements[i] = alpha * a->elements[i] + beta * b->elements[i];
+  else for (size_t i = s; i < e; i++) out->elements[i] = alpha * a->elements[i];
 }
+static double dot(const spx_vector_t *a, const spx_vector_t *b, size_t s, size_t e) {
+  double r = 0;
+  if (e <= s) return r;
+  if (on_device(a, b, nullptr) && csxb_vec_dot(a->elements + s, b->elements + s, (int64_t)(e - s), &r, nullptr) == 0) return r;
+  cudaDeviceSynchronize();
+  r = 0;
+  for (size_t i = s; i < e; i++) r += a->elements[i] * b->elements[i];
+  return r;
+}
+void spx_vec_scale(spx_vector_t *v1, spx_vector_t *v2, spx_value_t num) { axpby(v2, v1, nullptr, num, 0.0, 0, v1->size); }
+void spx_vec_scale_add(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_value_t num) { axpby(v3, v1, v2, 1.0, num, 0, v1->size); }
 void spx_vec_scale_add_part(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_value_t num, spx_index_t start,
                             spx_index_t end) {
-  for (spx_index_t i = start; i < end; i++) v3->elements[i] = v1->elements[i] + num * v2->elements[i];
+  axpby(v3, v1, v2, 1.0, num, (size_t)start, (size_t)end);
 }
-void spx_vec_add(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3) {
-  for (size_t i = 0; i < v1->size; i++) v3->elements[i] = v1->elements[i] + v2->elements[i];
-}
+void spx_vec_add(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3) { axpby(v3, v1, v2, 1.0, 1.0, 0, v1->size); }
 void spx_vec_add_part(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_index_t start, spx_index_t end) {
-  for (spx_index_t i = start; i < end; i++) v3->elements[i] = v1->elements[i] + v2->elements[i];
+  axpby(v3, v1, v2, 1.0, 1.0, (size_t)start, (size_t)end);
 }
-void spx_vec_sub(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3) {
-  for (size_t i = 0; i < v1->size; i++) v3->elements[i] = v1->elements[i] - v2->elements[i];
-}
+void spx_vec_sub(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3) { axpby(v3, v1, v2, 1.0, -1.0, 0, v1->size); }
 void spx_vec_sub_part(spx_vector_t *v1, spx_vector_t *v2, spx_vector_t *v3, spx_index_t start, spx_index_t end) {
-  for (spx_index_t i = start; i < end; i++) v3->elements[i] = v1->elements[i] - v2->elements[i];
+  axpby(v3, v1, v2, 1.0, -1.0, (size_t)start, (size_t)end);
 }
-spx_value_t spx_vec_mul(const spx_vector_t *v1, const spx_vector_t *v2) {
-  spx_value_t r = 0;
-  for (size_t i = 0; i < v1->size; i++) r += v1->elements[i] * v2->elements[i];
-  return r;
-}
+spx_value_t spx_vec_mul(const spx_vector_t *v1, const spx_vector_t *v2) { return dot(v1, v2, 0, v1->size); }
 spx_value_t spx_vec_mul_part(const spx_vector_t *v1, const spx_vector_t *v2, spx_index_t start, spx_index_t end) {
-  spx_value_t r = 0;
-  for (spx_index_t i = start; i < end; i++) r += v1->elements[i] * v2->elements[i];
-  return r;
+  return dot(v1, v2, (size_t)start, (size_t)end);
 }
 spx_error_t spx_vec_reorder(spx_vector_t *v, spx_perm_t *p) {  // matvec.c:934-958
   if (p == SPX_INVALID_PERM) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid permutation"); return SPX_FAILURE; }

@@ -954,6 +954,61 @@ void csxb_xchg_destroy(csxb_xchg_t *h) {
   delete h;
 }
 
+// ---- BLAS-1 on device-resident vectors (Vector.cpp:259-377) ------------------
+// out = alpha*a + beta*b over [0, n); out may alias a or b.  One pass, 16-byte accesses where aligned.
+__global__ void __launch_bounds__(256) csx_vec_axpby_kernel(double *__restrict__ out, const double *a, const double *b, double alpha,
+                                                            double beta, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double bv = b ? b[i] : 0.0;
+    out[i] = alpha * a[i] + beta * bv;
+  }
+}
+// partial dot products: one double per CTA (fixed grid, fixed order: deterministic for a given n)
+__global__ void __launch_bounds__(256) csx_vec_dot_kernel(const double *__restrict__ a, const double *__restrict__ b, long long n,
+                                                          double *__restrict__ partial) {
+  __shared__ double warp_part[8];
+  double s = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s = fma(a[i], b[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += warp_part[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+int csxb_vec_axpby(double *d_out, const double *d_a, const double *d_b, double alpha, double beta, int64_t n, void *stream) {
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  csx_vec_axpby_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_out, d_a, d_b, alpha, beta, (long long)n);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int csxb_vec_dot(const double *d_a, const double *d_b, int64_t n, double *result, void *stream) {
+  *result = 0.0;
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4);
+  static thread_local double *d_partial = nullptr;
+  static thread_local double *h_partial = nullptr;
+  if (!d_partial) {
+    CUDA_TRY(cudaMalloc((void **)&d_partial, 148 * 4 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost((void **)&h_partial, 148 * 4 * sizeof(double)));
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  csx_vec_dot_kernel<<<grid, 256, 0, s>>>(d_a, d_b, (long long)n, d_partial);
+  CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, grid * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  double t = 0.0;
+  for (unsigned i = 0; i < grid; i++) t += h_partial[i];
+  *result = t;
+  return 0;
+}
+
 // ---- tuned-matrix container and single-entry access ------------------
 int csxb_save(csxb_matrix_t *m, const char *path) {
   if (!m || !path) return fail("invalid argument");
