@@ -36,6 +36,9 @@ WORKLOADS = {
     "c4": ("c4_sym_block_banded_30M", dict(kind="symbb", nb=10_000_000, b=1024), {"spx.matrix.symmetric": "true"},
            dict(kind="symbb", nb=500_000, b=1024)),
     "c5": ("c5_rmat_26", dict(kind="rmat", scale=26), {"spx.preproc.xform": "none"}, dict(kind="rmat", scale=20)),
+    "c5s": ("c5_rmat_23_scaled_down", dict(kind="rmat", scale=23), {"spx.preproc.xform": "none"}, dict(kind="rmat", scale=20)),
+    "c4s": ("c4_sym_block_banded_3M_scaled_down", dict(kind="symbb", nb=1_000_000, b=1024), {"spx.matrix.symmetric": "true"},
+            dict(kind="symbb", nb=200_000, b=1024)),
     "small": ("small_poisson2d_512", dict(kind="poisson2d", g=512), {}, dict(kind="poisson2d", g=256)),
 }
 
@@ -380,6 +383,7 @@ def main():
            "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory); every rank uploads the "
                   "columns its partition reads and downloads its rows, slab-pipelined (H2D, kernels, D2H overlap)"}
     # check the device-resident result against the host-buffer path on the same x
+    peer_used = peer is not None
     if peer is not None:
         barrier()
         peer.close()
@@ -413,7 +417,7 @@ def main():
                              "algorithmic_bytes": traffic["total"],
                              "bytes": {k: traffic[k] for k in ("values", "ctl", "tables", "x", "y")},
                              "frac_of_8TBs_nominal": achieved / 8000.0},
-                "e2e": e2e, "gpu_launches": int(traffic["launches"]) * args.steps, "clocks": clocks}
+                "e2e": e2e, "gpu_launches": (int(traffic["launches"]) + (1 if peer_used else 0)) * args.steps, "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = cpu_reference_run(sample_kw, opts, 32, 2)

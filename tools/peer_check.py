@@ -60,6 +60,34 @@ def main():
         dist.barrier()
         ex.close()
         A.close()
+    # CSX-Sym across ranks: local SpMV, transposed contributions sent to their owners (SymHaloReduce, NCCL)
+    from sparsex_b200 import lib
+    from sparsex_b200.dist import SymHaloReduce, gather_row_ranges
+    from tests.matrices import sym_block_banded
+    rp, ci, va, n = sym_block_banded(30000, b=256)
+    A = CsxMatrix.tune_csr(rp, ci, va, n, n, {"spx.rt.nr_threads": world, "spx.matrix.symmetric": "true"},
+                           part_lo=rank, part_hi=rank + 1).upload(local)
+    L = lib()
+    lo, cnt = L.csxb_part_info(A._h, 0, 3), L.csxb_part_info(A._h, 0, 8)
+    ranges = gather_row_ranges(lo, cnt, "cuda")
+    hl = torch.tensor([L.csxb_info(A._h, 8), L.csxb_info(A._h, 9)], dtype=torch.int64, device="cuda")
+    allh = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(allh, hl)
+    x = np.random.default_rng(9).uniform(-1, 1, n)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")
+    A.spmv(0.5, dx, dy, overwrite=True)
+    SymHaloReduce(ranges, [(int(t[0]), int(t[1])) for t in allh], rank, dy)(dy)
+    torch.cuda.synchronize()
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    ref = 0.5 * np.bincount(rows, weights=va * x[ci], minlength=n)
+    bound = 0.5 * np.bincount(rows, weights=np.abs(va * x[ci]), minlength=n) + 1e-300
+    worst = float(np.max(np.abs(dy[lo:lo + cnt].cpu().numpy() - ref[lo:lo + cnt]) / bound[lo:lo + cnt]))
+    good = worst <= 1e-12
+    ok &= good
+    print("rank %d/%d sym      rows [%d,+%d) halo %s  max err/bound %.2e  %s" % (rank, world, lo, cnt, tuple(int(v) for v in hl), worst,
+                                                                              "ok" if good else "FAIL"), flush=True)
+    A.close()
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     dist.barrier()
