@@ -39,6 +39,7 @@ WORKLOADS = {
     "c5s": ("c5_rmat_23_scaled_down", dict(kind="rmat", scale=23), {"spx.preproc.xform": "none"}, dict(kind="rmat", scale=20)),
     "c4s": ("c4_sym_block_banded_3M_scaled_down", dict(kind="symbb", nb=1_000_000, b=1024), {"spx.matrix.symmetric": "true"},
             dict(kind="symbb", nb=200_000, b=1024)),
+    "c2q": ("c2_poisson2d_2048_quarter_size", dict(kind="poisson2d", g=2048), {}, dict(kind="poisson2d", g=1024)),
     "small": ("small_poisson2d_512", dict(kind="poisson2d", g=512), {}, dict(kind="poisson2d", g=256)),
 }
 
@@ -90,7 +91,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def finish(self):
         self._stop_evt.set()
@@ -244,7 +245,8 @@ def main():
         from sparsex_b200.dist import connect_peer_exchange
         peer, ranges, windows = connect_peer_exchange(eng, rank, world, "cuda")
         peer.vector(0).copy_(x)
-        exchange_kind = "fused into the SpMV kernel: rows other ranks read are stored into their vectors over NVLink (peer memory), device-side flags order the steps"
+        exchange_kind = ("fused into the SpMV kernel: rows other ranks read are stored into their vectors over NVLink (peer memory), "
+                         "device-side flags order the steps; protocol %d (1: edge tiles first, no sync kernel), %d edge tiles" % peer.protocol())
     elif world > 1:
         symred = None
         from sparsex_b200.dist import PieceExchange, WindowExchange, gather_row_ranges
@@ -383,7 +385,7 @@ def main():
            "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory); every rank uploads the "
                   "columns its partition reads and downloads its rows, slab-pipelined (H2D, kernels, D2H overlap)"}
     # check the device-resident result against the host-buffer path on the same x
-    peer_used = peer is not None
+    peer_sync_kernel = peer is not None and peer.protocol()[0] == 0   # protocol 0 ends every step with a sync kernel
     if peer is not None:
         barrier()
         peer.close()
@@ -417,7 +419,7 @@ def main():
                              "algorithmic_bytes": traffic["total"],
                              "bytes": {k: traffic[k] for k in ("values", "ctl", "tables", "x", "y")},
                              "frac_of_8TBs_nominal": achieved / 8000.0},
-                "e2e": e2e, "gpu_launches": (int(traffic["launches"]) + (1 if peer_used else 0)) * args.steps, "clocks": clocks}
+                "e2e": e2e, "gpu_launches": (int(traffic["launches"]) + (1 if peer_sync_kernel else 0)) * args.steps, "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = cpu_reference_run(sample_kw, opts, 32, 2)

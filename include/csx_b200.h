@@ -142,7 +142,9 @@ int csxb_vec_dot(const double *d_a, const double *d_b, int64_t n, double *result
  *             win_lo/win_hi = first/last column every rank reads
  *   vector  : device pointer of vec[which]; fill vec[0] with the initial x (all columns the rank reads)
  *   spmv    : one step (asynchronous on `stream`)
- *   status  : what = 0 steps finished, 1 error word (non-zero: a wait for a neighbour timed out) */
+ *   status  : what = 0 steps finished, 1 error word (non-zero: a wait for a neighbour timed out),
+ *             2 protocol (1: edge tiles first — the tiles that touch other ranks run first in every step and
+ *             publish it at once, nothing else waits; 0: one sync kernel at the end of every step), 3 edge tiles */
 typedef struct csxb_xchg csxb_xchg_t;
 csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world);
 int csxb_xchg_handle(csxb_xchg_t *x, void *handle64);

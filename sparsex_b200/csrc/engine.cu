@@ -123,6 +123,14 @@ struct XchgDev {
   unsigned long long *peer_flags[XCHG_MAX_PEERS];   // neighbours' flag arrays (peer memory), same order as wait_rank
   long long push_lo[XCHG_MAX_PEERS], push_hi[XCHG_MAX_PEERS];   // global rows [lo, hi) of mine that peer p reads
   double *push_vec[XCHG_MAX_PEERS][2];     // that peer's ping-pong vectors (peer memory)
+  // "edge tiles first" protocol (mode 1; partitions whose rows are final after kernel 1): the tiles that read rows
+  // of other ranks or whose rows other ranks read are the first `nb` CTAs of the step's kernel.  They wait for the
+  // neighbours' edge tiles of the previous step, and the last of them to finish publishes this step to the
+  // neighbours — a whole step before anybody needs it.  The other tiles touch no remote data and never wait.
+  int mode;                                // 0: sync kernel at the end of every step, 1: edge tiles first
+  int nb;                                  // number of edge tiles
+  int edge_lo_end, edge_hi_begin;          // edge tiles are [0, edge_lo_end) and [edge_hi_begin, ntiles)
+  unsigned long long *started, *bdone;     // local counters: CTAs that have read the step number / edge CTAs finished
 };
 struct NoXchg {};
 
@@ -146,21 +154,13 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 // VAR = 1 (4-rows-per-thread diagonal instantiation) issues the eight loads of a unit as one inline-PTX block so
 // that all of them are in flight before the first FMA; ptxas otherwise interleaves loads and FMAs at 32 registers.
 enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
-template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0, class XP = NoXchg>
-__global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __grid_constant__ PartDev P,
-                                                                  const double *__restrict__ x,
-                                                                  double *__restrict__ y, double alpha, double beta,
-                                                                  int overwrite, const __grid_constant__ XP X) {
-  constexpr bool XCHG = !std::is_same<XP, NoXchg>::value;
+// The work of one warp of one tile.  PUSH: rows that other ranks read are also stored into their vectors (exchange).
+template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool PUSH, class XP>
+__device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__restrict__ x, double *__restrict__ y, double alpha,
+                                          double beta, int overwrite, const long long tile, const XP &X, const unsigned long long xk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = (long long)blockIdx.x + P.tile0;
   const long long lrow0 = ((tile * (CTA_THREADS / 32) + warp) * RPT) * 32;   // first row of this warp (partition relative)
   if (lrow0 >= P.nrows) return;
-  unsigned long long xk = 0;
-  if constexpr (XCHG) {   // vectors by step parity (the sync kernel that ended the previous step has seen the halo arrive)
-    xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
-    x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
-  }
   double acc[RPT];
 #pragma unroll
   for (int k = 0; k < RPT; k++) acc[k] = 0.0;
@@ -252,15 +252,72 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __gri
       if (SYM) a += __ldg(P.dvalues + lrow) * __ldg(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
       const double r = overwrite ? alpha * a : alpha * a + beta * y[g];
       y[g] = r;
-      if constexpr (XCHG) {   // the exchange: rows another rank's partition reads go straight into its next x.
-        // No fence here (a system fence per store would wait for every NVLink acknowledgement in turn): the
-        // sync kernel that ends the step runs after this kernel on the same stream and issues the system-scope
-        // fence and release before the neighbours are told that the step is complete.
+      if constexpr (PUSH) {   // the exchange: rows another rank's partition reads go straight into its next x.
+        // No fence per store (a system fence would wait for every NVLink acknowledgement in turn): the step is
+        // published to the neighbours only after a system-scope fence (edge CTAs below, or the sync kernel).
         for (int p = 0; p < X.npush; p++)
           if (g >= X.push_lo[p] && g < X.push_hi[p]) X.push_vec[p][(xk & 1) ^ 1][g] = r;
       }
     }
   }
+}
+
+// Edge CTA of the edge-tiles-first protocol (XchgDev.mode 1): waits for the neighbours' edge tiles of the previous
+// step, computes and pushes its tile, and the last edge CTA of the step publishes it.  Kept out of line so that
+// the interior path of the kernel keeps the register allocation of the plain kernel.
+template <bool XD, bool SYM, int RPT, int KSET, int VAR>
+__device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, double *y, double alpha, long long tile,
+                                           const XchgDev &X, int ypar) {
+  // only the edge CTAs use the device-resident step number (the flags count steps across graph replays)
+  const unsigned long long xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+  if (threadIdx.x == 0 && xk > 0) {   // halo of this step arrived; the neighbours no longer read the buffer pushed into
+    for (int i = 0; i < X.nwait; i++) {
+      const unsigned long long *f = X.flags + X.wait_rank[i];
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < xk) {
+        if (clock64() - t0 > 6000000000ll) { atomicExch(X.error, 1ull); break; }
+      }
+    }
+  }
+  __syncthreads();
+  // spmv_tile pushes into push_vec[p][(k & 1) ^ 1]: hand it a step number with the parity of the target buffer
+  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev>(P, x, y, alpha, 0.0, 1, tile, X, (unsigned long long)(ypar ^ 1));
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(X.bdone, 1ull) == (unsigned long long)X.nb - 1) {   // last edge CTA of the step
+    *reinterpret_cast<volatile unsigned long long *>(X.bdone) = 0;
+    *reinterpret_cast<volatile unsigned long long *>(X.step) = xk + 1;
+    __threadfence_system();
+    for (int i = 0; i < X.nwait; i++) st_release_sys(X.peer_flags[i] + X.rank, xk + 1);
+  }
+}
+
+template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0, class XP = NoXchg>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __grid_constant__ PartDev P,
+                                                                  const double *__restrict__ x,
+                                                                  double *__restrict__ y, double alpha, double beta,
+                                                                  int overwrite, const __grid_constant__ XP X) {
+  constexpr bool XCHG = !std::is_same<XP, NoXchg>::value;
+  const long long tile = (long long)blockIdx.x + P.tile0;
+  unsigned long long xk = 0;
+  if constexpr (XCHG) {   // vectors by step parity (protocol 0: the sync kernel that ended the previous step saw the halo arrive)
+    xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
+    x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
+  }
+  spmv_tile<XD, SYM, RPT, KSET, VAR, XCHG, XP>(P, x, y, alpha, beta, overwrite, tile, X, xk);
+}
+
+// Kernel 1 under the edge-tiles-first protocol (XchgDev.mode 1): CTAs [0, nb) take the tiles at both ends of the
+// partition (out of line: wait, compute, push, publish), the others the interior tiles, which touch no other rank
+// and run exactly the plain tile code.  x / y are the step's source and target vectors (the host alternates them,
+// so a captured graph must hold an even number of steps); `ypar` is the index of y among the ping-pong vectors.
+template <bool XD, int RPT, int KSET, int MINB = 8, int VAR = 0>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_xe_kernel(const __grid_constant__ PartDev P,
+                                                                     const double *__restrict__ x, double *__restrict__ y,
+                                                                     double alpha, int ypar, const __grid_constant__ XchgDev X) {
+  const int b = (int)blockIdx.x;
+  if (b < X.nb) spmv_edge_cta<XD, false, RPT, KSET, VAR>(P, x, y, alpha, b < X.edge_lo_end ? b : X.edge_hi_begin + (b - X.edge_lo_end), X, ypar);
+  else spmv_tile<XD, false, RPT, KSET, VAR, false, NoXchg>(P, x, y, alpha, 0.0, 1, (long long)X.edge_lo_end + (b - X.nb), NoXchg(), 0ull);
 }
 
 // Exchange for partitions whose rows are only final after the chunk kernel: copies the rows the peers read.
@@ -275,9 +332,10 @@ __global__ void __launch_bounds__(256) csx_xchg_push_kernel(const __grid_constan
   }
 }
 // Rows past the last partition's rows belong to nobody: zero in every step's result (VecInit(y, 0), CsxKernels.cpp:93).
-__global__ void __launch_bounds__(256) csx_xchg_zero_tail_kernel(const __grid_constant__ XchgDev X, long long lo, long long hi) {
+__global__ void __launch_bounds__(256) csx_xchg_zero_tail_kernel(const __grid_constant__ XchgDev X, long long lo, long long hi,
+                                                                 int ypar) {
   const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(X.step);
-  double *dst = X.vec[(k & 1) ^ 1];
+  double *dst = X.vec[ypar >= 0 ? ypar : (int)((k & 1) ^ 1)];   // protocol 1: the host names the step's target vector
   for (long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < hi; g += (long long)gridDim.x * blockDim.x) dst[g] = 0.0;
 }
 // End of a step (one warp): publish "rank finished step k" to every neighbour, advance the local step counter,
@@ -701,6 +759,24 @@ static void launch_gather(const PartDev &P0, const PartLayout &pl, int64_t t0, i
     else launch_gather_k<SYM, 1, KSET_ANY>(P, pl, nt, x, y, alpha, beta, overwrite, s, X);
   }
 }
+// Kernel 1 of a whole partition under the edge-tiles-first exchange protocol.
+static void launch_gather_xe(const PartDev &P0, const PartLayout &pl, const double *x, double *y, double alpha, int ypar,
+                             cudaStream_t s, const XchgDev &X) {
+  if (!pl.ntiles) return;
+  PartDev P = P0;
+  P.tile0 = 0;
+  dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
+  const bool xd = !pl.xdesc.empty(), diag1 = pl.xd_diag1_only && xd;
+  if (pl.rpt == 4) {
+    if (diag1) csx_spmv_xe_kernel<true, 4, KSET_DIAG1, 8, 1><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    else if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    else csx_spmv_xe_kernel<false, 4, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+  } else {
+    if (diag1) csx_spmv_xe_kernel<true, 1, KSET_DIAG1><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    else if (xd) csx_spmv_xe_kernel<true, 1, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    else csx_spmv_xe_kernel<false, 1, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+  }
+}
 // Launches kernel 2 over chunks [c0, c1) of one partition.
 template <class XP>
 static void launch_chunks(const PartDev &P0, bool sym, uint32_t c0, uint32_t c1, const double *x, double *y, double alpha,
@@ -814,8 +890,11 @@ struct csxb_xchg {
   XchgDev dev;
   bool connected = false, fused_push = true;
   int64_t tail_lo = 0, tail_hi = 0;   // rows no rank owns (after the last partition's rows)
+  int parity = 0;                     // protocol 1: index of the vector the next step reads (host side)
+  int64_t issued = 0;                 // steps issued so far
 };
 static size_t xchg_vec_bytes(size_t n) { return ((n * 8 + 255) / 256) * 256; }
+static void xchg_choose_mode(csxb_xchg *h, int64_t own_lo, int64_t own_hi);
 
 csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world) {
   if (!m || !m->uploaded) { fail("matrix not uploaded (csxb_upload)"); return nullptr; }
@@ -835,10 +914,11 @@ csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world) {
   h->dev.vec[0] = (double *)h->base;
   h->dev.vec[1] = (double *)((char *)h->base + vb);
   unsigned long long *ctrl = (unsigned long long *)((char *)h->base + 2 * vb);
-  h->dev.step = ctrl; h->dev.error = ctrl + 1; h->dev.flags = ctrl + 16;
+  h->dev.step = ctrl; h->dev.error = ctrl + 1; h->dev.started = ctrl + 2; h->dev.bdone = ctrl + 3; h->dev.flags = ctrl + 16;
   h->dev.rank = rank;
   for (auto &pl : m->layout.parts) if (!pl.chunks.empty()) h->fused_push = false;
   if (world == 1) {
+    xchg_choose_mode(h, 0, (int64_t)h->n);
     h->connected = true;
     if (m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total) { h->tail_lo = m->covered_rows_end; h->tail_hi = (int64_t)h->n; }
   }
@@ -852,6 +932,30 @@ int csxb_xchg_handle(csxb_xchg_t *h, void *handle64) {
   CUDA_TRY(cudaIpcGetMemHandle(&ih, h->base));
   memcpy(handle64, &ih, 64);
   return 0;
+}
+
+// Edge-tiles-first protocol (XchgDev.mode 1) when the rank has one partition whose rows are final after kernel 1
+// and the tiles that touch other ranks (they read rows outside [own_lo, own_hi), or their rows are pushed) sit
+// at the two ends of the partition.
+static void xchg_choose_mode(csxb_xchg *h, int64_t own_lo, int64_t own_hi) {
+  XchgDev &D = h->dev;
+  D.mode = 0; D.nb = 0; D.edge_lo_end = 0; D.edge_hi_begin = 0;
+  static const int dbg = getenv("CSXB_XCHG_DEBUG") ? atoi(getenv("CSXB_XCHG_DEBUG")) : 0;
+  if (!h->fused_push || h->m->layout.parts.size() != 1 || (dbg & 8)) return;
+  const PartLayout &pl = h->m->layout.parts[0];
+  if (!pl.ntiles || pl.ntiles > (int64_t(1) << 30)) return;
+  const int64_t tr = pl.tile_rows();
+  auto is_edge = [&](int64_t t) {
+    if (pl.tile_cmax[t] >= pl.tile_cmin[t] && (pl.tile_cmin[t] < own_lo || pl.tile_cmax[t] >= own_hi)) return true;
+    const int64_t r0 = pl.row_start + t * tr, r1 = std::min(pl.row_start + pl.nrows, r0 + tr);
+    for (int p = 0; p < D.npush; p++) if (r0 < D.push_hi[p] && r1 > D.push_lo[p]) return true;
+    return false;
+  };
+  int64_t a = 0, b = pl.ntiles;
+  while (a < pl.ntiles && is_edge(a)) a++;
+  while (b > a && is_edge(b - 1)) b--;
+  for (int64_t t = a; t < b; t++) if (is_edge(t)) return;   // an interior tile touches another rank: keep the sync kernel
+  D.mode = 1; D.edge_lo_end = (int)a; D.edge_hi_begin = (int)b; D.nb = (int)(a + (pl.ntiles - b));
 }
 
 // bases[q] = rank q's block as seen from this device (IPC mapping, or the pointer itself inside one process)
@@ -885,6 +989,7 @@ static int xchg_plan(csxb_xchg *h, const std::vector<void *> &bases, const int64
   int64_t cov = 0;
   for (int q = 0; q < h->world; q++) cov = std::max(cov, row_lo[q] + row_n[q]);
   h->tail_lo = cov; h->tail_hi = (int64_t)h->n;
+  xchg_choose_mode(h, row_lo[h->rank], row_lo[h->rank] + row_n[h->rank]);
   h->connected = true;
   return 0;
 }
@@ -925,15 +1030,18 @@ int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
   if (!h->fused_push || (dbg & 4)) X.npush = 0;   // rows are final only after the chunk kernel: pushed by a copy kernel below
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
-    launch_gather<false>(m->pdev[i], pl, 0, pl.ntiles, nullptr, nullptr, alpha, 0.0, 1, s, X);
+    if (X.mode == 1) launch_gather_xe(m->pdev[i], pl, X.vec[h->parity], X.vec[h->parity ^ 1], alpha, h->parity ^ 1, s, X);
+    else launch_gather<false>(m->pdev[i], pl, 0, pl.ntiles, nullptr, nullptr, alpha, 0.0, 1, s, X);
   }
   for (size_t i = 0; i < m->pdev.size(); i++)
     launch_chunks(m->pdev[i], false, 0, (uint32_t)m->layout.parts[i].chunks.size(), nullptr, nullptr, alpha, s, X);
   if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 4, 256, 0, s>>>(h->dev);
   if (h->tail_hi > h->tail_lo)
-    csx_xchg_zero_tail_kernel<<<(unsigned)std::min<int64_t>(148, (h->tail_hi - h->tail_lo + 255) / 256), 256, 0, s>>>(h->dev, h->tail_lo, h->tail_hi);
-  if (!(dbg & 1)) csx_xchg_sync_kernel<<<1, 32, 0, s>>>(h->dev, dbg);
+    csx_xchg_zero_tail_kernel<<<(unsigned)std::min<int64_t>(148, (h->tail_hi - h->tail_lo + 255) / 256), 256, 0, s>>>(h->dev, h->tail_lo, h->tail_hi, h->dev.mode == 1 ? (h->parity ^ 1) : -1);
+  if (!(dbg & 1) && h->dev.mode == 0) csx_xchg_sync_kernel<<<1, 32, 0, s>>>(h->dev, dbg);
   CUDA_TRY(cudaGetLastError());
+  h->parity ^= 1;
+  h->issued++;
   return 0;
 }
 
@@ -941,6 +1049,9 @@ int64_t csxb_xchg_status(csxb_xchg_t *h, int what) {
   unsigned long long v[2] = {0, 0};
   if (cudaSetDevice(h->m->device) != cudaSuccess) return -1;
   if (cudaMemcpy(v, h->dev.step, 16, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (what == 0 && h->dev.mode == 1) { cudaDeviceSynchronize(); return h->issued; }
+  if (what == 2) return h->dev.mode;
+  if (what == 3) return h->dev.nb;
   return what == 0 ? (int64_t)v[0] : (int64_t)v[1];
 }
 

@@ -297,6 +297,10 @@ class PeerExchange(object):
     def error(self):
         return lib().csxb_xchg_status(self._h, 1)
 
+    def protocol(self):
+        """(mode, edge tiles): mode 1 = edge tiles first, 0 = sync kernel per step."""
+        return lib().csxb_xchg_status(self._h, 2), lib().csxb_xchg_status(self._h, 3)
+
     def close(self):
         if self._h:
             lib().csxb_xchg_destroy(self._h)
