@@ -282,7 +282,9 @@ __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, do
   __syncthreads();
   // spmv_tile pushes into push_vec[p][(k & 1) ^ 1]: hand it a step number with the parity of the target buffer
   spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev>(P, x, y, alpha, 0.0, 1, tile, X, (unsigned long long)(ypar ^ 1));
-  __threadfence_system();
+  // Every edge CTA orders its stores before its count at device scope; the last one then issues the single
+  // system-scope fence (cumulative over everything that happened before it) and the release stores of the flags.
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0 && atomicAdd(X.bdone, 1ull) == (unsigned long long)X.nb - 1) {   // last edge CTA of the step
     *reinterpret_cast<volatile unsigned long long *>(X.bdone) = 0;
