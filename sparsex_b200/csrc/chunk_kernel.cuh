@@ -273,7 +273,37 @@ __device__ __forceinline__ void process_chunk(const PartDev &P, const uint32_t c
     uint32_t e = 0;
     double acc = 0.0;
     const uint32_t bp0 = mis + body;
-    for (uint32_t t0 = 0; t0 < tmax; t0 += CHUNK_BATCH) {
+    // Rounds that hold only row-local slices (delta / horizontal units: all of an R-MAT stream, most of a mixed one)
+    // take a loop without the line bookkeeping of block and cross-row slices.
+    const bool all_rowlocal = __all_sync(FULL, rowlocal || total == 0);
+    for (uint32_t t0 = 0; all_rowlocal && t0 < tmax; t0 += CHUNK_BATCH) {
+      if (t0 >= total) continue;   // this lane's slice is done (no warp collective inside the loop)
+      uint32_t D[CHUNK_BATCH];
+      if (kind == K_HORIZ) {
+#pragma unroll
+        for (int i = 0; i < CHUNK_BATCH; i++) D[i] = cdelta;
+      } else {   // element j of a delta unit adds body[j - 1]; the unit's first element adds ucol instead
+        const uint32_t first = (j + t0 == 0) ? 1u : 0u;
+        uint32_t R[CHUNK_BATCH];
+        read_deltas4(cw, bp0 + (j + t0 + first - 1) * dw, dw, R);
+        D[0] = first ? 0u : R[0];
+#pragma unroll
+        for (int i = 1; i < CHUNK_BATCH; i++) D[i] = first ? R[i - 1] : R[i];
+      }
+      if (j + t0 == 0) D[0] = inc0;
+      const uint32_t left = total - t0;
+      uint32_t cl[CHUNK_BATCH];
+#pragma unroll
+      for (int i = 0; i < CHUNK_BATCH; i++) {
+        col += D[i];
+        cl[i] = col;
+        f.elem(i, (uint32_t)i < left, vi + i, row, col);
+      }
+      vi += CHUNK_BATCH;
+#pragma unroll
+      for (int i = 0; i < CHUNK_BATCH; i++) acc += f.use(i, (uint32_t)i < left, row, cl[i]);
+    }
+    for (uint32_t t0 = 0; !all_rowlocal && t0 < tmax; t0 += CHUNK_BATCH) {
       uint32_t D[CHUNK_BATCH];
 #pragma unroll
       for (int i = 0; i < CHUNK_BATCH; i++) D[i] = 1;
