@@ -100,6 +100,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def pin_to_gpu_numa_node(index):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the cores NVML reports as local to the
+    GPU, so that host<->device copies of different ranks do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and w * 64 + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "cpus %d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))
+    except Exception as ex:  # affinity is an optimisation only
+        return "not set: %r" % (ex,)
+    return "not set"
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -161,7 +180,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: exchange fused into the SpMV kernel over peer memory (default) or NCCL after it")
@@ -195,6 +214,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    numa_note = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api = sparsex_b200.load_spx_api()
@@ -240,14 +260,18 @@ def main():
     xbuf = [x, y]   # ping-pong: the SpMV writes the own rows of the other buffer, the exchange fills the halo
     peer = None
     sym = str(opts.get("spx.matrix.symmetric", "false")) == "true"
+    peer_note = None
     if world > 1 and args.exchange == "peer" and not sym:
         # the engine's own exchange: halo rows are stored into the neighbours' vectors by the SpMV kernel itself
-        from sparsex_b200.dist import connect_peer_exchange
-        peer, ranges, windows = connect_peer_exchange(eng, rank, world, "cuda")
+        import sparsex_b200.dist as sdist
+        peer, ranges, windows = sdist.connect_peer_exchange(eng, rank, world, "cuda")
+        if peer is None:
+            peer_note = "peer-memory exchange unavailable (%s): NCCL exchange used instead" % sdist.last_peer_error
+    if peer is not None:
         peer.vector(0).copy_(x)
         exchange_kind = ("fused into the SpMV kernel: rows other ranks read are stored into their vectors over NVLink (peer memory), "
                          "device-side flags order the steps; protocol %d (1: edge tiles first, no sync kernel), %d edge tiles" % peer.protocol())
-    elif world > 1:
+    if world > 1 and peer is None:
         symred = None
         from sparsex_b200.dist import PieceExchange, WindowExchange, gather_row_ranges
         L = sparsex_b200.lib()
@@ -393,6 +417,7 @@ def main():
         dist.all_reduce(hb)
     e2e = {"value": 2.0 * nnz * args.e2e_steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(hb[0]),
            "d2h_bytes_per_step": int(hb[1]), "steps": args.e2e_steps,
+           "host_affinity": numa_note,
            "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory); every rank uploads the "
                   "columns its partition reads and downloads its rows, slab-pipelined (H2D, kernels, D2H overlap)"}
     # check the device-resident result against the host-buffer path on the same x
@@ -420,7 +445,7 @@ def main():
                                "; then " + exchange_kind + " into the next x" if world > 1 else ""),
                            "l2_policy": "inputs larger than L2: %.0f MB of values+ctl per GPU vs 126 MB L2" % (
                                (traffic["values"] + traffic["ctl"]) / 1e6),
-                           "tune_s": round(tune_s, 2), "generate_s": round(gen_s, 2),
+                           "exchange_note": peer_note, "tune_s": round(tune_s, 2), "generate_s": round(gen_s, 2),
                            "self_check_rel": self_check},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu_traffic(name), "peak_source": peak_src,

@@ -126,12 +126,20 @@ def connect_peer_exchange(matrix, rank, world, device):
     """One process per GPU: creates the engine's peer-memory exchange for `matrix` (csxb_xchg_*, include/csx_b200.h),
     all-gathers the CUDA IPC handles, row ranges and column windows over torch.distributed (plumbing only) and
     connects.  Afterwards a step is `ex.spmv(alpha)`: kernel launches only, the halo rows travel inside the SpMV
-    kernel over NVLink."""
+    kernel over NVLink.  Returns (exchange, ranges, windows); exchange is None on every rank when any rank could
+    not set it up (no peer access between the GPUs, IPC not permitted ...), with the reason in `last_peer_error`."""
+    global last_peer_error
     import numpy as np
     from .engine import PeerExchange, lib
     L = lib()
-    ex = PeerExchange(matrix, rank, world)
-    mine = torch.from_numpy(ex.handle()).to(device)
+    ex, err = None, ""
+    handle = np.zeros(64, np.uint8)
+    try:
+        ex = PeerExchange(matrix, rank, world)
+        handle = ex.handle()
+    except Exception as e:  # noqa: BLE001 - reported through last_peer_error, every rank must reach the collectives
+        ex, err = None, repr(e)
+    mine = torch.from_numpy(handle).to(device)
     allh = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(allh, mine)
     info = torch.tensor([L.csxb_part_info(matrix._h, 0, 3), L.csxb_part_info(matrix._h, 0, 1),
@@ -140,6 +148,22 @@ def connect_peer_exchange(matrix, rank, world, device):
     dist.all_gather(alli, info)
     ranges = [(int(t[0]), int(t[1])) for t in alli]
     windows = [(int(t[2]), int(t[3])) for t in alli]
-    ex.connect(np.stack([t.cpu().numpy() for t in allh]), ranges, windows)
+    ok = torch.tensor([1 if ex is not None else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok[0]):
+        try:
+            ex.connect(np.stack([t.cpu().numpy() for t in allh]), ranges, windows)
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)
+            ok[0] = 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not int(ok[0]):
+        if ex is not None:
+            ex.close()
+        last_peer_error = err or "another rank could not set up the peer exchange"
+        return None, ranges, windows
     dist.barrier()
     return ex, ranges, windows
+
+
+last_peer_error = ""
