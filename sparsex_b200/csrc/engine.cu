@@ -154,12 +154,15 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 // VAR = 1 (4-rows-per-thread diagonal instantiation) issues the eight loads of a unit as one inline-PTX block so
 // that all of them are in flight before the first FMA; ptxas otherwise interleaves loads and FMAs at 32 registers.
 enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
-// The work of one warp of one tile.  PUSH: rows that other ranks read are also stored into their vectors (exchange).
+// The work of one warp of one CTA: rows [row_block * CTA_THREADS * RPT, +CTA_THREADS * RPT) with the descriptor list of
+// layout tile `tile` (the same number, unless an edge CTA of the exchange walks a quarter of a 4-rows-per-thread tile
+// with one row per thread).  PUSH: rows that other ranks read are also stored into their vectors (exchange).
 template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool PUSH, class XP>
 __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__restrict__ x, double *__restrict__ y, double alpha,
-                                          double beta, int overwrite, const long long tile, const XP &X, const unsigned long long xk) {
+                                          double beta, int overwrite, const long long tile, const long long row_block, const XP &X,
+                                          const unsigned long long xk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long lrow0 = ((tile * (CTA_THREADS / 32) + warp) * RPT) * 32;   // first row of this warp (partition relative)
+  const long long lrow0 = ((row_block * (CTA_THREADS / 32) + warp) * RPT) * 32;   // first row of this warp (partition relative)
   if (lrow0 >= P.nrows) return;
   double acc[RPT];
 #pragma unroll
@@ -267,7 +270,7 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
 // the interior path of the kernel keeps the register allocation of the plain kernel.
 template <bool XD, bool SYM, int RPT, int KSET, int VAR>
 __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, double *y, double alpha, long long tile,
-                                           const XchgDev &X, int ypar) {
+                                           long long row_block, const XchgDev &X, int ypar) {
   // only the edge CTAs use the device-resident step number (the flags count steps across graph replays)
   const unsigned long long xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
   if (threadIdx.x == 0 && xk > 0) {   // halo of this step arrived; the neighbours no longer read the buffer pushed into
@@ -281,7 +284,7 @@ __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, do
   }
   __syncthreads();
   // spmv_tile pushes into push_vec[p][(k & 1) ^ 1]: hand it a step number with the parity of the target buffer
-  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev>(P, x, y, alpha, 0.0, 1, tile, X, (unsigned long long)(ypar ^ 1));
+  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev>(P, x, y, alpha, 0.0, 1, tile, row_block, X, (unsigned long long)(ypar ^ 1));
   // Every edge CTA orders its stores before its count at device scope; the last one then issues the single
   // system-scope fence (cumulative over everything that happened before it) and the release stores of the flags.
   __threadfence();
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __gri
     xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
     x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
   }
-  spmv_tile<XD, SYM, RPT, KSET, VAR, XCHG, XP>(P, x, y, alpha, beta, overwrite, tile, X, xk);
+  spmv_tile<XD, SYM, RPT, KSET, VAR, XCHG, XP>(P, x, y, alpha, beta, overwrite, tile, tile, X, xk);
 }
 
 // Kernel 1 under the edge-tiles-first protocol (XchgDev.mode 1): CTAs [0, nb) take the tiles at both ends of the
@@ -318,8 +321,17 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_xe_kernel(const __
                                                                      const double *__restrict__ x, double *__restrict__ y,
                                                                      double alpha, int ypar, const __grid_constant__ XchgDev X) {
   const int b = (int)blockIdx.x;
-  if (b < X.nb) spmv_edge_cta<XD, false, RPT, KSET, VAR>(P, x, y, alpha, b < X.edge_lo_end ? b : X.edge_hi_begin + (b - X.edge_lo_end), X, ypar);
-  else spmv_tile<XD, false, RPT, KSET, VAR, false, NoXchg>(P, x, y, alpha, 0.0, 1, (long long)X.edge_lo_end + (b - X.nb), NoXchg(), 0ull);
+  if (b < X.nb) {
+    // Edge CTAs walk their tile with one row per thread (a 4-rows-per-thread tile is split over four CTAs): the sooner
+    // the edge rows are out, the more slack the neighbours have before their next step needs them.
+    constexpr int SPLIT = RPT == 4 ? 4 : 1;
+    const int bt = b / SPLIT, sub = b % SPLIT;
+    const long long tile = bt < X.edge_lo_end ? bt : X.edge_hi_begin + (bt - X.edge_lo_end);
+    spmv_edge_cta<XD, false, 1, KSET, 0>(P, x, y, alpha, tile, tile * SPLIT + sub, X, ypar);
+  } else {
+    const long long tile = (long long)X.edge_lo_end + (b - X.nb);
+    spmv_tile<XD, false, RPT, KSET, VAR, false, NoXchg>(P, x, y, alpha, 0.0, 1, tile, tile, NoXchg(), 0ull);
+  }
 }
 
 // Exchange for partitions whose rows are only final after the chunk kernel: copies the rows the peers read.
@@ -767,7 +779,7 @@ static void launch_gather_xe(const PartDev &P0, const PartLayout &pl, const doub
   if (!pl.ntiles) return;
   PartDev P = P0;
   P.tile0 = 0;
-  dim3 grid((unsigned)pl.ntiles), block(CTA_THREADS);
+  dim3 grid((unsigned)(X.nb + (X.edge_hi_begin - X.edge_lo_end))), block(CTA_THREADS);   // edge CTAs first, then the interior tiles
   const bool xd = !pl.xdesc.empty(), diag1 = pl.xd_diag1_only && xd;
   if (pl.rpt == 4) {
     if (diag1) csx_spmv_xe_kernel<true, 4, KSET_DIAG1, 8, 1><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
@@ -957,7 +969,8 @@ static void xchg_choose_mode(csxb_xchg *h, int64_t own_lo, int64_t own_hi) {
   while (a < pl.ntiles && is_edge(a)) a++;
   while (b > a && is_edge(b - 1)) b--;
   for (int64_t t = a; t < b; t++) if (is_edge(t)) return;   // an interior tile touches another rank: keep the sync kernel
-  D.mode = 1; D.edge_lo_end = (int)a; D.edge_hi_begin = (int)b; D.nb = (int)(a + (pl.ntiles - b));
+  const int split = pl.rpt == 4 ? 4 : 1;   // edge CTAs per edge tile (csx_spmv_xe_kernel)
+  D.mode = 1; D.edge_lo_end = (int)a; D.edge_hi_begin = (int)b; D.nb = (int)(a + (pl.ntiles - b)) * split;
 }
 
 // bases[q] = rank q's block as seen from this device (IPC mapping, or the pointer itself inside one process)

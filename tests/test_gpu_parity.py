@@ -304,7 +304,10 @@ def test_peer_exchange_logical_ranks(world):
     from sparsex_b200 import CsxMatrix, PeerExchange, lib
     rng = np.random.default_rng(world)
     cases = [poisson2d(70)[:3] + (4900, {}), stencil27(12)[:3] + (1728, {"spx.preproc.xform": "br,bc", "spx.preproc.sampling": "none"}),
-             rmat(11)[:3] + (2048, {"spx.preproc.xform": "none"})]
+             rmat(11)[:3] + (2048, {"spx.preproc.xform": "none"}),
+             # 4 rows per thread: edge tiles are split over four one-row-per-thread CTAs (csx_spmv_xe_kernel)
+             poisson2d(150)[:3] + (22500, {"spx.b200.rows_per_thread": 4}),
+             stencil27(22)[:3] + (10648, {"spx.b200.rows_per_thread": 4})]
     for rp, ci, va, n, opts in cases:
         o = dict(opts, **{"spx.rt.nr_threads": world})
         mats = [CsxMatrix.tune_csr(rp, ci, va, n, n, o, part_lo=r, part_hi=r + 1).upload(0) for r in range(world)]
