@@ -6,7 +6,7 @@
 // built once at tune time by decoding ctl on the host:
 //
 //   * chunk table — the ctl stream is cut at unit boundaries into chunks of
-//     at most 512 non-zeros / 128 units / 2 KB of ctl ("warp-segmented ctl
+//     at most 256 non-zeros / 64 units / 128 slices / 2 KB of ctl ("warp-segmented ctl
 //     chunks").  An entry holds the byte offset of the chunk's first unit, the
 //     index of its first value, the row it belongs to and the column cursor at
 //     that point (the decoder state a warp needs to start there), plus its
