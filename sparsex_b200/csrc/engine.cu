@@ -5,11 +5,13 @@
 //                        contributions of the long cross-row units (vertical, diagonal, anti-diagonal)
 //                        listed for its tile, then writes y = alpha*acc + beta*y once per row.
 //                        No atomics, deterministic, streams values with coalesced loads.
-//   2. csx_chunk_kernel  one warp per chunk of the ctl stream: unit heads and varints are parsed from a
-//                        shared-memory copy of the chunk, delta bodies are turned into columns with a
-//                        segmented warp prefix sum, block / short substructure elements get their
-//                        coordinates from the unit geometry; rows are reduced with segmented shuffle
-//                        reductions and added to y with fp64 red operations.
+//   2. csx_chunk_kernel  (chunk_kernel.cuh) one warp per chunk of the ctl stream: ctl bytes and values are staged in
+//                        shared memory, one unit head per lane is parsed, units are cut into slices and every
+//                        lane walks one slice per round (columns from the deltas or from the unit geometry);
+//                        row sums are combined with segmented shuffle reductions and added to y with fp64 red
+//                        operations.
+// Host-buffer calls are slab-pipelined (csxb_spmv_host); repeated SpMV across GPUs exchanges the halo rows from
+// inside kernel 1 over CUDA-IPC peer memory (csxb_xchg_*, csx_spmv_xe_kernel).
 // SpMV is HBM-bound fp64 work: no tensor cores; every value and ctl byte is read once.
 //
 // Reference semantics reproduced: src/templates/csx_spmv_tmpl.c:66-101 and the
