@@ -14,6 +14,8 @@
 //   ctl emission         CsxManager.hpp:237-706, CtlBuilder.cpp:32-81, Delta.hpp:35-48
 //   CSX-Sym              SparsePartition.hpp:965-1074, CsxBuild.hpp:204-288, 400-581
 // Non-NUMA semantics (SPX_USE_NUMA == 0) throughout.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <chrono>
 #include <climits>
@@ -58,6 +60,38 @@ struct Rec {
   uint64_t vptr;
 };
 static_assert(sizeof(Rec) == 24, "Rec layout");
+
+// resize() without the serial zero fill: the big arrays are written in full by parallel loops right afterwards
+// (which also spreads the first touch of their pages over the threads)
+template <class T>
+struct default_init_alloc : std::allocator<T> {
+  template <class U> struct rebind { using other = default_init_alloc<U>; };
+  default_init_alloc() = default;
+  template <class U> default_init_alloc(const default_init_alloc<U> &) {}
+  template <class U, class... A>
+  void construct(U *ptr, A &&...a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void *)ptr) U;
+    else ::new ((void *)ptr) U(std::forward<A>(a)...);
+  }
+  // big arrays: 2 MB alignment and a transparent-huge-page hint (the first touch of gigabytes in 4 KB pages
+  // costs more than filling them)
+  T *allocate(size_t n) {
+    const size_t bytes = n * sizeof(T);
+    if (bytes >= (size_t(64) << 20)) {
+      void *ptr = nullptr;
+      if (posix_memalign(&ptr, size_t(2) << 20, bytes) == 0 && ptr) {
+        madvise(ptr, bytes, MADV_HUGEPAGE);
+        return (T *)ptr;
+      }
+    }
+    void *ptr = malloc(bytes ? bytes : 1);
+    if (!ptr) throw std::bad_alloc();
+    return (T *)ptr;
+  }
+  void deallocate(T *ptr, size_t) { free(ptr); }
+};
+using RecVec = std::vector<Rec, default_init_alloc<Rec>>;
+using ValVec = std::vector<double, default_init_alloc<double>>;
 
 inline bool is_pattern(const Rec &e) { return e.delta != 0; }  // Element.hpp:372-377
 
@@ -111,10 +145,12 @@ void parallel_slices(size_t n, Fn fn) {
 // Stable LSD radix sort of (key, index) pairs; only the populated bit ranges
 // of the packed (row << 32 | col) key are visited.  Each pass: per-thread
 // histograms, one exclusive scan over (digit, thread), per-thread stable scatter.
-void radix_sort_pairs(std::vector<uint64_t> &key, std::vector<uint32_t> &idx, int bits_lo, int bits_hi) {
+using KeyVec = std::vector<uint64_t, default_init_alloc<uint64_t>>;
+using IdxVec = std::vector<uint32_t, default_init_alloc<uint32_t>>;
+void radix_sort_pairs(KeyVec &key, IdxVec &idx, int bits_lo, int bits_hi) {
   size_t n = key.size();
-  std::vector<uint64_t> key2(n);
-  std::vector<uint32_t> idx2(n);
+  KeyVec key2(n);
+  IdxVec idx2(n);
   const int RB = 11;
   const size_t NB = size_t(1) << RB;
   int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
@@ -148,9 +184,9 @@ struct Part {
   int64_t nr_rows = 0, nr_cols = 0, nr_nzeros = 0;
   int type = T_NONE;
   int64_t row_start = 0;
-  std::vector<Rec> e;
+  RecVec e;
   std::vector<int64_t> rowptr;   // rowptr[j] = #records with row <= j ; size = last row + 1
-  std::vector<double> *pool = nullptr;
+  ValVec *pool = nullptr;
 
   // The reference rebuilds a full rowptr after every reordering (SparsePartition.hpp:543-563, 852-891) — up to
   // nr_rows + nr_cols entries in the diagonal orders.  Only its length is ever used outside the Horizontal
@@ -165,6 +201,23 @@ struct Part {
     nrowptr_ = (size_t)last + 1;
     if (type != T_HORIZ) return;
     rowptr.assign((size_t)last + 1, 0);
+    const size_t n = e.size();
+    if (n >= (size_t(1) << 20)) {
+      // rows are non-decreasing in horizontal order: rowptr[j] = index behind the last element of a row <= j,
+      // written where the row number changes (disjoint ranges, one per change; threads share nothing)
+      std::vector<char> bad(64, 0);
+      parallel_slices(n, [&](int t, size_t b, size_t en) {
+        for (size_t i = b; i < en; i++) {
+          const int32_t r0 = e[i].r, r1 = i + 1 < n ? e[i + 1].r : last + 1;
+          if (r1 < r0) { bad[t] = 1; return; }
+          for (int32_t j = r0; j < r1 && j <= last; j++) rowptr[j] = (int64_t)(i + 1);
+        }
+      });
+      bool ok = true;
+      for (char c : bad) if (c) ok = false;
+      if (ok) return;
+      std::fill(rowptr.begin(), rowptr.end(), 0);
+    }
     for (const Rec &x : e) rowptr[x.r]++;
     int64_t s = 0;
     for (size_t j = 1; j < rowptr.size(); j++) { s += rowptr[j]; rowptr[j] = s; }
@@ -177,8 +230,8 @@ struct Part {
     const int t2type = t;
     size_t n = e.size();
     if (n) {
-      std::vector<uint64_t> key(n);
-      std::vector<uint32_t> idx(n);
+      KeyVec key(n);
+      IdxVec idx(n);
       const int from = type;
       const int32_t R = (int32_t)nr_rows, C = (int32_t)nr_cols;
       std::vector<uint32_t> mr(64, 0), mc(64, 0);
@@ -212,7 +265,7 @@ struct Part {
         } else {
           radix_sort_pairs(key, idx, bit_width32(maxc), bit_width32(maxr));
         }
-        std::vector<Rec> out(n);
+        RecVec out(n);
         parallel_slices(n, [&](int, size_t b, size_t en) { for (size_t i = b; i < en; i++) out[i] = e[idx[i]]; });
         e.swap(out);
       }
@@ -642,14 +695,14 @@ class Miner {
   // are copied behind each other at the end of the pool.
   Rec pattern(int32_t row, int32_t col, const Rec *buf, size_t m0, size_t cnt, int type, size_t delta) {
     if (cnt == 1) return single(row, col, buf[m0].vptr);  // Element.hpp:234-236
-    std::vector<double> &pool = *spm_->pool;
+    ValVec &pool = *spm_->pool;
     uint64_t at = pool.size();
     for (size_t k = 0; k < cnt; k++) pool.push_back(pool[buf[m0 + k].vptr]);
     return Rec{row, col, (uint32_t)delta, (uint8_t)type, (uint8_t)cnt, 0, at};
   }
 
   // DoEncode, :1003-1082 — buf[0..n) are the consecutive singles of one row.
-  void encode_linear(int32_t row, const Rec *buf, size_t n, std::vector<Rec> &out) {
+  void encode_linear(int32_t row, const Rec *buf, size_t n, RecVec &out) {
     int type = spm_->type;
     scan_runs(buf, 0, n, runs_);
     size_t vi = 0;
@@ -675,7 +728,7 @@ class Miner {
   }
 
   // DoEncodeBlock (:1085-1192, split_blocks=false) and DoEncodeBlockAlt (:1194-1290)
-  void encode_block(int32_t row, const Rec *buf, size_t n, std::vector<Rec> &out) {
+  void encode_block(int32_t row, const Rec *buf, size_t n, RecVec &out) {
     int type = spm_->type;
     size_t a = blk_align(type);
     scan_runs(buf, 0, n, runs_);
@@ -736,7 +789,7 @@ class Miner {
     if (t == T_NONE) return;
     spm_->transform(t);
     Trace tr("encode rows");
-    std::vector<Rec> out;
+    RecVec out;
     out.reserve(spm_->e.size());
     const Rec *recs = spm_->e.data();
     const size_t n = spm_->e.size();
@@ -868,7 +921,7 @@ class CtlWriter {
     cols_.clear();
   }
   void emit(size_t &k, size_t e, bool left_only) {  // DoRow / DoSymRow, :504-613
-    const std::vector<double> &pool = *spm_->pool;
+    const ValVec &pool = *spm_->pool;
     for (; k < e; k++) {
       const Rec &x = spm_->e[k];
       if (left_only && !(x.c < spm_->row_start + 1)) break;
@@ -930,9 +983,53 @@ struct Cursor {
 // `keep == false` only advances the cursor (partition not owned by this process).
 struct SplitResult { int64_t taken = 0; int64_t rows = 0; int64_t diag = 0; int32_t cmin = INT32_MAX, cmax = 0; };
 SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sym, bool keep, Part &p,
-                           std::vector<double> &pool, std::vector<double> &diag) {
+                           ValVec &pool, std::vector<double> &diag) {
   Trace tr("take_partition");
   SplitResult res;
+  if (cur.csr && !sym && keep && !cur.end()) {
+    // CSR input, plain CSX: the loop below ends the partition at the first row start at or after `limit` elements
+    // (:525-533), which is a lookup in rowptr; the records are then filled in parallel.
+    const CsrView &A = *cur.csr;
+    const int64_t pos0 = cur.pos, n = cur.n;
+    int64_t pos_end = n;
+    if (limit && pos0 + (int64_t)limit < n)
+      pos_end = *std::lower_bound(A.rowptr, A.rowptr + A.nrows + 1, (int)(pos0 + (int64_t)limit));
+    const size_t cnt = (size_t)(pos_end - pos0);
+    const size_t pbase = pool.size();
+    p.e.resize(cnt);
+    pool.resize(pbase + cnt);
+    int T = (cnt < (size_t(1) << 20)) ? 1 : g_sort_threads;
+    std::vector<int32_t> tmin((size_t)T, INT32_MAX), tmax((size_t)T, 0);
+    parallel_slices(cnt, [&](int t, size_t b, size_t en) {
+      if (b >= en) return;
+      // row of element pos0 + b: last row whose rowptr is <= that position and that is not empty there
+      int64_t row = std::upper_bound(A.rowptr, A.rowptr + A.nrows + 1, (int)(pos0 + (int64_t)b)) - A.rowptr - 1;
+      int32_t lo = INT32_MAX, hi = 0;
+      for (size_t k = b; k < en; k++) {
+        const int64_t pos = pos0 + (int64_t)k;
+        while (A.rowptr[row + 1] <= pos) row++;
+        const int32_t col = A.colind[pos] + 1;
+        p.e[k] = Rec{(int32_t)(row + 1 - row_start), col, 0, 0, 1, 0, (uint64_t)(pbase + k)};
+        pool[pbase + k] = A.values[pos];
+        lo = std::min(lo, col); hi = std::max(hi, col);
+      }
+      tmin[t] = lo; tmax[t] = hi;
+    });
+    for (int t = 0; t < T; t++) { res.cmin = std::min(res.cmin, tmin[t]); res.cmax = std::max(res.cmax, tmax[t]); }
+    const int32_t last_row = cnt ? p.e[cnt - 1].r : 0;
+    cur.pos = pos_end;
+    while (cur.row < A.nrows && A.rowptr[cur.row + 1] <= cur.pos) cur.row++;
+    res.taken = (int64_t)cnt;
+    res.rows = (int64_t)last_row;
+    res.diag = 0;
+    p.nr_nzeros = (int64_t)cnt;
+    p.nr_rows = last_row;
+    p.row_start = row_start;
+    p.type = T_HORIZ;
+    p.pool = &pool;
+    p.build_rowptr();
+    return res;
+  }
   int32_t row_prev = 1, last_row = 0;
   size_t cnt = 0, dcnt = 0;
   if (keep) {
@@ -977,9 +1074,13 @@ SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sy
 
 void check_sorted_cols(const Part &p) {
   Trace tr("check_sorted_cols");
-  for (size_t i = 1; i < p.e.size(); i++)
-    if (p.e[i].r == p.e[i - 1].r && p.e[i].c <= p.e[i - 1].c)
-      throw TuneError("column indices must be strictly increasing within each row");
+  std::vector<char> bad(64, 0);
+  parallel_slices(p.e.size(), [&](int t, size_t b, size_t en) {
+    for (size_t i = std::max<size_t>(b, 1); i < en; i++)
+      if (p.e[i].r == p.e[i - 1].r && p.e[i].c <= p.e[i - 1].c) { bad[t] = 1; return; }
+  });
+  for (char c : bad)
+    if (c) throw TuneError("column indices must be strictly increasing within each row");
 }
 
 void mine(Part &p, const TuneOptions &opt, const XformSeq &q, bool run_all, std::string *log, bool *undef) {
@@ -1006,7 +1107,7 @@ void split_lower(const Part &lower, Part &m1, Part &m2) {
   }
 }
 void merge_lower(Part &lower, const Part &m1, const Part &m2) {
-  std::vector<Rec> out;
+  RecVec out;
   out.reserve(m1.e.size() + m2.e.size());
   size_t nr = (size_t)lower.nr_rows;
   std::vector<int64_t> rp(nr + 1, 0);
@@ -1073,7 +1174,8 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
     uint64_t total = sym ? (uint64_t)(cur.n + ncols) / 2 : (uint64_t)cur.n, done = 0;
     int64_t row_start = 0;
     std::vector<Part> parts(np);
-    std::vector<std::vector<double>> pools(np), diags(np);
+    std::vector<ValVec> pools(np);
+    std::vector<std::vector<double>> diags(np);
     for (int i = 0; i < np; i++) {
       size_t limit = (size_t)((total - done) / (uint64_t)(np - i));
       // the sym reduction map needs every partition's lower triangle
@@ -1112,8 +1214,8 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
         CtlWriter(&p, opt.full_colind, opt.build_rows_info).run(true, o);
         o.dvalues = diags[i];
       }
-      std::vector<Rec>().swap(p.e);
-      std::vector<double>().swap(pools[i]);
+      RecVec().swap(p.e);
+      ValVec().swap(pools[i]);
     };
     // one preprocessing thread per partition like CsxBuild.hpp:290-326, capped by host_threads
     int hw = opt.host_threads > 0 ? opt.host_threads : (int)std::thread::hardware_concurrency();
