@@ -129,9 +129,15 @@ inline RC retarget(int from, int to, RC p, int32_t R, int32_t C) {
 // ------------------------------------------------------------- radix sort --
 // Slices [0, n) over worker threads (the sorts dominate spx_mat_tune on large partitions).
 int g_sort_threads = 1;
+// Arrays shorter than this are processed by one thread.  SPXB_PAR_MIN lowers it so that the test suite can run the
+// threaded paths on small inputs (tests/test_cpu_refpin.py).
+inline size_t par_min() {
+  static const size_t v = getenv("SPXB_PAR_MIN") ? (size_t)atoll(getenv("SPXB_PAR_MIN")) : (size_t(1) << 20);
+  return v;
+}
 template <class Fn>
 void parallel_slices(size_t n, Fn fn) {
-  int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
+  int T = (n < par_min()) ? 1 : g_sort_threads;
   if (T <= 1) { fn(0, size_t(0), n); return; }
   std::vector<std::thread> th;
   size_t per = (n + T - 1) / T;
@@ -153,7 +159,7 @@ void radix_sort_pairs(KeyVec &key, IdxVec &idx, int bits_lo, int bits_hi) {
   IdxVec idx2(n);
   const int RB = 11;
   const size_t NB = size_t(1) << RB;
-  int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
+  int T = (n < par_min()) ? 1 : g_sort_threads;
   std::vector<size_t> hist((size_t)T * NB);
   auto pass = [&](int shift, int nbits) {
     uint64_t mask = (uint64_t(1) << nbits) - 1;
@@ -202,7 +208,7 @@ struct Part {
     if (type != T_HORIZ) return;
     rowptr.assign((size_t)last + 1, 0);
     const size_t n = e.size();
-    if (n >= (size_t(1) << 20)) {
+    if (n >= par_min()) {
       // rows are non-decreasing in horizontal order: rowptr[j] = index behind the last element of a row <= j,
       // written where the row number changes (disjoint ranges, one per change; threads share nothing)
       std::vector<char> bad(64, 0);
@@ -255,12 +261,12 @@ struct Part {
       bool sorted = true;
       for (char u : unsorted) if (u) sorted = false;
       if (sorted) {  // slices are sorted inside; check the seams
-        int T = (n < (size_t(1) << 20)) ? 1 : g_sort_threads;
+        int T = (n < par_min()) ? 1 : g_sort_threads;
         size_t per = (n + T - 1) / T;
         for (int t = 1; t < T && sorted; t++) { size_t b = std::min(n, per * t); if (b > 0 && b < n && key[b - 1] > key[b]) sorted = false; }
       }
       if (!sorted) {
-        if (n < 32768) {
+        if (n < std::min<size_t>(32768, par_min())) {
           std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
         } else {
           radix_sort_pairs(key, idx, bit_width32(maxc), bit_width32(maxr));
@@ -998,7 +1004,7 @@ SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sy
     const size_t pbase = pool.size();
     p.e.resize(cnt);
     pool.resize(pbase + cnt);
-    int T = (cnt < (size_t(1) << 20)) ? 1 : g_sort_threads;
+    int T = (cnt < par_min()) ? 1 : g_sort_threads;
     std::vector<int32_t> tmin((size_t)T, INT32_MAX), tmax((size_t)T, 0);
     parallel_slices(cnt, [&](int t, size_t b, size_t en) {
       if (b >= en) return;
