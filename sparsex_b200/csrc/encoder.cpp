@@ -699,21 +699,29 @@ class Miner {
   Rec single(int32_t row, int32_t col, uint64_t vptr) { return Rec{row, col, 0, 0, 1, 0, vptr}; }
   // Build a substructure record from buffer members [m0, m0+cnt): their values
   // are copied behind each other at the end of the pool.
-  Rec pattern(int32_t row, int32_t col, const Rec *buf, size_t m0, size_t cnt, int type, size_t delta) {
+  // `lp` (threaded encoding): the values go to the thread's own pool and the record is tagged; encode() moves them
+  // behind the shared pool afterwards and rewrites the tagged pointers.
+  static constexpr uint64_t LOCAL_VPTR = uint64_t(1) << 63;
+  Rec pattern(int32_t row, int32_t col, const Rec *buf, size_t m0, size_t cnt, int type, size_t delta, ValVec *lp) {
     if (cnt == 1) return single(row, col, buf[m0].vptr);  // Element.hpp:234-236
     ValVec &pool = *spm_->pool;
+    if (lp) {
+      uint64_t at = lp->size();
+      for (size_t k = 0; k < cnt; k++) lp->push_back(pool[buf[m0 + k].vptr]);
+      return Rec{row, col, (uint32_t)delta, (uint8_t)type, (uint8_t)cnt, 0, at | LOCAL_VPTR};
+    }
     uint64_t at = pool.size();
     for (size_t k = 0; k < cnt; k++) pool.push_back(pool[buf[m0 + k].vptr]);
     return Rec{row, col, (uint32_t)delta, (uint8_t)type, (uint8_t)cnt, 0, at};
   }
 
   // DoEncode, :1003-1082 — buf[0..n) are the consecutive singles of one row.
-  void encode_linear(int32_t row, const Rec *buf, size_t n, RecVec &out) {
+  void encode_linear(int32_t row, const Rec *buf, size_t n, RecVec &out, std::vector<Run> &runs, ValVec *lp) {
     int type = spm_->type;
-    scan_runs(buf, 0, n, runs_);
+    scan_runs(buf, 0, n, runs);
     size_t vi = 0;
     int64_t col = 0;
-    for (const Run &r : runs_) {
+    for (const Run &r : runs) {
       size_t left = r.freq;
       if (left != 1 && chosen_.count(Inst(type, (size_t)r.val))) {
         col += r.val;
@@ -723,7 +731,7 @@ class Miner {
         }
         while (left >= min_) {
           size_t take = std::min(max_, left);
-          out.push_back(pattern(row, (int32_t)start, buf, vi, take, type, (size_t)r.val));
+          out.push_back(pattern(row, (int32_t)start, buf, vi, take, type, (size_t)r.val, lp));
           vi += take; start += (int64_t)r.val * (int64_t)take; left -= take;
         }
         col = start - r.val;
@@ -734,13 +742,13 @@ class Miner {
   }
 
   // DoEncodeBlock (:1085-1192, split_blocks=false) and DoEncodeBlockAlt (:1194-1290)
-  void encode_block(int32_t row, const Rec *buf, size_t n, RecVec &out) {
+  void encode_block(int32_t row, const Rec *buf, size_t n, RecVec &out, std::vector<Run> &runs, ValVec *lp) {
     int type = spm_->type;
     size_t a = blk_align(type);
-    scan_runs(buf, 0, n, runs_);
+    scan_runs(buf, 0, n, runs);
     size_t vi = 0;
     int64_t col = 0;
-    for (const Run &r : runs_) {
+    for (const Run &r : runs) {
       size_t skip_front, skip_back, cnt;
       col += r.val;
       if (col == 1) { skip_front = 0; cnt = r.freq; }
@@ -767,7 +775,7 @@ class Miner {
             if (it->first != type) continue;
             while (other >= it->second) {
               size_t take = a * it->second;
-              out.push_back(pattern(row, (int32_t)start, buf, vi, take, type, it->second));
+              out.push_back(pattern(row, (int32_t)start, buf, vi, take, type, it->second, lp));
               start += (int64_t)take; vi += take; cnt -= take; other -= it->second;
             }
           }
@@ -777,7 +785,7 @@ class Miner {
           size_t nblocks = cnt / cap, per = std::min(cap, cnt);
           if (nblocks == 0) nblocks = 1; else skip_back += cnt - per * nblocks;
           for (size_t b = 0; b < nblocks; b++) {
-            out.push_back(pattern(row, (int32_t)start, buf, vi, per, type, per / a));
+            out.push_back(pattern(row, (int32_t)start, buf, vi, per, type, per / a, lp));
             start += (int64_t)per; vi += per;
           }
         }
@@ -790,32 +798,82 @@ class Miner {
     if (vi != n) throw TuneError("internal: encode_block consumed " + std::to_string(vi) + " of " + std::to_string(n));
   }
 
-  // Encode + EncodeRow, :863-903, 1292-1319
-  void encode(int t) {
-    if (t == T_NONE) return;
-    spm_->transform(t);
-    Trace tr("encode rows");
-    RecVec out;
-    out.reserve(spm_->e.size());
-    const Rec *recs = spm_->e.data();
-    const size_t n = spm_->e.size();
-    bool blk = is_blk(t);
-    size_t b = 0;
-    while (b < n) {
+  // EncodeRow, :1292-1319, for the records [b0, b1) (whole rows)
+  void encode_rows(const Rec *recs, size_t b0, size_t b1, bool blk, RecVec &out, std::vector<Run> &runs, ValVec *lp) {
+    size_t b = b0;
+    while (b < b1) {
       size_t e = b + 1;
-      while (e < n && recs[e].r == recs[b].r) e++;
+      while (e < b1 && recs[e].r == recs[b].r) e++;
       int32_t row = recs[b].r;
       size_t k = b;
       while (k < e) {
         if (is_pattern(recs[k])) { out.push_back(recs[k++]); continue; }
         size_t m = k;
         while (m < e && !is_pattern(recs[m])) m++;
-        if (blk) encode_block(row, recs + k, m - k, out); else encode_linear(row, recs + k, m - k, out);
+        if (blk) encode_block(row, recs + k, m - k, out, runs, lp); else encode_linear(row, recs + k, m - k, out, runs, lp);
         k = m;
       }
       b = e;
     }
-    spm_->e.swap(out);
+  }
+
+  // Encode, :863-903.  Rows are independent: big partitions are cut at row boundaries and encoded by several threads,
+  // each into its own record list and value pool, which are then put behind each other in row order (the final CSX
+  // arrays depend on the order of the records only, not on where a substructure's values sit in the pool).
+  void encode(int t) {
+    if (t == T_NONE) return;
+    spm_->transform(t);
+    Trace tr("encode rows");
+    const Rec *recs = spm_->e.data();
+    const size_t n = spm_->e.size();
+    bool blk = is_blk(t);
+    const int T = (n < par_min()) ? 1 : g_sort_threads;
+    if (T <= 1) {
+      RecVec out;
+      out.reserve(n);
+      encode_rows(recs, 0, n, blk, out, runs_, nullptr);
+      spm_->e.swap(out);
+    } else {
+      std::vector<size_t> cut((size_t)T + 1, n);
+      cut[0] = 0;
+      for (int k = 1; k < T; k++) {
+        size_t b = std::max(cut[k - 1], n / T * k);
+        while (b < n && b > 0 && recs[b].r == recs[b - 1].r) b++;   // to the next row start
+        cut[k] = b;
+      }
+      std::vector<RecVec> outs((size_t)T);
+      std::vector<ValVec> pools((size_t)T);
+      std::vector<std::string> errs((size_t)T);
+      std::vector<std::thread> th;
+      for (int k = 0; k < T; k++)
+        th.emplace_back([&, k]() {
+          try {
+            std::vector<Run> runs;
+            outs[k].reserve(cut[k + 1] - cut[k]);
+            encode_rows(recs, cut[k], cut[k + 1], blk, outs[k], runs, &pools[k]);
+          } catch (std::exception &ex) { errs[k] = ex.what(); }
+        });
+      for (auto &x : th) x.join();
+      for (auto &er : errs) if (!er.empty()) throw TuneError(er);
+      ValVec &pool = *spm_->pool;
+      std::vector<size_t> obase((size_t)T + 1, 0), pbase((size_t)T + 1, pool.size());
+      for (int k = 0; k < T; k++) { obase[k + 1] = obase[k] + outs[k].size(); pbase[k + 1] = pbase[k] + pools[k].size(); }
+      pool.resize(pbase[T]);
+      RecVec out(obase[T]);
+      th.clear();
+      for (int k = 0; k < T; k++)
+        th.emplace_back([&, k]() {
+          std::copy(pools[k].begin(), pools[k].end(), pool.begin() + (std::ptrdiff_t)pbase[k]);
+          Rec *dst = out.data() + obase[k];
+          for (size_t i = 0; i < outs[k].size(); i++) {
+            Rec r = outs[k][i];
+            if (r.vptr & LOCAL_VPTR) r.vptr = (r.vptr & ~LOCAL_VPTR) + pbase[k];
+            dst[i] = r;
+          }
+        });
+      for (auto &x : th) x.join();
+      spm_->e.swap(out);
+    }
     spm_->build_rowptr();
     ignore_[t] = true;
   }
