@@ -1,17 +1,19 @@
-// Host emulation of the chunk kernel (test infrastructure): tunes a CSR matrix with the product encoder,
-// builds the product's GPU layout and then executes sparsex_b200/csrc/chunk_kernel.cuh — the same text nvcc
-// compiles — warp by warp on the fibre emulation of warp_emul.hpp.  The cross-row unit table is applied with
-// a plain loop (that kernel is covered on the GPU).  Lets the CPU test suite check the decode logic of the
-// chunk kernel against the CSR input without a GPU.
+// Host emulation of both SpMV kernels (test infrastructure): tunes a CSR matrix with the product encoder, builds
+// the product's GPU layout and then executes sparsex_b200/csrc/gather_kernel.cuh (kernel 1, generic instantiations)
+// and chunk_kernel.cuh (kernel 2) — the same text nvcc compiles — warp by warp on the fibre emulation of
+// warp_emul.hpp.  Lets the CPU test suite check the traversal logic of the kernels against the CSR input without
+// a GPU.
 #include "warp_emul.hpp"
 
+#include <cmath>
 #include <sstream>
 #include <string>
 #include <vector>
 
 #define CSXB_EMUL 1
 #include "../../sparsex_b200/csrc/csx_host.hpp"
-#include "../../sparsex_b200/csrc/chunk_kernel.cuh"
+#include <type_traits>
+#include "../../sparsex_b200/csrc/gather_kernel.cuh"
 
 namespace {
 void put_err(char *err, size_t n, const std::string &m) {
@@ -49,16 +51,19 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     memcpy(vals.data() + L.parts[i].val_base, M.parts[i].values.data(), M.parts[i].values.size() * 8);
     memcpy(ctl.data() + L.parts[i].ctl_base, M.parts[i].ctl.data(), M.parts[i].ctl.size());
   }
-  for (int64_t i = 0; i < nrows; i++) y[i] = 0.0;
+  // stale content of y must not leak: kernel 1 writes every owned row; rows behind the last partition are cleared by
+  // the host side of csxb_spmv (VecInit(y, 0), CsxKernels.cpp:93)
+  int64_t covered = 0;
+  for (size_t i = 0; i < L.parts.size(); i++) covered = std::max<int64_t>(covered, L.parts[i].row_start + L.parts[i].nrows);
+  for (int64_t i = 0; i < nrows; i++) y[i] = i < covered ? std::nan("") : 0.0;
   for (int64_t i = 0; i < (int64_t)L.total_values; i++) { dec_rows[i] = -1; dec_cols[i] = -1; }
   int64_t nchunks = 0, nunits = 0, nxd = 0;
   static ChunkSmem smem;
+  std::vector<PartDev> pdev;
   for (size_t i = 0; i < L.parts.size(); i++) {
     const PartLayout &pl = L.parts[i];
     const CsxPartition &hp = M.parts[i];
-    // kernel 1 stand-in: diagonal (CSX-Sym) and the table units, each unit once (under the tile of its first row)
-    if (M.symmetric)
-      for (int64_t r = 0; r < pl.nrows; r++) y[pl.row_start + r] += alpha * hp.dvalues[r] * x[pl.row_start + r];
+    // decoded coordinates of the table units, each unit once (under the tile of its first row)
     for (int64_t t = 0; t < pl.ntiles; t++)
       for (uint32_t j = pl.tile_xoff[t]; j < pl.tile_xoff[t + 1]; j++) {
         const XDesc &d = pl.xdesc[j];
@@ -70,9 +75,6 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
         for (uint32_t k = 0; k < size; k++) {
           const int64_t r = d.row + (int64_t)k * delta;
           const int64_t c = kind == K_VERT ? d.col : (kind == K_DIAG ? d.col + (int64_t)k * delta : d.col - (int64_t)k * delta);
-          const double val = vals[d.voff + k];
-          y[r] += alpha * val * x[c];
-          if (M.symmetric) y[c] += alpha * val * x[r];
           dec_rows[d.voff + k] = (int32_t)r; dec_cols[d.voff + k] = (int32_t)c;
         }
       }
@@ -82,13 +84,51 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     P.values = vals.data();
     P.chunks = pl.chunks.data();
     P.uoffs = pl.uoffs.data();
+    P.tile_xoff = pl.tile_xoff.data();
+    P.xdesc = reinterpret_cast<const uint4 *>(pl.xdesc.data());
+    P.ktab = L.ktab.data();
+    P.dvalues = hp.dvalues.data();
     P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
     P.nchunks = (uint32_t)pl.chunks.size();
     P.full_colind = L.full_colind;
     P.rpt = pl.rpt;
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
+    pdev.push_back(P);
     nchunks += (int64_t)pl.chunks.size();
     nunits += (int64_t)pl.uoffs.size();
+    if (stats) stats[3] = pl.slice;
+  }
+  // kernel 1 of every partition first (it initialises y; under CSX-Sym chunks add into rows of other partitions),
+  // with the instantiation launch_gather would pick (the PTX variant of the diagonal kernel is device-only)
+  for (size_t i = 0; i < L.parts.size(); i++) {
+    const PartLayout &pl = L.parts[i];
+    const PartDev &P = pdev[i];
+    const bool xd = !pl.xdesc.empty(), diag1 = !M.symmetric && pl.xd_diag1_only && xd;
+    for (int64_t t = 0; t < pl.ntiles; t++)
+      for (int w = 0; w < CTA_THREADS / 32; w++) {
+        warp_emul::warp_in_cta() = w;
+        warp_emul::run_warp([&](int) {
+          const NoXchg nx;
+          if (M.symmetric) {
+            if (pl.rpt == 4) { if (xd) spmv_tile<true, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+                               else spmv_tile<false, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0); }
+            else { if (xd) spmv_tile<true, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+                   else spmv_tile<false, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0); }
+          } else if (pl.rpt == 4) {
+            if (diag1) spmv_tile<true, false, 4, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+            else if (xd) spmv_tile<true, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+            else spmv_tile<false, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+          } else {
+            if (diag1) spmv_tile<true, false, 1, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+            else if (xd) spmv_tile<true, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+            else spmv_tile<false, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+          }
+        });
+      }
+  }
+  warp_emul::warp_in_cta() = 0;
+  for (size_t i = 0; i < L.parts.size(); i++) {
+    const PartDev &P = pdev[i];
     for (uint32_t ch = 0; ch < P.nchunks; ch++) {
       for (int pass = 0; pass < 2; pass++) {
         if (pass == 0) {
@@ -111,7 +151,6 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
         }
       }
     }
-    if (stats) stats[3] = pl.slice;
   }
   for (size_t i = 0; i < M.parts.size(); i++) M.parts[i].nrows = saved[i];
   if (stats) { stats[0] = nchunks; stats[1] = nunits; stats[2] = nxd; }

@@ -85,7 +85,12 @@ inline const uint64_t *exchange(uint64_t bits) {
   return w->slot[ph & 1];
 }
 inline int lane_id() { return cur()->lane; }
+// threadIdx of the emulated thread: the harness sets the warp's position in its CTA before run_warp()
+inline int &warp_in_cta() { static int w = 0; return w; }
+struct Tid { int x; };
+inline Tid tid() { return Tid{warp_in_cta() * 32 + lane_id()}; }
 }  // namespace warp_emul
+#define threadIdx (warp_emul::tid())
 
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) { const uint64_t *s = warp_emul::exchange(warp_emul::to_bits(v)); return warp_emul::from_bits<T>(s[src & 31]); }
@@ -124,6 +129,7 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
 inline void __syncwarp() { warp_emul::exchange(0); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c) {

@@ -54,6 +54,23 @@ def test_emulated_chunk_kernel_symmetric(seed):
                                           "spx.preproc.sampling": "none", "spx.rt.nr_threads": nt}, sym=True)
 
 
+def test_emulated_gather_kernel_tile_shapes_and_diagonal_variant():
+    """Kernel 1 (gather over the cross-row unit table): one and four rows per thread, the stride-1 diagonal
+    instantiation the stencil configs run, carry-in descriptors across tiles, CSX-Sym transposed images."""
+    from tests.matrices import poisson2d
+    rp, ci, va, n = poisson2d(40, perturb=False)   # symmetric values: also used with spx.matrix.symmetric
+    for rpt in (1, 4):
+        for o in ({"spx.preproc.xform": "d", "spx.preproc.sampling": "none"}, {"spx.preproc.sampling": "none"},
+                  {"spx.preproc.xform": "v,d,ad", "spx.preproc.sampling": "none", "spx.rt.nr_threads": 3},
+                  {"spx.preproc.xform": "d,v", "spx.preproc.sampling": "none", "spx.matrix.symmetric": "true", "spx.rt.nr_threads": 2}):
+            st = _check(rp, ci, va, n, n, dict(o, **{"spx.b200.rows_per_thread": rpt}), sym="spx.matrix.symmetric" in o)
+            assert st[2] > 0   # table units present
+    rng = np.random.default_rng(9)
+    rp, ci, va = random_structured(rng, 700, 650)
+    for rpt in (1, 4):
+        _check(rp, ci, va, 700, 650, {"spx.preproc.xform": "v,d,ad", "spx.preproc.sampling": "none", "spx.b200.rows_per_thread": rpt})
+
+
 def test_emulated_chunk_kernel_config_shapes():
     """Scaled-down BASELINE configs: block stencil, symmetric block-banded, R-MAT."""
     rp, ci, va, n = stencil27(14)
