@@ -124,3 +124,42 @@ def test_symmetric_halo_reduce(world):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _peer_fallback_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sparsex_b200.dist as sdist
+        from sparsex_b200 import CsxMatrix
+        from tests.matrices import poisson2d
+        rp, ci, va, n = poisson2d(40)
+        A = CsxMatrix.tune_csr(rp, ci, va, n, n, {"spx.rt.nr_threads": world}, part_lo=rank, part_hi=rank + 1)
+        # no GPU here: the exchange cannot be created; every rank must learn that and agree on the fallback,
+        # without any rank hanging in a collective
+        ex, ranges, windows = sdist.connect_peer_exchange(A, rank, world, "cpu")
+        assert ex is None and sdist.last_peer_error
+        assert sum(cnt for _, cnt in ranges) == n and len(windows) == world
+        lo, cnt = ranges[rank]
+        assert windows[rank][0] <= lo and windows[rank][1] >= lo + cnt - 1
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL %r" % (e,)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_falls_back_consistently():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_peer_fallback_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
