@@ -143,7 +143,8 @@ int csxb_vec_dot(const double *d_a, const double *d_b, int64_t n, double *result
  *   vector  : device pointer of vec[which]; fill vec[0] with the initial x (all columns the rank reads)
  *   spmv    : one step (asynchronous on `stream`).  The host alternates the two vectors from call to call, so a
  *             CUDA graph that is replayed must capture an even number of steps
- *   status  : what = 0 steps finished, 1 error word (non-zero: a wait for a neighbour timed out),
+ *   status  : what = 0 steps finished, 1 error word (non-zero: a wait for a neighbour timed out — device-side waits
+ *             give up after about three seconds, so ranks have to issue their steps within that time of each other),
  *             2 protocol (1: edge tiles first — the tiles that touch other ranks run first in every step and
  *             publish it at once, nothing else waits; 0: one sync kernel at the end of every step), 3 edge tiles */
 typedef struct csxb_xchg csxb_xchg_t;
