@@ -23,6 +23,16 @@ struct PartDev {
   int full_colind;
   int rpt;                     // rows per thread: a tile has CTA_THREADS * rpt rows
   uint32_t tile0, chunk0;      // first tile / chunk of this launch (a launch may cover a sub-range)
+  // stream kernel (stream_kernel.cuh; non-symmetric partitions)
+  const uint4 *sk_chunks;      // 32-byte chunk entries (SkEntry)
+  const uint16_t *sk_uoffs;    // unit head offsets inside the chunks
+  double *sk_scratch;          // sums a chunk contributes to rows of other chunks
+  const int32_t *sk_fix_rows;  // rows with such contributions, their scratch slots sk_fix_idx[ptr[i] .. ptr[i+1])
+  const uint32_t *sk_fix_ptr, *sk_fix_idx;
+  const long long *sk_gaps;    // pairs [lo, hi) of partition-relative rows no chunk window covers
+  uint32_t sk_c0, sk_c1;       // chunks of this launch
+  uint32_t sk_f0, sk_f1;       // fix rows of this launch
+  uint32_t sk_g0, sk_g1;       // gaps of this launch
   IdEntry idtab[64];
 };
 

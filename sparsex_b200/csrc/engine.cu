@@ -33,6 +33,7 @@
 #include "csx_host.hpp"
 #include "gpu_layout.hpp"
 #include "chunk_kernel.cuh"
+#include "stream_kernel.cuh"
 
 #include "gather_kernel.cuh"
 
@@ -198,6 +199,67 @@ __global__ void __launch_bounds__(CTA_THREADS) csx_decode_gather_kernel(const __
   }
 }
 
+// ---- kernel 2 of non-symmetric partitions: stream kernel (stream_kernel.cuh), one warp per chunk ----------------
+__device__ __forceinline__ void sk_vectors(const SkIO &io, const double *&x, double *&y) {
+  x = io.x; y = io.y;
+  if (io.step) {   // multi-GPU exchange: vectors by step parity
+    const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(io.step);
+    x = io.vec[k & 1]; y = io.vec[(k & 1) ^ 1];
+  }
+}
+template <int R, uint32_t KM>
+__global__ void __launch_bounds__(SK_WARPS * 32, 4) csx_stream_kernel(const __grid_constant__ PartDev P, const __grid_constant__ SkIO io,
+                                                                     double alpha, double beta, int overwrite) {
+  __shared__ double sacc[SK_WARPS][SK_WIN];
+  __shared__ uint4 sid[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 64) {
+    const IdEntry &ie = P.idtab[threadIdx.x];
+    sid[threadIdx.x] = make_uint4(ie.kind_align, ie.delta, ie.sl, ie.recip);
+  }
+  __syncthreads();
+  const uint32_t ch = P.sk_c0 + blockIdx.x * SK_WARPS + warp;
+  if (ch >= P.sk_c1) return;
+  const double *x; double *y;
+  sk_vectors(io, x, y);
+  sk_chunk<R, KM, false>(P, ch, sacc[warp], sid, lane, x, y, alpha, beta, overwrite, nullptr, nullptr);
+}
+__global__ void __launch_bounds__(SK_WARPS * 32) csx_stream_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
+  __shared__ double sacc[SK_WARPS][SK_WIN];
+  __shared__ uint4 sid[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 64) {
+    const IdEntry &ie = P.idtab[threadIdx.x];
+    sid[threadIdx.x] = make_uint4(ie.kind_align, ie.delta, ie.sl, ie.recip);
+  }
+  __syncthreads();
+  const uint32_t ch = P.sk_c0 + blockIdx.x * SK_WARPS + warp;
+  if (ch >= P.sk_c1) return;
+  sk_chunk<8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, true>(P, ch, sacc[warp], sid, lane, nullptr, nullptr, 0.0, 0.0, 1, rows + P.val_base,
+                                                         cols + P.val_base);
+}
+// After the stream kernel: adds what chunks contributed to rows of other chunks (in chunk order: deterministic) and
+// clears the rows no chunk window covers (long runs of empty rows), clipped to [clip_lo, clip_hi).
+__global__ void __launch_bounds__(256) csx_stream_fixup_kernel(const __grid_constant__ PartDev P, const __grid_constant__ SkIO io,
+                                                                double alpha, double beta, int overwrite, long long clip_lo,
+                                                                long long clip_hi) {
+  const double *x; double *y;
+  sk_vectors(io, x, y);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = P.sk_f0 + tid; i < P.sk_f1; i += nth) {
+    double s = 0.0;
+    for (uint32_t j = P.sk_fix_ptr[i]; j < P.sk_fix_ptr[i + 1]; j++) s += P.sk_scratch[P.sk_fix_idx[j]];
+    y[P.row_start + P.sk_fix_rows[i]] += alpha * s;
+  }
+  for (uint32_t g = P.sk_g0; g < P.sk_g1; g++) {
+    const long long lo = max(P.sk_gaps[2 * g], clip_lo), hi = min(P.sk_gaps[2 * g + 1], clip_hi);
+    for (long long r = lo + tid; r < hi; r += nth) {
+      double *yp = y + P.row_start + r;
+      *yp = overwrite ? 0.0 : beta * *yp;
+    }
+  }
+}
+
 // --------------------------------------------------------------- host side --
 static thread_local std::string g_last_error;
 static int fail(const std::string &m) { g_last_error = m; return -1; }
@@ -221,7 +283,11 @@ struct csxb_matrix {
   int64_t sym_halo_lo = 0, sym_halo_hi = 0;   // CSX-Sym, partial device: rows of other devices this one adds into
   // pipelined host-buffer path (csxb_spmv_host): row slabs with the x columns they need and the y rows that are
   // final once they have run
-  struct Slab { int part; int64_t tile0, tile1; uint32_t chunk0, chunk1; int64_t x_lo, x_hi, row_lo, row_hi, y_lo, y_hi; };
+  struct Slab {
+    int part; int64_t tile0, tile1;
+    uint32_t chunk0, chunk1, f0, f1, g0, g1;   // stream-kernel chunks, fix rows and gaps that run with this slab
+    int64_t x_lo, x_hi, row_lo, row_hi, y_lo, y_hi, yup_hi;
+  };
   std::vector<Slab> slabs;
   std::vector<cudaEvent_t> slab_ev;
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
@@ -384,9 +450,9 @@ static int dev_copy(csxb_matrix *m, const T *src, size_t n, T **dst, size_t extr
   return 0;
 }
 
-// Row slabs of the pipelined host-buffer path: about 4 MB of y per slab.  A chunk runs with the slab that
-// holds the last row it touches (kernel 1 must have initialised every row a chunk adds into), and a slab's y
-// rows travel back only up to the first row of the first chunk that runs later.
+// Row slabs of the pipelined host-buffer path (non-symmetric matrices): about 4 MB of y per slab.  A stream-kernel
+// chunk runs with the first slab whose rows reach its window; the rows of a slab are final once its chunks, its
+// fix-ups and its tiles of the gather kernel have run, and travel back then.
 static void build_slabs(csxb_matrix *m) {
   m->slabs.clear();
   const int64_t SLAB_ROWS = m->host.slab_rows;
@@ -394,32 +460,35 @@ static void build_slabs(csxb_matrix *m) {
     const PartLayout &pl = m->layout.parts[i];
     if (!pl.ntiles) continue;
     const int64_t tr = pl.tile_rows(), tiles_per = std::max<int64_t>(1, SLAB_ROWS / tr);
-    uint32_t c = 0;
-    const uint32_t nc = (uint32_t)pl.chunks.size();
-    int64_t y_done = pl.row_start, xmax = -1, xmin = INT32_MAX;
+    uint32_t c = 0, f = 0;
+    const uint32_t nc = (uint32_t)pl.sk_chunks.size(), nf = (uint32_t)pl.sk_fix_rows.size(), ng = (uint32_t)pl.sk_gaps.size();
+    int64_t xmax = -1, yup = 0;
     for (int64_t t0 = 0; t0 < pl.ntiles; t0 += tiles_per) {
       csxb_matrix::Slab sl;
       sl.part = (int)i; sl.tile0 = t0; sl.tile1 = std::min(pl.ntiles, t0 + tiles_per);
-      const int64_t r1 = std::min(pl.nrows, sl.tile1 * tr);   // partition-relative end row
-      sl.row_lo = pl.row_start + t0 * tr; sl.row_hi = pl.row_start + r1;
+      const int64_t r0 = t0 * tr, r1 = std::min(pl.nrows, sl.tile1 * tr);   // partition-relative rows
+      sl.row_lo = pl.row_start + r0; sl.row_hi = pl.row_start + r1;
       for (int64_t t = sl.tile0; t < sl.tile1; t++)
-        if (pl.tile_cmax[t] >= pl.tile_cmin[t]) { xmax = std::max<int64_t>(xmax, pl.tile_cmax[t]); xmin = std::min<int64_t>(xmin, pl.tile_cmin[t]); }
+        if (pl.tile_cmax[t] >= pl.tile_cmin[t]) xmax = std::max<int64_t>(xmax, pl.tile_cmax[t]);
       sl.chunk0 = c;
-      int32_t last = -1;
-      while (c < nc) {   // chunks in stream order; running maximum of the last rows they touch
-        last = std::max(last, pl.chunk_last_row[c]);
-        if (last >= r1) break;
+      while (c < nc && pl.sk_first_row[c] < r1) {
+        xmax = std::max<int64_t>(xmax, pl.sk_cmax[c]);
+        yup = std::max<int64_t>(yup, (int64_t)pl.sk_last_row[c] + 1);
         c++;
       }
       sl.chunk1 = c;
+      sl.f0 = f;
+      while (f < nf && pl.sk_fix_rows[f] < r1) f++;
+      sl.f1 = f;
+      sl.g0 = 0;
+      while (sl.g0 < ng && pl.sk_gaps[sl.g0].hi <= r0) sl.g0++;
+      sl.g1 = sl.g0;
+      while (sl.g1 < ng && pl.sk_gaps[sl.g1].lo < r1) sl.g1++;
       sl.x_lo = 0; sl.x_hi = xmax + 1;
-      sl.y_lo = y_done;
-      sl.y_hi = c < nc ? std::min<int64_t>(sl.row_hi, pl.row_start + pl.chunks[c].row) : sl.row_hi;
-      sl.y_hi = std::max(sl.y_hi, sl.y_lo);
-      y_done = sl.y_hi;
+      sl.y_lo = sl.row_lo; sl.y_hi = sl.row_hi;
+      sl.yup_hi = pl.row_start + std::max(r1, std::min(yup, pl.nrows));
       m->slabs.push_back(sl);
     }
-    (void)xmin;
   }
   // x travels in ascending column order starting at the smallest column any local slab reads
   int64_t lo = INT64_MAX;
@@ -475,6 +544,27 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     if (dev_copy(m, pl.tile_xoff.data(), pl.tile_xoff.size(), &tx)) return -1;
     if (dev_copy(m, pl.xdesc.data(), pl.xdesc.size(), &xd)) return -1;
     P.chunks = ch; P.nchunks = (uint32_t)pl.chunks.size();
+    if (!pl.sk_chunks.empty()) {   // stream kernel tables
+      SkEntry *se = nullptr; uint16_t *so = nullptr; int32_t *fr = nullptr; uint32_t *fp = nullptr, *fi = nullptr; long long *gp = nullptr;
+      if (dev_copy(m, pl.sk_chunks.data(), pl.sk_chunks.size(), &se)) return -1;
+      if (dev_copy(m, pl.sk_uoffs.data(), pl.sk_uoffs.size(), &so)) return -1;
+      if (dev_copy(m, pl.sk_fix_rows.data(), pl.sk_fix_rows.size(), &fr)) return -1;
+      if (dev_copy(m, pl.sk_fix_ptr.data(), pl.sk_fix_ptr.size(), &fp)) return -1;
+      if (dev_copy(m, pl.sk_fix_idx.data(), pl.sk_fix_idx.size(), &fi)) return -1;
+      static_assert(sizeof(SkGap) == 16, "gap layout");
+      if (dev_copy(m, reinterpret_cast<const long long *>(pl.sk_gaps.data()), pl.sk_gaps.size() * 2, &gp)) return -1;
+      void *sc = nullptr;
+      CUDA_TRY(cudaMalloc(&sc, std::max<size_t>(pl.sk_scratch, 2) * 8));
+      m->allocs.push_back(sc);
+      P.sk_chunks = (const uint4 *)se; P.sk_uoffs = so; P.sk_scratch = (double *)sc;
+      P.sk_fix_rows = fr; P.sk_fix_ptr = fp; P.sk_fix_idx = fi; P.sk_gaps = gp;
+      P.sk_c0 = 0; P.sk_c1 = (uint32_t)pl.sk_chunks.size();
+      P.sk_f0 = 0; P.sk_f1 = (uint32_t)pl.sk_fix_rows.size();
+      P.sk_g0 = 0; P.sk_g1 = (uint32_t)pl.sk_gaps.size();
+      // chunk table, unit offsets, fix-up lists, and the scratch sums (written once, read once)
+      tables += (int64_t)pl.sk_chunks.size() * (int64_t)sizeof(SkEntry) + (int64_t)pl.sk_uoffs.size() * 2 +
+                (int64_t)pl.sk_fix_rows.size() * 8 + (int64_t)pl.sk_fix_idx.size() * 4 + (int64_t)pl.sk_scratch * 16;
+    }
     P.tile_xoff = tx; P.xdesc = (const uint4 *)xd; P.ktab = d_ktab;
     if (H.symmetric) {
       double *dd = nullptr;
@@ -489,7 +579,11 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
     tables += (int64_t)pl.chunks.size() * (int64_t)sizeof(ChunkEntry) + (int64_t)pl.uoffs.size() * 2;
-    if (pl.nrows) launches += 1 + (pl.chunks.empty() ? 0 : 1);
+    if (pl.nrows) {
+      if (!pl.sk_chunks.empty())
+        launches += 1 + ((pl.sk_fix_rows.empty() && pl.sk_gaps.empty()) ? 0 : 1) + (pl.xdesc.empty() ? 0 : 1);
+      else launches += 1 + (pl.chunks.empty() ? 0 : 1);
+    }
     m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
     if (free_host) std::vector<double>().swap(hp.values);
   }
@@ -582,6 +676,59 @@ static void launch_chunks(const PartDev &P0, bool sym, uint32_t c0, uint32_t c1,
   else csx_chunk_kernel<false, XP><<<grid, CHUNK_WARPS * 32, 0, s>>>(P, x, y, alpha, X);
 }
 
+// Launches the stream kernel over chunks [c0, c1) of one partition: the instantiation is chosen by the partition's
+// pattern set (kinds of units, rows of a block task) — the counterpart of the per-partition JIT (CsxJit.hpp:359-732).
+static int launch_stream(const PartDev &P0, const PartLayout &pl, uint32_t c0, uint32_t c1, const SkIO &io, double alpha, double beta,
+                         int overwrite, cudaStream_t s) {
+  if (c1 <= c0) return 0;
+  PartDev P = P0;
+  P.sk_c0 = c0; P.sk_c1 = c1;
+  const unsigned grid = (unsigned)((c1 - c0 + SK_WARPS - 1) / SK_WARPS);
+  const uint32_t km = pl.sk_kmask;
+  const int r = pl.sk_rows;
+#define SK_TRY(RR, KK)                                                                                       \
+  if (r <= RR && (km & ~(uint32_t)(KK)) == 0) {                                                              \
+    csx_stream_kernel<RR, (KK)><<<grid, SK_WARPS * 32, 0, s>>>(P, io, alpha, beta, overwrite);               \
+    return 0;                                                                                                \
+  }
+  SK_TRY(1, SKM_DELTA)
+  SK_TRY(1, SKM_ROWLOCAL)
+  SK_TRY(2, SKM_ROWLOCAL | SKM_BCOL)
+  SK_TRY(3, SKM_ROWLOCAL | SKM_BCOL)
+  SK_TRY(4, SKM_ROWLOCAL | SKM_BCOL)
+  SK_TRY(2, SKM_ROWLOCAL | SKM_BROW)
+  SK_TRY(3, SKM_ROWLOCAL | SKM_BROW)
+  SK_TRY(4, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
+  SK_TRY(8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
+#undef SK_TRY
+  return -1;
+}
+// Fix-up of rows [r0, r1) (partition relative) after the stream kernel: foreign contributions f0..f1, gaps g0..g1.
+static void launch_fixup(const PartDev &P0, uint32_t f0, uint32_t f1, uint32_t g0, uint32_t g1, int64_t r0, int64_t r1, const SkIO &io,
+                         double alpha, double beta, int overwrite, cudaStream_t s) {
+  if (f1 <= f0 && g1 <= g0) return;
+  PartDev P = P0;
+  P.sk_f0 = f0; P.sk_f1 = f1; P.sk_g0 = g0; P.sk_g1 = g1;
+  int64_t work = (int64_t)(f1 - f0);
+  if (g1 > g0) work = std::max<int64_t>(work, 148 * 4 * 256);
+  const unsigned grid = (unsigned)std::min<int64_t>(148 * 4, (work + 255) / 256);
+  csx_stream_fixup_kernel<<<grid, 256, 0, s>>>(P, io, alpha, beta, overwrite, (long long)r0, (long long)r1);
+}
+// One partition of a non-symmetric matrix, whole: stream kernel (writes y), fix-up, then the gather over the table,
+// which adds (beta = 1).  Without stream chunks the gather kernel alone writes y.
+template <class XP>
+static int run_partition(const PartDev &P, const PartLayout &pl, const SkIO &io, double alpha, double beta, int overwrite,
+                         cudaStream_t s, const XP &X) {
+  if (pl.sk_chunks.empty()) {
+    launch_gather<false>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, beta, overwrite, s, X);
+    return 0;
+  }
+  if (launch_stream(P, pl, 0, (uint32_t)pl.sk_chunks.size(), io, alpha, beta, overwrite, s)) return -1;
+  launch_fixup(P, 0, (uint32_t)pl.sk_fix_rows.size(), 0, (uint32_t)pl.sk_gaps.size(), 0, pl.nrows, io, alpha, beta, overwrite, s);
+  if (!pl.xdesc.empty()) launch_gather<false>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, 1.0, 0, s, X);
+  return 0;
+}
+
 extern "C" {
 
 int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, double *d_y, int overwrite, void *stream) {
@@ -592,13 +739,19 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
     CUDA_TRY(cudaMemsetAsync(d_y + m->sym_halo_lo, 0, (size_t)(m->sym_halo_hi - m->sym_halo_lo) * 8, s));
   // kernel 1 of every partition first: it initialises y, and under CSX-Sym the chunk kernel of one
   // partition adds into rows that another partition owns
-  for (size_t i = 0; i < m->pdev.size(); i++) {
-    const PartLayout &pl = m->layout.parts[i];
-    if (sym) launch_gather<true>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, beta, overwrite, s, NoXchg());
-    else launch_gather<false>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, beta, overwrite, s, NoXchg());
+  if (!sym) {
+    SkIO io;
+    io.x = d_x; io.y = d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
+    for (size_t i = 0; i < m->pdev.size(); i++)
+      if (run_partition(m->pdev[i], m->layout.parts[i], io, alpha, beta, overwrite, s, NoXchg())) return fail("no stream kernel for the partition's pattern set");
+  } else {
+    for (size_t i = 0; i < m->pdev.size(); i++) {
+      const PartLayout &pl = m->layout.parts[i];
+      launch_gather<true>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, beta, overwrite, s, NoXchg());
+    }
+    for (size_t i = 0; i < m->pdev.size(); i++)
+      launch_chunks(m->pdev[i], sym, 0, (uint32_t)m->layout.parts[i].chunks.size(), d_x, d_y, alpha, s, NoXchg());
   }
-  for (size_t i = 0; i < m->pdev.size(); i++)
-    launch_chunks(m->pdev[i], sym, 0, (uint32_t)m->layout.parts[i].chunks.size(), d_x, d_y, alpha, s, NoXchg());
   // rows after the last partition's last non-empty row belong to nobody; VecInit(y,0) clears them (CsxKernels.cpp:93)
   if (overwrite && m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total && m->covered_rows_end < m->host.nrows)
     CUDA_TRY(cudaMemsetAsync(d_y + m->covered_rows_end, 0, (size_t)(m->host.nrows - m->covered_rows_end) * 8, s));
@@ -642,6 +795,7 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
       for (size_t i = old; i < m->slab_ev.size(); i++) CUDA_TRY(cudaEventCreateWithFlags(&m->slab_ev[i], cudaEventDisableTiming));
     }
     int64_t x_done = m->slabs.front().x_lo;   // columns [x_lo of the first slab, x_done) are on the device
+    int64_t y_up = 0;                         // y rows below this one are on the device (spx_matvec_kernel semantics)
     for (size_t k = 0; k < m->slabs.size(); k++) {
       const csxb_matrix::Slab &sl = m->slabs[k];
       const PartLayout &pl = m->layout.parts[sl.part];
@@ -649,12 +803,24 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
         CUDA_TRY(cudaMemcpyAsync(m->d_x + x_done, h_x + x_done, (size_t)(sl.x_hi - x_done) * 8, cudaMemcpyHostToDevice, m->s_h2d));
         x_done = sl.x_hi;
       }
-      if (!overwrite && sl.row_hi > sl.row_lo)
-        CUDA_TRY(cudaMemcpyAsync(m->d_y + sl.row_lo, h_y + sl.row_lo, (size_t)(sl.row_hi - sl.row_lo) * 8, cudaMemcpyHostToDevice, m->s_h2d));
+      if (!overwrite) {   // y rows the slab's kernels read: its own rows and the rows its chunks own behind them
+        if (k == 0 || m->slabs[k - 1].part != sl.part) y_up = sl.row_lo;
+        if (sl.yup_hi > y_up) {
+          CUDA_TRY(cudaMemcpyAsync(m->d_y + y_up, h_y + y_up, (size_t)(sl.yup_hi - y_up) * 8, cudaMemcpyHostToDevice, m->s_h2d));
+          y_up = sl.yup_hi;
+        }
+      }
       CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k], m->s_h2d));
       CUDA_TRY(cudaStreamWaitEvent(m->s_run, m->slab_ev[2 * k], 0));
-      launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, beta, overwrite, m->s_run, NoXchg());
-      launch_chunks(m->pdev[sl.part], false, sl.chunk0, sl.chunk1, m->d_x, m->d_y, alpha, m->s_run, NoXchg());
+      if (pl.sk_chunks.empty()) {
+        launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, beta, overwrite, m->s_run, NoXchg());
+      } else {   // stream kernel writes y, fix-up, then the gather over the table adds
+        SkIO io;
+        io.x = m->d_x; io.y = m->d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
+        if (launch_stream(m->pdev[sl.part], pl, sl.chunk0, sl.chunk1, io, alpha, beta, overwrite, m->s_run)) return fail("no stream kernel for the partition's pattern set");
+        launch_fixup(m->pdev[sl.part], sl.f0, sl.f1, sl.g0, sl.g1, sl.row_lo - pl.row_start, sl.row_hi - pl.row_start, io, alpha, beta, overwrite, m->s_run);
+        if (!pl.xdesc.empty()) launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, 1.0, 0, m->s_run, NoXchg());
+      }
       CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k + 1], m->s_run));
       if (sl.y_hi > sl.y_lo) {
         CUDA_TRY(cudaStreamWaitEvent(m->s_d2h, m->slab_ev[2 * k + 1], 0));
@@ -709,7 +875,7 @@ csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world) {
   unsigned long long *ctrl = (unsigned long long *)((char *)h->base + 2 * vb);
   h->dev.step = ctrl; h->dev.error = ctrl + 1; h->dev.started = ctrl + 2; h->dev.bdone = ctrl + 3; h->dev.flags = ctrl + 16;
   h->dev.rank = rank;
-  for (auto &pl : m->layout.parts) if (!pl.chunks.empty()) h->fused_push = false;
+  for (auto &pl : m->layout.parts) if (!pl.chunks.empty() || !pl.sk_chunks.empty()) h->fused_push = false;
   if (world == 1) {
     xchg_choose_mode(h, 0, (int64_t)h->n);
     h->connected = true;
@@ -822,13 +988,13 @@ int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
   static const int dbg = getenv("CSXB_XCHG_DEBUG") ? atoi(getenv("CSXB_XCHG_DEBUG")) : 0;   // tuning aid
   XchgDev X = h->dev;
   if (!h->fused_push || (dbg & 4)) X.npush = 0;   // rows are final only after the chunk kernel: pushed by a copy kernel below
+  SkIO io;
+  io.x = nullptr; io.y = nullptr; io.step = h->dev.step; io.vec[0] = h->dev.vec[0]; io.vec[1] = h->dev.vec[1];
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
     if (X.mode == 1) launch_gather_xe(m->pdev[i], pl, X.vec[h->parity], X.vec[h->parity ^ 1], alpha, h->parity ^ 1, s, X);
-    else launch_gather<false>(m->pdev[i], pl, 0, pl.ntiles, nullptr, nullptr, alpha, 0.0, 1, s, X);
+    else if (run_partition(m->pdev[i], pl, io, alpha, 0.0, 1, s, X)) return fail("no stream kernel for the partition's pattern set");
   }
-  for (size_t i = 0; i < m->pdev.size(); i++)
-    launch_chunks(m->pdev[i], false, 0, (uint32_t)m->layout.parts[i].chunks.size(), nullptr, nullptr, alpha, s, X);
   if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 4, 256, 0, s>>>(h->dev);
   if (h->tail_hi > h->tail_lo)
     csx_xchg_zero_tail_kernel<<<(unsigned)std::min<int64_t>(148, (h->tail_hi - h->tail_lo + 255) / 256), 256, 0, s>>>(h->dev, h->tail_lo, h->tail_hi, h->dev.mode == 1 ? (h->parity ^ 1) : -1);
@@ -1008,6 +1174,8 @@ int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t
   if (pl.ntiles && !pl.xdesc.empty()) csx_decode_gather_kernel<<<(unsigned)pl.ntiles, CTA_THREADS>>>(m->pdev[part], dr, dcl);
   if (!pl.chunks.empty())
     csx_decode_chunk_kernel<<<(unsigned)((pl.chunks.size() + CHUNK_WARPS - 1) / CHUNK_WARPS), CHUNK_WARPS * 32>>>(m->pdev[part], dr, dcl);
+  if (!pl.sk_chunks.empty())
+    csx_stream_decode_kernel<<<(unsigned)((pl.sk_chunks.size() + SK_WARPS - 1) / SK_WARPS), SK_WARPS * 32>>>(m->pdev[part], dr, dcl);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy(rows, dr + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(cols, dcl + pl.val_base, (size_t)pl.nnz * 4, cudaMemcpyDeviceToHost));

@@ -132,6 +132,109 @@ std::string choose_slice(const CsxPartition &cp, const CsxMatrix &m, size_t nid,
   return "";
 }
 
+
+// ---- stream kernel chunking (see gpu_layout.hpp) -----------------------------------------------------------
+struct SkUnit {
+  uint64_t off, end;        // ctl offsets of the unit head and of the byte behind the unit
+  uint32_t size, ntasks;
+  int64_t row, reach;       // partition-relative start row, rows below it the unit touches
+  int64_t cmin, cmax;       // columns it reads
+  int64_t val;              // partition-relative index of its first value
+  int64_t cursor_before;    // column cursor before the unit (0 when it starts a row)
+  bool multi_bcol;          // block-column unit cut into several tasks
+};
+
+class SkBuilder {
+ public:
+  SkBuilder(PartLayout &L, int64_t nrows) : L_(L), nrows_(nrows) {}
+  void add(const SkUnit &u) {
+    while (!open_.empty() && !fits(u)) split(u);
+    if (open_.empty()) wrow_ = (first_ && u.row + u.reach <= 64) ? 0 : u.row;
+    open_.push_back(u);
+  }
+  void finish() {
+    if (!open_.empty()) close(open_.size(), 0, false);
+    open_.clear();
+    std::stable_sort(fixes_.begin(), fixes_.end(),
+                     [](const std::pair<int32_t, uint32_t> &a, const std::pair<int32_t, uint32_t> &b) { return a.first < b.first; });
+    for (size_t i = 0; i < fixes_.size(); i++) {
+      if (i == 0 || fixes_[i].first != fixes_[i - 1].first) { L_.sk_fix_rows.push_back(fixes_[i].first); L_.sk_fix_ptr.push_back((uint32_t)i); }
+      L_.sk_fix_idx.push_back(fixes_[i].second);
+    }
+    L_.sk_fix_ptr.push_back((uint32_t)fixes_.size());
+  }
+  void discard() {   // the partition's stream units were folded into the table
+    open_.clear(); fixes_.clear();
+    L_.sk_chunks.clear(); L_.sk_uoffs.clear(); L_.sk_gaps.clear(); L_.sk_scratch = 0;
+    L_.sk_first_row.clear(); L_.sk_last_row.clear(); L_.sk_cmin.clear(); L_.sk_cmax.clear();
+    L_.sk_fix_rows.clear(); L_.sk_fix_ptr.clear(); L_.sk_fix_idx.clear();
+  }
+
+ private:
+  bool fits(const SkUnit &u) const {
+    uint32_t tasks = u.ntasks, elems = u.size;
+    for (const SkUnit &o : open_) { tasks += o.ntasks; elems += o.size; }
+    return open_.size() + 1 <= (size_t)SK_MAX_UNITS && tasks <= (uint32_t)SK_MAX_TASKS && elems <= (uint32_t)SK_MAX_ELEMS &&
+           u.end - open_.front().off <= (uint64_t)SK_MAX_BYTES && u.row + u.reach - wrow_ <= SK_WROWS - 1 &&
+           u.row - wrow_ <= SK_WROWS - 2;
+  }
+  // The open chunk cannot take `next`: close it, preferably at the start of its last row when `next` continues
+  // that row and the cut keeps the chunk at least three quarters full (a chunk that ends with its row needs no
+  // fix-up), and keep the units behind the cut open.
+  void split(const SkUnit &next) {
+    size_t b = open_.size();
+    if (next.row == open_.back().row) {
+      for (size_t i = open_.size() - 1; i > 0; i--)
+        if (open_[i].row != open_[i - 1].row) { if (4 * i >= 3 * open_.size()) b = i; break; }
+    }
+    close(b, b < open_.size() ? open_[b].row : next.row, true);
+    open_.erase(open_.begin(), open_.begin() + (long)b);
+    if (!open_.empty()) wrow_ = open_.front().row;
+  }
+  void close(size_t b, int64_t next_row, bool has_next) {
+    const int64_t ra = open_[0].row, rl = open_[b - 1].row;
+    int64_t touch_hi = 0, cmin = INT64_MAX, cmax = -1;
+    bool multib = false;
+    for (size_t i = 0; i < b; i++) {
+      touch_hi = std::max(touch_hi, open_[i].row + open_[i].reach);
+      cmin = std::min(cmin, open_[i].cmin); cmax = std::max(cmax, open_[i].cmax);
+      multib |= open_[i].multi_bcol;
+    }
+    int64_t own_lo = first_ ? 0 : prev_own_hi_;
+    if (first_ && wrow_ != 0) { L_.sk_gaps.push_back(SkGap{0, ra}); own_lo = ra; }
+    const int64_t own_hi = has_next ? (next_row > rl ? next_row : rl + 1) : nrows_;
+    const bool head = !first_ && own_lo > ra;
+    const int64_t f_lo = own_lo - wrow_, f_hi = std::min(own_hi, wrow_ + SK_WROWS) - wrow_;
+    if (own_hi > wrow_ + SK_WROWS) L_.sk_gaps.push_back(SkGap{wrow_ + SK_WROWS, own_hi});
+    const int64_t t_hi = touch_hi >= own_hi ? touch_hi - wrow_ + 1 : f_hi;
+    const uint32_t slot = L_.sk_scratch;
+    L_.sk_scratch += (uint32_t)(head ? 1 : 0) + (uint32_t)(t_hi - f_hi);
+    if (head) fixes_.push_back(std::make_pair((int32_t)ra, slot));
+    for (int64_t i = 0; i < t_hi - f_hi; i++) fixes_.push_back(std::make_pair((int32_t)(own_hi + i), slot + (head ? 1u : 0u) + (uint32_t)i));
+    SkEntry e;
+    const uint64_t off0 = open_[0].off;
+    e.w[0] = (uint32_t)off0; e.w[1] = (uint32_t)open_[0].val; e.w[2] = (uint32_t)open_[0].cursor_before;
+    e.w[3] = (uint32_t)(int32_t)wrow_; e.w[4] = (uint32_t)L_.sk_uoffs.size(); e.w[5] = slot;
+    e.w[6] = (uint32_t)(b - 1) | ((uint32_t)(ra - wrow_) << 5) | ((uint32_t)f_lo << 13) | ((uint32_t)((off0 >> 32) & 0xff) << 21) |
+             ((uint32_t)head << 29) | ((uint32_t)multib << 30);
+    e.w[7] = (uint32_t)f_hi | ((uint32_t)t_hi << 9);
+    L_.sk_chunks.push_back(e);
+    for (size_t i = 0; i < b; i++) L_.sk_uoffs.push_back((uint16_t)(open_[i].off - off0));
+    L_.sk_first_row.push_back((int32_t)wrow_);
+    L_.sk_last_row.push_back((int32_t)std::max(touch_hi, wrow_ + f_hi - 1));
+    L_.sk_cmin.push_back(cmin == INT64_MAX ? INT32_MAX : (int32_t)cmin);
+    L_.sk_cmax.push_back((int32_t)cmax);
+    prev_own_hi_ = own_hi;
+    first_ = false;
+  }
+  PartLayout &L_;
+  int64_t nrows_;
+  std::vector<SkUnit> open_;
+  std::vector<std::pair<int32_t, uint32_t>> fixes_;   // (row, scratch slot), in chunk order
+  int64_t wrow_ = 0, prev_own_hi_ = 0;
+  bool first_ = true;
+};
+
 }  // namespace
 
 std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
@@ -194,6 +297,25 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     bool first = true;
     std::string serr = choose_slice(cp, m, nid, L);
     if (!serr.empty()) return serr;
+    SkBuilder sk(L, cp.nrows);
+    if (!m.symmetric) {   // task shapes of the stream kernel (sk_unit_tasks)
+      for (size_t id = 0; id < nid; id++) {
+        IdEntry &ie = L.idtab[id];
+        const uint32_t kind = ie.kind_align & 0xff, align = (ie.kind_align >> 8) & 0xff;
+        uint32_t sl = 1;
+        if (kind <= K_HORIZ) sl = SK_RL_E;
+        else if (kind == K_BROW) { sl = std::min<uint32_t>(SK_BLK_LINES, std::max<uint32_t>(1, SK_BLK_E / align)); L.sk_rows = std::max<int>(L.sk_rows, (int)align); }
+        else if (kind == K_BCOL) {   // rows of the unit spread evenly over its tasks
+          const uint32_t tmax = std::min<uint32_t>(SK_BLK_LINES, std::max<uint32_t>(1, SK_BLK_E / align));
+          const uint32_t nt = (ie.delta + tmax - 1) / tmax;
+          sl = (ie.delta + nt - 1) / nt;
+          L.sk_rows = std::max<int>(L.sk_rows, (int)sl);
+        }
+        ie.sl = sl;
+        ie.recip = (65536 + sl - 1) / sl;
+        if (kind <= K_HORIZ || kind >= K_BROW) L.sk_kmask |= 1u << kind;
+      }
+    }
     // A partition whose chunk-kernel share is tiny (stencil matrices: a few boundary elements next to
     // millions of diagonal units) gets those elements as one-element table units instead; that saves the
     // second kernel launch.  Coordinates are collected while the share stays under the cap.
@@ -268,7 +390,21 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       // another device cannot be gathered by a local owner; the chunk kernel adds it to those rows of the
       // local y instead and the caller reduces the halo across devices.
       const bool image_local = !m.symmetric || (owner_of(cmin) >= 0 && owner_of(cmax) >= 0);
-      if (!goes_to_xdt(kind, size) || !image_local) {
+      // non-symmetric partitions: every vertical / diagonal / anti-diagonal unit is a table unit, everything else
+      // belongs to the stream kernel, which also parses the heads of the table units (they move the cursor)
+      const bool to_table = m.symmetric ? (goes_to_xdt(kind, size) && image_local) : (kind >= K_VERT && kind <= K_ADIAG);
+      if (!m.symmetric) {
+        const IdEntry &ie = L.idtab[id];
+        SkUnit su;
+        su.off = unit_off; su.end = p; su.size = size;
+        su.ntasks = sk_unit_tasks(kind, size, delta, ie.sl, ie.recip);
+        su.row = row; su.reach = span; su.cmin = cmin; su.cmax = cmax; su.val = v; su.cursor_before = cursor_before;
+        su.multi_bcol = kind == K_BCOL && su.ntasks > 1;
+        if (L.sk_uoffs.size() >= 0xfffffff0ull) return "unit-offset table too large";
+        sk.add(su);
+      }
+      if (!to_table) {
+        if (m.symmetric) {
         // chunk kernel: extend the open chunk or start a new one at this unit
         uint64_t ubytes = p - unit_off;
         const int64_t nsl = unit_slices(kind, size, delta, L.idtab[id]);
@@ -289,6 +425,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         L.chunk_last_row.back() = std::max<int32_t>(L.chunk_last_row.back(), (int32_t)(row + span));
         L.uoffs.push_back((uint16_t)(unit_off - ch_start));
         ch_elems += size; ch_units += 1; ch_slices += nsl;
+        }
         L.has_flat = true;
         L.flat_elems += size;
         if (singles_ok && image_local && singles.size() + size <= single_cap) {
@@ -338,6 +475,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     }
     close_chunk(end);
     if (v != cp.nnz) return "ctl stream covers " + std::to_string(v) + " values, expected " + std::to_string(cp.nnz);
+    if (!m.symmetric) { if (L.has_flat) sk.finish(); else sk.discard(); }
     if (L.has_flat && singles_ok && (int64_t)singles.size() == L.flat_elems) {
       // fold the few chunk-kernel elements into the table as diagonal units of one element
       KindEntry ke{K_DIAG, 1};
@@ -363,6 +501,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       L.chunks.clear();
       L.chunk_last_row.clear();
       L.uoffs.clear();
+      sk.discard();
       L.has_flat = false;
       L.flat_elems = 0;
     }

@@ -94,8 +94,60 @@ struct ChunkEntry {
   uint32_t pad;
 };
 
+// ---- stream kernel (kernel 2 of non-symmetric partitions; stream_kernel.cuh) ---------------------------------
+// The ctl stream is cut at unit boundaries into chunks of at most SK_MAX_UNITS units / SK_MAX_TASKS lane tasks /
+// SK_MAX_ELEMS non-zeros / SK_MAX_BYTES ctl bytes whose rows fit a window of SK_WROWS rows.  A warp parses one
+// unit head per lane, cuts the units into tasks (at most SK_RL_E consecutive elements of a delta / horizontal
+// unit; a column range of a block-row unit or a row range of a block-column unit with all its rows in register
+// accumulators) and walks 32 tasks at a time.  Row sums are combined across lanes with a segmented shuffle
+// reduction and collected in a per-warp shared-memory window of y rows; at the end of the chunk the warp writes
+// the rows the chunk owns with plain coalesced stores (y = alpha*sum + beta*y): no atomics, bit-reproducible.
+// Rows are owned by the chunk in which their first unit starts; what a chunk contributes to rows of other chunks
+// (a row cut by a chunk boundary, block units reaching below the next chunk's first row) goes to a scratch array
+// and is added by a small fix-up kernel in chunk order.  Long runs of empty rows are listed as gaps and cleared
+// by the same fix-up kernel.  Vertical / diagonal / anti-diagonal units live in the cross-row unit table; the
+// stream kernel only parses their heads (they move the column cursor) and gives them an empty task.
+constexpr int SK_MAX_UNITS = 32;
+constexpr int SK_MAX_TASKS = 128;
+constexpr int SK_MAX_ELEMS = 1023;
+constexpr int SK_MAX_BYTES = 4095;
+constexpr int SK_WROWS = 256;        // rows of the per-warp y window
+constexpr int SK_RL_E = 4;           // elements per task of a row-local unit
+constexpr int SK_BLK_E = 12;         // element budget of a block task
+constexpr int SK_BLK_LINES = 4;      // at most this many columns (block-row) / rows (block-column) per block task
+// 32-byte chunk entry (device layout: 2 x uint4)
+//   w0 ctl offset (low 32 bits)      w1 index of the first value (partition relative)
+//   w2 column cursor before the first unit   w3 window base row (partition relative)
+//   w4 first entry in the unit-offset table  w5 first scratch slot of the chunk's foreign rows
+//   w6 [0:5) units-1  [5:13) first unit's row - window base  [13:21) first flushed window row
+//      [21:29) ctl offset bits 32..39  [29] head row is foreign  [30] a block-column unit has several tasks
+//   w7 [0:9) end of the flushed window rows  [9:18) end of the foreign tail rows
+struct SkEntry { uint32_t w[8]; };
+struct SkGap { int64_t lo, hi; };    // partition-relative rows [lo, hi) no chunk window covers
+
+// Tasks of a unit (same arithmetic on host and device).  ie.sl = elements (row-local), columns (block-row) or
+// rows (block-column) per task, ie.recip = ceil(2^16 / sl).
+SPXB_HD inline uint32_t sk_unit_tasks(uint32_t kind, uint32_t size, uint32_t delta, uint32_t sl, uint32_t recip) {
+  if (kind <= 4u) return (size + SK_RL_E - 1) / SK_RL_E;          // K_DELTA8..K_HORIZ
+  if (kind >= 8u) return ((delta + sl - 1) * recip) >> 16;        // K_BROW, K_BCOL: delta = free dimension
+  return 1;                                                       // table units: one empty task
+}
+
 struct PartLayout {
   int64_t nrows = 0, row_start = 0, nnz = 0, ctl_size = 0;
+  // stream kernel tables (non-symmetric partitions)
+  std::vector<SkEntry> sk_chunks;
+  std::vector<uint16_t> sk_uoffs;        // offset of every unit head inside its chunk
+  std::vector<int32_t> sk_fix_rows;      // rows that receive foreign contributions ...
+  std::vector<uint32_t> sk_fix_ptr;      // ... their scratch slots sk_fix_idx[ptr[i] .. ptr[i+1]) in chunk order
+  std::vector<uint32_t> sk_fix_idx;
+  std::vector<SkGap> sk_gaps;
+  uint32_t sk_scratch = 0;               // scratch doubles
+  uint32_t sk_kmask = 0;                 // unit kinds the stream kernel meets: bit k = Kind k
+  int sk_rows = 1;                       // register accumulators a task needs (rows of a block task)
+  // host side only (slabs of the pipelined host-buffer SpMV): per chunk the window base row, the last row it
+  // touches and the columns it reads
+  std::vector<int32_t> sk_first_row, sk_last_row, sk_cmin, sk_cmax;
   uint64_t val_base = 0, ctl_base = 0;   // offsets into the device-wide arrays
   bool has_flat = false;                 // some unit is handled by the chunk kernel
   bool xd_diag1_only = true;             // every descriptor of this partition's table is a direct diagonal unit of stride 1

@@ -1,0 +1,359 @@
+// Device code of the stream kernel (kernel 2 of non-symmetric partitions): decodes the CSX ctl stream in registers
+// and multiplies every unit that is not a table unit — delta8/16/32/64 and horizontal units (delta_tmpl.c,
+// horiz_tmpl.c), block-row and block-column units (block_row_tmpl.c, block_col_tmpl.c).  gpu_layout.hpp describes
+// the chunk table it walks.  Included by engine.cu (nvcc, sm_100a); tests/emul/ compiles the same text for the host on
+// the fibre emulation of the warp intrinsics (CSXB_EMUL).
+//
+// One warp = one chunk.  (1) One unit head per lane is parsed straight from global memory (three aligned words and
+// funnel shifts give the 12 bytes behind the head; varints are decoded branch-free for up to four bytes); warp
+// prefix sums give every unit its row, its first value and its first task.  (2) Units are cut into lane tasks: up to
+// SK_RL_E consecutive elements of a delta / horizontal unit, a column range of a block-row unit or a row range of a
+// block-column unit.  32 tasks are walked at a time: a lane finds its unit with a ballot / population count, reads
+// the unit record with three shuffles, loads its deltas once (aligned words + funnel shifts) and sums them; a
+// segmented warp prefix sum over the task totals gives every task its column cursor; the lane then gathers x and
+// multiplies — a block task loads x once per column and keeps one register accumulator per block row.  (3) Tasks
+// that start in the same row sit in neighbouring lanes: a segmented shuffle reduction combines them and the last
+// lane of a run adds the sums into the warp's shared-memory window of y rows.  (4) The chunk's own rows leave the
+// window with coalesced plain stores, y = alpha*sum + beta*y; contributions to rows of other chunks go to the
+// scratch array (csx_stream_fixup_kernel adds them in chunk order).  No atomics: the result is bit-reproducible.
+//
+// The kernel is instantiated per pattern set (R = register accumulators = rows of a block task, KM = mask of unit
+// kinds): the counterpart of the reference's per-partition JIT (CsxJit.hpp:359-732), which emits one loop per unit
+// kind of the partition's id_map.
+#pragma once
+#include "chunk_kernel.cuh"
+
+constexpr uint32_t SKM_DELTA = (1u << K_DELTA8) | (1u << K_DELTA16) | (1u << K_DELTA32);
+constexpr uint32_t SKM_ROWLOCAL = SKM_DELTA | (1u << K_DELTA64) | (1u << K_HORIZ);
+constexpr uint32_t SKM_BROW = 1u << K_BROW, SKM_BCOL = 1u << K_BCOL;
+constexpr int SK_WARPS = 8;                         // warps (chunks) per CTA
+constexpr int SK_WIN = SK_WROWS + 8;                // window doubles per warp (slack for idle accumulators)
+
+// Source / target vectors of one launch.  `step` != nullptr: vectors by step parity of the multi-GPU exchange
+// (gather_kernel.cuh: XchgDev), read from the device-resident step counter so that a captured graph can be replayed.
+struct SkIO {
+  const double *x;
+  double *y;
+  const unsigned long long *step;
+  double *vec[2];
+};
+
+#ifdef CSXB_EMUL
+inline uint64_t sk_ldg64(const uint64_t *p) { return *p; }
+#endif
+
+// 32 bits at any byte address (ctl is readable CTL_PAD bytes past its end)
+__device__ __forceinline__ uint32_t sk_ld32(const uint8_t *p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
+}
+// variable-length integer (CtlUtil.hpp:110-133) at the low end of `win` (`mem` = its address), modulo 2^32;
+// `len` = bytes consumed
+__device__ __forceinline__ uint32_t sk_varint(uint64_t win, const uint8_t *mem, uint32_t &len) {
+  const uint32_t lo = (uint32_t)win;
+  const uint32_t stop = ~lo & 0x80808080u;
+  if (stop) {   // at most four bytes
+    len = (uint32_t)__ffs((int)stop) >> 3;
+    const uint32_t v = (lo & 0x7fu) | ((lo >> 1) & 0x3f80u) | ((lo >> 2) & 0x1fc000u) | ((lo >> 3) & 0xfe00000u);
+    return v & ((1u << (7 * len)) - 1u);
+  }
+  // five to ten bytes (columns from 2^28, "negative" column jumps: SURVEY App. A): walk the bytes
+  uint32_t v = 0, shift = 0;
+  len = 0;
+  for (;;) {
+    const uint32_t b = mem[len++];
+    if (shift < 32) v |= (b & 0x7fu) << shift;
+    shift += 7;
+    if (!(b & 0x80u)) break;
+  }
+  return v;
+}
+
+// Four consecutive deltas of `w` bytes starting at byte address p (low 32 bits of delta64).
+template <uint32_t KM>
+__device__ __forceinline__ void sk_deltas4(const uint8_t *p, uint32_t kind, uint32_t D[4]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(a & 3) * 8;
+  if ((KM >> K_DELTA8 & 1) && kind == K_DELTA8) {
+    const uint32_t q = __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
+    D[0] = q & 0xffu; D[1] = (q >> 8) & 0xffu; D[2] = (q >> 16) & 0xffu; D[3] = q >> 24;
+  } else if ((KM >> K_DELTA16 & 1) && kind == K_DELTA16) {
+    const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2);
+    const uint32_t q0 = __funnelshift_r(a0, a1, sh), q1 = __funnelshift_r(a1, a2, sh);
+    D[0] = q0 & 0xffffu; D[1] = q0 >> 16; D[2] = q1 & 0xffffu; D[3] = q1 >> 16;
+  } else if ((KM >> K_DELTA32 & 1) && kind == K_DELTA32) {
+    const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2), a3 = __ldg(w + 3), a4 = __ldg(w + 4);
+    D[0] = __funnelshift_r(a0, a1, sh); D[1] = __funnelshift_r(a1, a2, sh);
+    D[2] = __funnelshift_r(a2, a3, sh); D[3] = __funnelshift_r(a3, a4, sh);
+  } else if (KM >> K_DELTA64 & 1) {   // K_DELTA64: columns below 2^32, the low words suffice
+#pragma unroll
+    for (int i = 0; i < 4; i++) D[i] = sk_ld32(p + 8 * i);
+  }
+}
+
+// One chunk.  DECODE: parity aid — store the decoded (row, column) of every value instead of multiplying.
+template <int R, uint32_t KM, bool DECODE>
+__device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, double *sacc, const uint4 *sid, const int lane,
+                                         const double *__restrict__ x, double *__restrict__ y, const double alpha, const double beta,
+                                         const int overwrite, int *drows, int *dcols) {
+  const uint32_t lemask = 0xffffffffu >> (31 - lane);
+  const uint4 *q = P.sk_chunks + 2 * (size_t)ch;
+  const uint4 qa = __ldg(q), qb = __ldg(q + 1);
+  const uint32_t val_off = qa.y, cursor0 = qa.z;
+  const int wrow = (int)qa.w;
+  const uint32_t c6 = qb.z, c7 = qb.w;
+  const uint32_t nunits = (c6 & 31u) + 1u, row0rel = (c6 >> 5) & 0xffu, f_lo = (c6 >> 13) & 0xffu;
+  const bool headf = (c6 >> 29) & 1u, multib = (c6 >> 30) & 1u;
+  const uint32_t f_hi = c7 & 0x1ffu, t_hi = (c7 >> 9) & 0x1ffu;
+  const uint8_t *cbase = P.ctl + ((uint64_t)qa.x | ((uint64_t)((c6 >> 21) & 0xffu) << 32));
+  const double *__restrict__ values = P.values + P.val_base + val_off;
+  if (!DECODE) {   // the window rows this chunk adds into start from zero
+    for (uint32_t i = lane; i < max(f_hi, t_hi); i += 32) sacc[i] = 0.0;
+    __syncwarp();
+  }
+
+  // ---- 1. unit heads, one per lane ----------------------------------------------------------------------------
+  uint32_t size = 0, nt = 0, rowinc = 0, ucol = 0, body = 0, id = 0;
+  bool ureset = false, rjmp = false;
+  if ((uint32_t)lane < nunits) {
+    const uint32_t off = __ldg(P.sk_uoffs + qb.x + lane);
+    const uint8_t *hp = cbase + off;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(hp);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+    const uint32_t flags = b0 & 0xffu;
+    size = (b0 >> 8) & 0xffu;
+    id = flags & 0x3fu;
+    uint64_t win = (uint64_t)__funnelshift_r(b0, b1, 16) | ((uint64_t)__funnelshift_r(b1, b2, 16) << 32);   // bytes 2..9
+    uint32_t hl = 2;
+    const bool nr = (flags & 0x80u) != 0;
+    if (nr) {   // csx_spmv_tmpl.c:86-91; the first unit's row comes from the chunk entry
+      uint32_t jmp = 1;
+      if (flags & 0x40u) {
+        uint32_t len;
+        jmp = sk_varint(win, hp + hl, len);
+        hl += len;
+        win = len >= 8 ? 0 : win >> (8 * len);
+        rjmp = true;
+      }
+      if (lane != 0) rowinc = jmp;
+    }
+    if (P.full_colind) { ucol = hl == 2 ? (uint32_t)win : sk_ld32(hp + hl); hl += 4; }
+    else {
+      uint32_t len;
+      ucol = hl <= 6 ? sk_varint(win, hp + hl, len) : sk_varint(sk_ld32(hp + hl) | ((uint64_t)sk_ld32(hp + hl + 4) << 32), hp + hl, len);
+      hl += len;
+    }
+    ureset = lane == 0 || nr || P.full_colind;   // the column cursor restarts at this unit
+    if (lane == 0 && !P.full_colind) ucol += cursor0;
+    body = off + hl;
+    const uint4 ie = sid[id];
+    nt = sk_unit_tasks(ie.x & 0xffu, size, ie.y, ie.z, ie.w);
+  }
+  // inclusive scans over the units: elements | tasks << 16, rows
+  uint32_t et = size | (nt << 16), rs = rowinc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t a = __shfl_up_sync(FULL, et, o);
+    if (lane >= o) et += a;
+  }
+  if (__any_sync(FULL, rjmp)) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t b = __shfl_up_sync(FULL, rs, o);
+      if (lane >= o) rs += b;
+    }
+  } else {
+    rs = (uint32_t)__popc(__ballot_sync(FULL, rowinc != 0) & lemask);
+  }
+  const uint32_t ntasks = __shfl_sync(FULL, et, 31) >> 16;
+  const uint32_t ts = (et >> 16) - nt, es = (et & 0xffffu) - size;
+  // unit record: A = first task | first element << 8 | size << 18 | id << 26, B = row | body offset << 8 | restart << 21, C = ucol
+  const uint32_t recA = ts | (es << 8) | (size << 18) | (id << 26);
+  const uint32_t recB = (row0rel + rs) | (body << 8) | ((uint32_t)ureset << 21);
+  const bool single = ntasks == nunits;   // every unit is one task: lane = unit
+
+  // ---- 2. tasks, 32 at a time -----------------------------------------------------------------------------------
+  uint32_t carry = 0;   // column cursor behind the last task of the previous round
+  for (uint32_t t0 = 0; t0 < ntasks; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    const bool valid = t < ntasks;
+    uint32_t A = recA, B = recB, C = ucol;
+    if (!single) {
+      const uint32_t rel = ts - t0;
+      const uint32_t bit = ((uint32_t)lane < nunits && rel < 32u) ? 1u << rel : 0u;
+      const uint32_t M = __reduce_or_sync(FULL, bit);
+      const uint32_t nb = (uint32_t)__popc(__ballot_sync(FULL, (uint32_t)lane < nunits && ts < t0));
+      const int U = (int)(nb + (uint32_t)__popc(M & lemask)) - 1;
+      A = __shfl_sync(FULL, recA, U); B = __shfl_sync(FULL, recB, U); C = __shfl_sync(FULL, ucol, U);
+    }
+    const uint32_t k = t - (A & 0xffu), ues = (A >> 8) & 0x3ffu, usize = (A >> 18) & 0xffu;
+    const uint4 ie = sid[A >> 26];
+    const uint32_t kind = ie.x & 0xffu, align = (ie.x >> 8) & 0xffu, delta = ie.y, tpar = ie.z;
+    const uint32_t rowrel = B & 0xffu;
+    const bool first = k == 0;
+    // geometry of the task: n elements; row-local: column steps D[]; blocks: nl lines of the free dimension from l0
+    uint32_t n = 0, adv = 0, key = 0x1000u + lane, vi = ues, l0 = 0, nl = 0;
+    uint32_t D[SK_RL_E] = {0, 0, 0, 0};
+    if (valid) {
+      key = rowrel;
+      if (kind <= K_HORIZ) {
+        const uint32_t j0 = k * SK_RL_E;
+        n = min((uint32_t)SK_RL_E, usize - j0);
+        vi = ues + j0;
+        if ((KM >> K_HORIZ & 1) && kind == K_HORIZ) {
+#pragma unroll
+          for (int i = 0; i < SK_RL_E; i++) D[i] = delta;
+          if (first) D[0] = C;
+        } else {   // element j of a delta unit adds body[j - 1]; the unit's first element adds ucol instead (delta_tmpl.c)
+          const uint32_t w = delta;   // bytes per delta
+          if (first) {
+            uint32_t Rw[SK_RL_E] = {0, 0, 0, 0};
+            if (usize > 1) sk_deltas4<KM>(cbase + ((B >> 8) & 0x1fffu), kind, Rw);
+            D[0] = C; D[1] = Rw[0]; D[2] = Rw[1]; D[3] = Rw[2];
+          } else {
+            sk_deltas4<KM>(cbase + ((B >> 8) & 0x1fffu) + (j0 - 1) * w, kind, D);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < SK_RL_E; i++) adv += (uint32_t)i < n ? D[i] : 0u;
+      } else if ((KM & SKM_BROW) && kind == K_BROW) {   // align rows x delta columns, values column-major; task = column range
+        l0 = k * tpar; nl = min(tpar, delta - l0);
+        n = nl * align; vi = ues + l0 * align;
+        if (first) adv = C;
+      } else if ((KM & SKM_BCOL) && kind == K_BCOL) {   // delta rows x align columns, values row-major; task = row range
+        l0 = k * tpar; nl = min(tpar, delta - l0);
+        n = nl * align; vi = ues + l0 * align;
+        key = rowrel + l0;
+        if (first) adv = C;
+      } else {   // table unit: moves the cursor to its start column
+        adv = C;
+      }
+    }
+    const bool reset = valid && first && ((B >> 21) & 1u);
+    // column cursor before every task: inclusive scan of the advances, restarted where the cursor restarts
+    uint32_t incl = adv;
+    const uint32_t rmask = __ballot_sync(FULL, reset) & lemask;   // restarts at or before this lane
+    const int rseg = 31 - __clz(rmask);                            // lane of the last restart (-1: none)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a = __shfl_up_sync(FULL, incl, o);
+      if (lane - o >= rseg && lane >= o) incl += a;
+    }
+    if (rseg < 0) incl += carry;
+    carry = __shfl_sync(FULL, incl, 31);
+    uint32_t col = incl - adv;   // cursor before this task (0 at a restart)
+
+    // ---- elements ----
+    double acc[R];
+#pragma unroll
+    for (int a = 0; a < R; a++) acc[a] = 0.0;
+    if (kind <= K_HORIZ) {
+      if (n) {
+        uint32_t cl[SK_RL_E];
+#pragma unroll
+        for (int i = 0; i < SK_RL_E; i++) { col += D[i]; cl[i] = col; }
+        if (DECODE) {
+#pragma unroll
+          for (int i = 0; i < SK_RL_E; i++)
+            if ((uint32_t)i < n) { drows[val_off + vi + i] = (int)(P.row_start + wrow + rowrel); dcols[val_off + vi + i] = (int)cl[i]; }
+        } else {
+          double v[SK_RL_E], xv[SK_RL_E];
+#pragma unroll
+          for (int i = 0; i < SK_RL_E; i++) {
+            v[i] = 0.0; xv[i] = 0.0;
+            if ((uint32_t)i < n) { v[i] = __ldg(values + vi + i); xv[i] = __ldg(x + cl[i]); }
+          }
+#pragma unroll
+          for (int i = 0; i < SK_RL_E; i++) acc[0] += v[i] * xv[i];
+        }
+      }
+    } else if ((KM & SKM_BROW) && kind == K_BROW) {
+      const uint32_t c0 = col + (first ? C : 0u) + l0;   // first column of the task
+      if (DECODE) {
+        for (uint32_t e = 0; e < n; e++) {
+          drows[val_off + vi + e] = (int)(P.row_start + wrow + rowrel + e % align);
+          dcols[val_off + vi + e] = (int)(c0 + e / align);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SK_BLK_LINES; j++) {
+          if ((uint32_t)j < nl) {
+            const double xv = __ldg(x + c0 + j);   // x once per column (block_row_tmpl.c)
+#pragma unroll
+            for (int a = 0; a < R; a++)
+              if ((uint32_t)a < align) acc[a] += __ldg(values + vi + j * align + a) * xv;
+          }
+        }
+      }
+    } else if ((KM & SKM_BCOL) && kind == K_BCOL) {
+      const uint32_t c0 = col + (first ? C : 0u);
+      if (DECODE) {
+        for (uint32_t e = 0; e < n; e++) {
+          drows[val_off + vi + e] = (int)(P.row_start + wrow + key + e / align);
+          dcols[val_off + vi + e] = (int)(c0 + e % align);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if ((uint32_t)j < align) {
+            const double xv = __ldg(x + c0 + j);   // x once per column (block_col_tmpl.c)
+#pragma unroll
+            for (int a = 0; a < R && a < SK_BLK_LINES; a++)
+              if ((uint32_t)a < nl) acc[a] += __ldg(values + vi + a * align + j) * xv;
+          }
+        }
+      }
+    }
+    if (DECODE) continue;
+
+    // ---- row sums: tasks that start in the same row are neighbours; the last lane of a run adds into the window ----
+    const uint32_t kprev = __shfl_up_sync(FULL, key, 1);
+    const uint32_t heads = __ballot_sync(FULL, lane == 0 || kprev != key);
+    const int seg = 31 - __clz(heads & lemask);
+    const bool last = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+#pragma unroll
+    for (int a = 0; a < R; a++) {
+      double s = acc[a];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double tv = __shfl_up_sync(FULL, s, o);
+        if (lane - o >= seg) s += tv;
+      }
+      bool add = last;
+      if (R > 1 && multib) {
+        // runs of different block-column tasks can end in the same row: the first lane of such a group adds the others
+        const uint32_t target = last ? key + a : 0x2000u + lane;
+        const uint32_t peers = __match_any_sync(FULL, target);
+        uint32_t others = peers & ~(1u << lane);
+        add = last && (peers & ((1u << lane) - 1u)) == 0;
+        const double s0 = s;
+        while (__any_sync(FULL, others != 0)) {
+          const int src = others ? __ffs((int)others) - 1 : lane;
+          const double ov = __shfl_sync(FULL, s0, src);
+          if (others) { s += ov; others &= others - 1; }
+        }
+      }
+      if (add) sacc[key + a] += s;
+      __syncwarp();
+    }
+  }
+  if (DECODE) return;
+
+  // ---- 3. the chunk's rows leave the window ---------------------------------------------------------------------
+  for (uint32_t i = f_lo + lane; i < f_hi; i += 32) {
+    const double v = sacc[i];
+    double *yp = y + (P.row_start + wrow + i);
+    *yp = overwrite ? alpha * v : alpha * v + beta * *yp;
+  }
+  if (headf | (t_hi > f_hi)) {   // rows of other chunks: to the scratch array
+    double *sc = P.sk_scratch + qb.y;
+    if (headf && lane == 0) sc[0] = sacc[row0rel];
+    for (uint32_t i = f_hi + lane; i < t_hi; i += 32) sc[(headf ? 1u : 0u) + (i - f_hi)] = sacc[i];
+  }
+  __syncwarp();
+}

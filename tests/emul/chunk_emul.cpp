@@ -13,6 +13,7 @@
 #define CSXB_EMUL 1
 #include "../../sparsex_b200/csrc/csx_host.hpp"
 #include <type_traits>
+#include "../../sparsex_b200/csrc/stream_kernel.cuh"
 #include "../../sparsex_b200/csrc/gather_kernel.cuh"
 
 namespace {
@@ -60,6 +61,7 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
   int64_t nchunks = 0, nunits = 0, nxd = 0;
   static ChunkSmem smem;
   std::vector<PartDev> pdev;
+  std::vector<std::vector<double>> scratch(L.parts.size());
   for (size_t i = 0; i < L.parts.size(); i++) {
     const PartLayout &pl = L.parts[i];
     const CsxPartition &hp = M.parts[i];
@@ -90,6 +92,16 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     P.dvalues = hp.dvalues.data();
     P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
     P.nchunks = (uint32_t)pl.chunks.size();
+    P.sk_chunks = reinterpret_cast<const uint4 *>(pl.sk_chunks.data());
+    P.sk_uoffs = pl.sk_uoffs.data();
+    scratch[i].assign(pl.sk_scratch + 2, std::nan(""));
+    P.sk_scratch = scratch[i].data();
+    P.sk_fix_rows = pl.sk_fix_rows.data(); P.sk_fix_ptr = pl.sk_fix_ptr.data(); P.sk_fix_idx = pl.sk_fix_idx.data();
+    P.sk_gaps = reinterpret_cast<const long long *>(pl.sk_gaps.data());
+    P.sk_c0 = 0; P.sk_c1 = (uint32_t)pl.sk_chunks.size();
+    nchunks += (int64_t)pl.sk_chunks.size();
+    nunits += (int64_t)pl.sk_uoffs.size();
+    if (stats) { stats[4] += (int64_t)pl.sk_fix_idx.size(); stats[5] += (int64_t)pl.sk_gaps.size(); stats[6] = pl.sk_rows; stats[7] = pl.sk_kmask; }
     P.full_colind = L.full_colind;
     P.rpt = pl.rpt;
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
@@ -98,30 +110,77 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     nunits += (int64_t)pl.uoffs.size();
     if (stats) stats[3] = pl.slice;
   }
+  // non-symmetric partitions with stream units: stream kernel (writes y), fix-up, then kernel 1 adds (engine.cu: run_partition)
+  static double sacc[SK_WIN];
+  static uint4 sid[64];
+  std::vector<bool> streamed(L.parts.size(), false);
+  for (size_t i = 0; i < L.parts.size() && !M.symmetric; i++) {
+    const PartLayout &pl = L.parts[i];
+    const PartDev &P = pdev[i];
+    if (pl.sk_chunks.empty()) continue;
+    streamed[i] = true;
+    for (int k = 0; k < 64; k++) sid[k] = make_uint4(P.idtab[k].kind_align, P.idtab[k].delta, P.idtab[k].sl, P.idtab[k].recip);
+    for (uint32_t ch = 0; ch < P.sk_c1; ch++) {
+      for (int k = 0; k < SK_WIN; k++) sacc[k] = std::nan("");   // the kernel must clear what it uses
+      warp_emul::run_warp([&](int lane) {
+        sk_chunk<8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, true>(P, ch, sacc, sid, lane, nullptr, nullptr, 0.0, 0.0, 1, dec_rows + P.val_base, dec_cols + P.val_base);
+      });
+      const uint32_t km = pl.sk_kmask;
+      const int r = pl.sk_rows;
+      bool done = false;
+#define SK_TRY(RR, KK)                                                                                              \
+  if (!done && r <= RR && (km & ~(uint32_t)(KK)) == 0) {                                                            \
+    done = true;                                                                                                    \
+    warp_emul::run_warp([&](int lane) { sk_chunk<RR, (KK), false>(P, ch, sacc, sid, lane, x, y, alpha, 0.0, 1, nullptr, nullptr); }); \
+  }
+      SK_TRY(1, SKM_DELTA)
+      SK_TRY(1, SKM_ROWLOCAL)
+      SK_TRY(2, SKM_ROWLOCAL | SKM_BCOL)
+      SK_TRY(3, SKM_ROWLOCAL | SKM_BCOL)
+      SK_TRY(4, SKM_ROWLOCAL | SKM_BCOL)
+      SK_TRY(2, SKM_ROWLOCAL | SKM_BROW)
+      SK_TRY(3, SKM_ROWLOCAL | SKM_BROW)
+      SK_TRY(4, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
+      SK_TRY(8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
+#undef SK_TRY
+      if (!done) { put_err(err, errlen, "no stream kernel instantiation"); return -1; }
+    }
+    // csx_stream_fixup_kernel
+    for (size_t f = 0; f < pl.sk_fix_rows.size(); f++) {
+      double sum = 0.0;
+      for (uint32_t j = pl.sk_fix_ptr[f]; j < pl.sk_fix_ptr[f + 1]; j++) sum += scratch[i][pl.sk_fix_idx[j]];
+      y[pl.row_start + pl.sk_fix_rows[f]] += alpha * sum;
+    }
+    for (const SkGap &g : pl.sk_gaps)
+      for (int64_t rr = g.lo; rr < g.hi; rr++) y[pl.row_start + rr] = 0.0;
+  }
   // kernel 1 of every partition first (it initialises y; under CSX-Sym chunks add into rows of other partitions),
   // with the instantiation launch_gather would pick (the PTX variant of the diagonal kernel is device-only)
   for (size_t i = 0; i < L.parts.size(); i++) {
     const PartLayout &pl = L.parts[i];
     const PartDev &P = pdev[i];
     const bool xd = !pl.xdesc.empty(), diag1 = !M.symmetric && pl.xd_diag1_only && xd;
+    if (streamed[i] && !xd) continue;
+    const double beta = streamed[i] ? 1.0 : 0.0;
+    const int ow = streamed[i] ? 0 : 1;
     for (int64_t t = 0; t < pl.ntiles; t++)
       for (int w = 0; w < CTA_THREADS / 32; w++) {
         warp_emul::warp_in_cta() = w;
         warp_emul::run_warp([&](int) {
           const NoXchg nx;
           if (M.symmetric) {
-            if (pl.rpt == 4) { if (xd) spmv_tile<true, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
-                               else spmv_tile<false, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0); }
-            else { if (xd) spmv_tile<true, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
-                   else spmv_tile<false, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0); }
+            if (pl.rpt == 4) { if (xd) spmv_tile<true, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+                               else spmv_tile<false, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0); }
+            else { if (xd) spmv_tile<true, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+                   else spmv_tile<false, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0); }
           } else if (pl.rpt == 4) {
-            if (diag1) spmv_tile<true, false, 4, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
-            else if (xd) spmv_tile<true, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
-            else spmv_tile<false, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+            if (diag1) spmv_tile<true, false, 4, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else if (xd) spmv_tile<true, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else spmv_tile<false, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
           } else {
-            if (diag1) spmv_tile<true, false, 1, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
-            else if (xd) spmv_tile<true, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
-            else spmv_tile<false, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, 0.0, 1, t, t, nx, 0);
+            if (diag1) spmv_tile<true, false, 1, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else if (xd) spmv_tile<true, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else spmv_tile<false, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
           }
         });
       }

@@ -21,6 +21,7 @@
 struct uint4 { uint32_t x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 using std::min;
+using std::max;
 using std::fma;
 
 namespace warp_emul {
@@ -126,6 +127,19 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   for (int i = 0; i < 32; i++) r = std::max(r, (unsigned)s[i]);
   return r;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+  const uint64_t *s = warp_emul::exchange(v);
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r |= (unsigned)s[i];
+  return r;
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+  const uint64_t *s = warp_emul::exchange(v);
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r |= (unsigned)((unsigned)s[i] == v) << i;
+  return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline void __syncwarp() { warp_emul::exchange(0); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
