@@ -207,7 +207,7 @@ __device__ __forceinline__ void sk_vectors(const SkIO &io, const double *&x, dou
     x = io.vec[k & 1]; y = io.vec[(k & 1) ^ 1];
   }
 }
-template <int R, uint32_t KM>
+template <int R, uint32_t KM, int BC, int BRC>
 __global__ void __launch_bounds__(SK_WARPS * 32, 4) csx_stream_kernel(const __grid_constant__ PartDev P, const __grid_constant__ SkIO io,
                                                                      double alpha, double beta, int overwrite) {
   __shared__ double sacc[SK_WARPS][SK_WIN];
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32, 4) csx_stream_kernel(const __gr
   if (ch >= P.sk_c1) return;
   const double *x; double *y;
   sk_vectors(io, x, y);
-  sk_chunk<R, KM, false>(P, ch, sacc[warp], sid, lane, x, y, alpha, beta, overwrite, nullptr, nullptr);
+  sk_chunk<R, KM, BC, BRC, false>(P, ch, sacc[warp], sid, lane, x, y, alpha, beta, overwrite, nullptr, nullptr);
 }
 __global__ void __launch_bounds__(SK_WARPS * 32) csx_stream_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
   __shared__ double sacc[SK_WARPS][SK_WIN];
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32) csx_stream_decode_kernel(const 
   __syncthreads();
   const uint32_t ch = P.sk_c0 + blockIdx.x * SK_WARPS + warp;
   if (ch >= P.sk_c1) return;
-  sk_chunk<8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, true>(P, ch, sacc[warp], sid, lane, nullptr, nullptr, 0.0, 0.0, 1, rows + P.val_base,
-                                                         cols + P.val_base);
+  sk_chunk<8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, 0, 0, true>(P, ch, sacc[warp], sid, lane, nullptr, nullptr, 0.0, 0.0, 1,
+                                                               rows + P.val_base, cols + P.val_base);
 }
 // After the stream kernel: adds what chunks contributed to rows of other chunks (in chunk order: deterministic) and
 // clears the rows no chunk window covers (long runs of empty rows), clipped to [clip_lo, clip_hi).
@@ -251,9 +251,9 @@ __global__ void __launch_bounds__(256) csx_stream_fixup_kernel(const __grid_cons
     for (uint32_t j = P.sk_fix_ptr[i]; j < P.sk_fix_ptr[i + 1]; j++) s += P.sk_scratch[P.sk_fix_idx[j]];
     y[P.row_start + P.sk_fix_rows[i]] += alpha * s;
   }
-  for (uint32_t g = P.sk_g0; g < P.sk_g1; g++) {
+  for (uint32_t g = P.sk_g0 + blockIdx.x; g < P.sk_g1; g += gridDim.x) {   // one CTA per gap (most gaps are short)
     const long long lo = max(P.sk_gaps[2 * g], clip_lo), hi = min(P.sk_gaps[2 * g + 1], clip_hi);
-    for (long long r = lo + tid; r < hi; r += nth) {
+    for (long long r = lo + threadIdx.x; r < hi; r += blockDim.x) {
       double *yp = y + P.row_start + r;
       *yp = overwrite ? 0.0 : beta * *yp;
     }
@@ -684,22 +684,12 @@ static int launch_stream(const PartDev &P0, const PartLayout &pl, uint32_t c0, u
   PartDev P = P0;
   P.sk_c0 = c0; P.sk_c1 = c1;
   const unsigned grid = (unsigned)((c1 - c0 + SK_WARPS - 1) / SK_WARPS);
-  const uint32_t km = pl.sk_kmask;
-  const int r = pl.sk_rows;
-#define SK_TRY(RR, KK)                                                                                       \
-  if (r <= RR && (km & ~(uint32_t)(KK)) == 0) {                                                              \
-    csx_stream_kernel<RR, (KK)><<<grid, SK_WARPS * 32, 0, s>>>(P, io, alpha, beta, overwrite);               \
-    return 0;                                                                                                \
+#define SK_TRY(RR, KK, BCC, BRR)                                                                                         \
+  if (sk_instance_serves(RR, (KK), BCC, BRR, pl.sk_kmask, pl.sk_rows, pl.sk_bc, pl.sk_brc)) {                            \
+    csx_stream_kernel<RR, (KK), BCC, BRR><<<grid, SK_WARPS * 32, 0, s>>>(P, io, alpha, beta, overwrite);                 \
+    return 0;                                                                                                            \
   }
-  SK_TRY(1, SKM_DELTA)
-  SK_TRY(1, SKM_ROWLOCAL)
-  SK_TRY(2, SKM_ROWLOCAL | SKM_BCOL)
-  SK_TRY(3, SKM_ROWLOCAL | SKM_BCOL)
-  SK_TRY(4, SKM_ROWLOCAL | SKM_BCOL)
-  SK_TRY(2, SKM_ROWLOCAL | SKM_BROW)
-  SK_TRY(3, SKM_ROWLOCAL | SKM_BROW)
-  SK_TRY(4, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
-  SK_TRY(8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
+  SK_INSTANCES(SK_TRY)
 #undef SK_TRY
   return -1;
 }
@@ -709,9 +699,8 @@ static void launch_fixup(const PartDev &P0, uint32_t f0, uint32_t f1, uint32_t g
   if (f1 <= f0 && g1 <= g0) return;
   PartDev P = P0;
   P.sk_f0 = f0; P.sk_f1 = f1; P.sk_g0 = g0; P.sk_g1 = g1;
-  int64_t work = (int64_t)(f1 - f0);
-  if (g1 > g0) work = std::max<int64_t>(work, 148 * 4 * 256);
-  const unsigned grid = (unsigned)std::min<int64_t>(148 * 4, (work + 255) / 256);
+  const int64_t ctas = std::max<int64_t>(((int64_t)(f1 - f0) + 255) / 256, (int64_t)(g1 - g0));
+  const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, ctas);
   csx_stream_fixup_kernel<<<grid, 256, 0, s>>>(P, io, alpha, beta, overwrite, (long long)r0, (long long)r1);
 }
 // One partition of a non-symmetric matrix, whole: stream kernel (writes y), fix-up, then the gather over the table,

@@ -148,7 +148,10 @@ class SkBuilder {
  public:
   SkBuilder(PartLayout &L, int64_t nrows) : L_(L), nrows_(nrows) {}
   void add(const SkUnit &u) {
-    while (!open_.empty() && !fits(u)) split(u);
+    while (!open_.empty() && !fits(u)) {
+      std::vector<SkUnit> rest = split(u);   // units behind the cut: their rounds change, so they are added again
+      for (const SkUnit &w : rest) add(w);
+    }
     if (open_.empty()) wrow_ = (first_ && u.row + u.reach <= 64) ? 0 : u.row;
     open_.push_back(u);
   }
@@ -172,24 +175,27 @@ class SkBuilder {
 
  private:
   bool fits(const SkUnit &u) const {
-    uint32_t tasks = u.ntasks, elems = u.size;
-    for (const SkUnit &o : open_) { tasks += o.ntasks; elems += o.size; }
-    return open_.size() + 1 <= (size_t)SK_MAX_UNITS && tasks <= (uint32_t)SK_MAX_TASKS && elems <= (uint32_t)SK_MAX_ELEMS &&
+    const size_t n = open_.size();
+    if (n == (size_t)SK_MAX_UNITS) return false;
+    uint32_t tasks = u.ntasks, elems = u.size;   // of the round the unit would join
+    for (size_t i = n / SK_ROUND_UNITS * SK_ROUND_UNITS; i < n; i++) { tasks += open_[i].ntasks; elems += open_[i].size; }
+    return tasks <= (uint32_t)SK_MAX_TASKS && elems <= (uint32_t)SK_MAX_ELEMS &&
            u.end - open_.front().off <= (uint64_t)SK_MAX_BYTES && u.row + u.reach - wrow_ <= SK_WROWS - 1 &&
            u.row - wrow_ <= SK_WROWS - 2;
   }
   // The open chunk cannot take `next`: close it, preferably at the start of its last row when `next` continues
   // that row and the cut keeps the chunk at least three quarters full (a chunk that ends with its row needs no
-  // fix-up), and keep the units behind the cut open.
-  void split(const SkUnit &next) {
+  // fix-up).  Returns the units behind the cut.
+  std::vector<SkUnit> split(const SkUnit &next) {
     size_t b = open_.size();
     if (next.row == open_.back().row) {
       for (size_t i = open_.size() - 1; i > 0; i--)
         if (open_[i].row != open_[i - 1].row) { if (4 * i >= 3 * open_.size()) b = i; break; }
     }
     close(b, b < open_.size() ? open_[b].row : next.row, true);
-    open_.erase(open_.begin(), open_.begin() + (long)b);
-    if (!open_.empty()) wrow_ = open_.front().row;
+    std::vector<SkUnit> rest(open_.begin() + (long)b, open_.end());
+    open_.clear();
+    return rest;
   }
   void close(size_t b, int64_t next_row, bool has_next) {
     const int64_t ra = open_[0].row, rl = open_[b - 1].row;
@@ -215,8 +221,8 @@ class SkBuilder {
     const uint64_t off0 = open_[0].off;
     e.w[0] = (uint32_t)off0; e.w[1] = (uint32_t)open_[0].val; e.w[2] = (uint32_t)open_[0].cursor_before;
     e.w[3] = (uint32_t)(int32_t)wrow_; e.w[4] = (uint32_t)L_.sk_uoffs.size(); e.w[5] = slot;
-    e.w[6] = (uint32_t)(b - 1) | ((uint32_t)(ra - wrow_) << 5) | ((uint32_t)f_lo << 13) | ((uint32_t)((off0 >> 32) & 0xff) << 21) |
-             ((uint32_t)head << 29) | ((uint32_t)multib << 30);
+    e.w[6] = (uint32_t)(b - 1) | ((uint32_t)(ra - wrow_) << 8) | ((uint32_t)f_lo << 16) | ((uint32_t)((off0 >> 32) & 0x3f) << 24) |
+             ((uint32_t)head << 30) | ((uint32_t)multib << 31);
     e.w[7] = (uint32_t)f_hi | ((uint32_t)t_hi << 9);
     L_.sk_chunks.push_back(e);
     for (size_t i = 0; i < b; i++) L_.sk_uoffs.push_back((uint16_t)(open_[i].off - off0));
@@ -315,6 +321,20 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         ie.recip = (65536 + sl - 1) / sl;
         if (kind <= K_HORIZ || kind >= K_BROW) L.sk_kmask |= 1u << kind;
       }
+      // block tasks of one compile-time shape (the kernel is instantiated for the common ones)
+      int bc = -1, brc = -1;
+      for (size_t id = 0; id < nid; id++) {
+        const IdEntry &ie = L.idtab[id];
+        const uint32_t kind = ie.kind_align & 0xff, align = (ie.kind_align >> 8) & 0xff;
+        if (kind == K_BCOL) {
+          const bool full = (int)ie.sl == L.sk_rows && ie.delta % ie.sl == 0;
+          bc = (full && (bc == -1 || bc == (int)align)) ? (int)align : 0;
+        } else if (kind == K_BROW) {
+          const bool full = (int)align == L.sk_rows && ie.delta % ie.sl == 0;
+          brc = (full && (brc == -1 || brc == (int)ie.sl)) ? (int)ie.sl : 0;
+        }
+      }
+      L.sk_bc = std::max(bc, 0); L.sk_brc = std::max(brc, 0);
     }
     // A partition whose chunk-kernel share is tiny (stencil matrices: a few boundary elements next to
     // millions of diagonal units) gets those elements as one-element table units instead; that saves the

@@ -95,8 +95,9 @@ struct ChunkEntry {
 };
 
 // ---- stream kernel (kernel 2 of non-symmetric partitions; stream_kernel.cuh) ---------------------------------
-// The ctl stream is cut at unit boundaries into chunks of at most SK_MAX_UNITS units / SK_MAX_TASKS lane tasks /
-// SK_MAX_ELEMS non-zeros / SK_MAX_BYTES ctl bytes whose rows fit a window of SK_WROWS rows.  A warp parses one
+// The ctl stream is cut at unit boundaries into chunks of up to SK_MAX_ROUNDS rounds of 32 units (every round but
+// the last is full; a round holds at most SK_MAX_TASKS lane tasks and SK_MAX_ELEMS non-zeros), at most SK_MAX_BYTES
+// ctl bytes, whose rows fit a window of SK_WROWS rows.  A warp parses one
 // unit head per lane, cuts the units into tasks (at most SK_RL_E consecutive elements of a delta / horizontal
 // unit; a column range of a block-row unit or a row range of a block-column unit with all its rows in register
 // accumulators) and walks 32 tasks at a time.  Row sums are combined across lanes with a segmented shuffle
@@ -107,10 +108,12 @@ struct ChunkEntry {
 // and is added by a small fix-up kernel in chunk order.  Long runs of empty rows are listed as gaps and cleared
 // by the same fix-up kernel.  Vertical / diagonal / anti-diagonal units live in the cross-row unit table; the
 // stream kernel only parses their heads (they move the column cursor) and gives them an empty task.
-constexpr int SK_MAX_UNITS = 32;
+constexpr int SK_ROUND_UNITS = 32;
+constexpr int SK_MAX_ROUNDS = 4;
+constexpr int SK_MAX_UNITS = SK_ROUND_UNITS * SK_MAX_ROUNDS;
 constexpr int SK_MAX_TASKS = 128;
 constexpr int SK_MAX_ELEMS = 1023;
-constexpr int SK_MAX_BYTES = 4095;
+constexpr int SK_MAX_BYTES = 8191;
 constexpr int SK_WROWS = 256;        // rows of the per-warp y window
 constexpr int SK_RL_E = 4;           // elements per task of a row-local unit
 constexpr int SK_BLK_E = 12;         // element budget of a block task
@@ -119,8 +122,8 @@ constexpr int SK_BLK_LINES = 4;      // at most this many columns (block-row) / 
 //   w0 ctl offset (low 32 bits)      w1 index of the first value (partition relative)
 //   w2 column cursor before the first unit   w3 window base row (partition relative)
 //   w4 first entry in the unit-offset table  w5 first scratch slot of the chunk's foreign rows
-//   w6 [0:5) units-1  [5:13) first unit's row - window base  [13:21) first flushed window row
-//      [21:29) ctl offset bits 32..39  [29] head row is foreign  [30] a block-column unit has several tasks
+//   w6 [0:8) units-1  [8:16) first unit's row - window base  [16:24) first flushed window row
+//      [24:30) ctl offset bits 32..37  [30] head row is foreign  [31] a block-column unit has several tasks
 //   w7 [0:9) end of the flushed window rows  [9:18) end of the foreign tail rows
 struct SkEntry { uint32_t w[8]; };
 struct SkGap { int64_t lo, hi; };    // partition-relative rows [lo, hi) no chunk window covers
@@ -145,6 +148,8 @@ struct PartLayout {
   uint32_t sk_scratch = 0;               // scratch doubles
   uint32_t sk_kmask = 0;                 // unit kinds the stream kernel meets: bit k = Kind k
   int sk_rows = 1;                       // register accumulators a task needs (rows of a block task)
+  int sk_bc = 0;                         // > 0: every block-column task is exactly sk_rows rows x sk_bc columns
+  int sk_brc = 0;                        // > 0: every block-row task is exactly sk_rows rows x sk_brc columns
   // host side only (slabs of the pipelined host-buffer SpMV): per chunk the window base row, the last row it
   // touches and the columns it reads
   std::vector<int32_t> sk_first_row, sk_last_row, sk_cmin, sk_cmax;

@@ -38,10 +38,6 @@ struct SkIO {
   double *vec[2];
 };
 
-#ifdef CSXB_EMUL
-inline uint64_t sk_ldg64(const uint64_t *p) { return *p; }
-#endif
-
 // 32 bits at any byte address (ctl is readable CTL_PAD bytes past its end)
 __device__ __forceinline__ uint32_t sk_ld32(const uint8_t *p) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -93,262 +89,366 @@ __device__ __forceinline__ void sk_deltas4(const uint8_t *p, uint32_t kind, uint
   }
 }
 
-// One chunk.  DECODE: parity aid — store the decoded (row, column) of every value instead of multiplying.
-template <int R, uint32_t KM, bool DECODE>
-__device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, double *sacc, const uint4 *sid, const int lane,
-                                         const double *__restrict__ x, double *__restrict__ y, const double alpha, const double beta,
-                                         const int overwrite, int *drows, int *dcols) {
-  const uint32_t lemask = 0xffffffffu >> (31 - lane);
-  const uint4 *q = P.sk_chunks + 2 * (size_t)ch;
-  const uint4 qa = __ldg(q), qb = __ldg(q + 1);
-  const uint32_t val_off = qa.y, cursor0 = qa.z;
-  const int wrow = (int)qa.w;
-  const uint32_t c6 = qb.z, c7 = qb.w;
-  const uint32_t nunits = (c6 & 31u) + 1u, row0rel = (c6 >> 5) & 0xffu, f_lo = (c6 >> 13) & 0xffu;
-  const bool headf = (c6 >> 29) & 1u, multib = (c6 >> 30) & 1u;
-  const uint32_t f_hi = c7 & 0x1ffu, t_hi = (c7 >> 9) & 0x1ffu;
-  const uint8_t *cbase = P.ctl + ((uint64_t)qa.x | ((uint64_t)((c6 >> 21) & 0xffu) << 32));
-  const double *__restrict__ values = P.values + P.val_base + val_off;
-  if (!DECODE) {   // the window rows this chunk adds into start from zero
-    for (uint32_t i = lane; i < max(f_hi, t_hi); i += 32) sacc[i] = 0.0;
-    __syncwarp();
-  }
+// Instantiations of the kernel, first match wins: X(R, KM, BC, BRC).  The shaped ones (BC / BRC > 0) need the
+// partition's block tasks to have exactly that shape (PartLayout::sk_bc / sk_brc); the generic ones take any
+// partition whose kinds are in KM and whose block tasks have at most R rows.
+#define SK_INSTANCES(X)                         \
+  X(2, SKM_ROWLOCAL | SKM_BCOL, 2, 0)           \
+  X(3, SKM_ROWLOCAL | SKM_BCOL, 3, 0)           \
+  X(4, SKM_ROWLOCAL | SKM_BCOL, 2, 0)           \
+  X(2, SKM_ROWLOCAL | SKM_BROW, 0, 4)           \
+  X(3, SKM_ROWLOCAL | SKM_BROW, 0, 4)           \
+  X(1, SKM_DELTA, 0, 0)                         \
+  X(1, SKM_ROWLOCAL, 0, 0)                      \
+  X(2, SKM_ROWLOCAL | SKM_BCOL, 0, 0)           \
+  X(4, SKM_ROWLOCAL | SKM_BCOL, 0, 0)           \
+  X(4, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, 0, 0) \
+  X(8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, 0, 0)
+// does instance (RR, KK, BCC, BRR) serve a partition with kinds km, r rows per block task and shapes bc / brc?
+inline bool sk_instance_serves(int RR, uint32_t KK, int BCC, int BRR, uint32_t km, int r, int bc, int brc) {
+  if (km & ~KK) return false;
+  if (BCC == 0 && BRR == 0) return r <= RR;
+  return r == RR && (!(KK & SKM_BCOL) || bc == BCC) && (!(KK & SKM_BROW) || brc == BRR);
+}
 
-  // ---- 1. unit heads, one per lane ----------------------------------------------------------------------------
-  uint32_t size = 0, nt = 0, rowinc = 0, ucol = 0, body = 0, id = 0;
-  bool ureset = false, rjmp = false;
-  if ((uint32_t)lane < nunits) {
-    const uint32_t off = __ldg(P.sk_uoffs + qb.x + lane);
-    const uint8_t *hp = cbase + off;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(hp);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-    const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
-    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
-    const uint32_t flags = b0 & 0xffu;
-    size = (b0 >> 8) & 0xffu;
-    id = flags & 0x3fu;
-    uint64_t win = (uint64_t)__funnelshift_r(b0, b1, 16) | ((uint64_t)__funnelshift_r(b1, b2, 16) << 32);   // bytes 2..9
-    uint32_t hl = 2;
-    const bool nr = (flags & 0x80u) != 0;
-    if (nr) {   // csx_spmv_tmpl.c:86-91; the first unit's row comes from the chunk entry
-      uint32_t jmp = 1;
-      if (flags & 0x40u) {
-        uint32_t len;
-        jmp = sk_varint(win, hp + hl, len);
-        hl += len;
-        win = len >= 8 ? 0 : win >> (8 * len);
-        rjmp = true;
-      }
-      if (lane != 0) rowinc = jmp;
-    }
-    if (P.full_colind) { ucol = hl == 2 ? (uint32_t)win : sk_ld32(hp + hl); hl += 4; }
-    else {
-      uint32_t len;
-      ucol = hl <= 6 ? sk_varint(win, hp + hl, len) : sk_varint(sk_ld32(hp + hl) | ((uint64_t)sk_ld32(hp + hl + 4) << 32), hp + hl, len);
-      hl += len;
-    }
-    ureset = lane == 0 || nr || P.full_colind;   // the column cursor restarts at this unit
-    if (lane == 0 && !P.full_colind) ucol += cursor0;
-    body = off + hl;
-    const uint4 ie = sid[id];
-    nt = sk_unit_tasks(ie.x & 0xffu, size, ie.y, ie.z, ie.w);
-  }
-  // inclusive scans over the units: elements | tasks << 16, rows
-  uint32_t et = size | (nt << 16), rs = rowinc;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t a = __shfl_up_sync(FULL, et, o);
-    if (lane >= o) et += a;
-  }
-  if (__any_sync(FULL, rjmp)) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t b = __shfl_up_sync(FULL, rs, o);
-      if (lane >= o) rs += b;
-    }
-  } else {
-    rs = (uint32_t)__popc(__ballot_sync(FULL, rowinc != 0) & lemask);
-  }
-  const uint32_t ntasks = __shfl_sync(FULL, et, 31) >> 16;
-  const uint32_t ts = (et >> 16) - nt, es = (et & 0xffffu) - size;
-  // unit record: A = first task | first element << 8 | size << 18 | id << 26, B = row | body offset << 8 | restart << 21, C = ucol
-  const uint32_t recA = ts | (es << 8) | (size << 18) | (id << 26);
-  const uint32_t recB = (row0rel + rs) | (body << 8) | ((uint32_t)ureset << 21);
-  const bool single = ntasks == nunits;   // every unit is one task: lane = unit
+// Per-chunk constants of a warp.
+struct SkCtx {
+  const uint8_t *cbase;      // ctl bytes of the chunk
+  const double *values;      // values of the current round of units
+  const double *x;
+  double *sacc;              // the warp's window of y rows
+  const uint4 *sid;          // unit id -> kind | align << 8, delta, lines per task, its reciprocal (shared memory)
+  int lane;
+  uint32_t lemask;           // lanes up to and including this one
+  bool multib;               // a block-column unit of the chunk has several tasks
+  long long grow0;           // global row of the window base
+  int *drows, *dcols;        // DECODE: coordinates per value of the current round
+};
 
-  // ---- 2. tasks, 32 at a time -----------------------------------------------------------------------------------
-  uint32_t carry = 0;   // column cursor behind the last task of the previous round
-  for (uint32_t t0 = 0; t0 < ntasks; t0 += 32) {
-    const uint32_t t = t0 + lane;
-    const bool valid = t < ntasks;
-    uint32_t A = recA, B = recB, C = ucol;
-    if (!single) {
-      const uint32_t rel = ts - t0;
-      const uint32_t bit = ((uint32_t)lane < nunits && rel < 32u) ? 1u << rel : 0u;
-      const uint32_t M = __reduce_or_sync(FULL, bit);
-      const uint32_t nb = (uint32_t)__popc(__ballot_sync(FULL, (uint32_t)lane < nunits && ts < t0));
-      const int U = (int)(nb + (uint32_t)__popc(M & lemask)) - 1;
-      A = __shfl_sync(FULL, recA, U); B = __shfl_sync(FULL, recB, U); C = __shfl_sync(FULL, ucol, U);
-    }
-    const uint32_t k = t - (A & 0xffu), ues = (A >> 8) & 0x3ffu, usize = (A >> 18) & 0xffu;
-    const uint4 ie = sid[A >> 26];
-    const uint32_t kind = ie.x & 0xffu, align = (ie.x >> 8) & 0xffu, delta = ie.y, tpar = ie.z;
-    const uint32_t rowrel = B & 0xffu;
-    const bool first = k == 0;
-    // geometry of the task: n elements; row-local: column steps D[]; blocks: nl lines of the free dimension from l0
-    uint32_t n = 0, adv = 0, key = 0x1000u + lane, vi = ues, l0 = 0, nl = 0;
-    uint32_t D[SK_RL_E] = {0, 0, 0, 0};
-    if (valid) {
-      key = rowrel;
-      if (kind <= K_HORIZ) {
-        const uint32_t j0 = k * SK_RL_E;
-        n = min((uint32_t)SK_RL_E, usize - j0);
-        vi = ues + j0;
-        if ((KM >> K_HORIZ & 1) && kind == K_HORIZ) {
+// 32 lane tasks.  A, B, C = record of the task's unit (see sk_chunk), ie = its kind entry, k = index of the task inside
+// the unit.  SINGLE: every unit of the round is one task (lane = unit, k = 0).
+// BC > 0: every block-column task of the partition is exactly R rows x BC columns; BRC > 0: every block-row task is
+// exactly R rows x BRC columns (compile-time shapes: no predicates, all loads issued together).
+template <int R, uint32_t KM, int BC, int BRC, bool DECODE, bool SINGLE>
+__device__ __forceinline__ void sk_window(const SkCtx &c, const uint32_t A, const uint32_t B, const uint32_t C, const uint4 ie,
+                                          const uint32_t k, const uint32_t nvalid, uint32_t &carry) {
+  const int lane = c.lane;
+  const bool valid = (uint32_t)lane < nvalid;   // the first nvalid lanes hold tasks
+  const uint32_t ues = (A >> 8) & 0x3ffu, usize = (A >> 18) & 0xffu;
+  const uint32_t kind = ie.x & 0xffu, align = (ie.x >> 8) & 0xffu, delta = ie.y, tpar = ie.z;
+  const uint32_t rowrel = B & 0xffu;
+  const bool first = SINGLE || k == 0;
+  // geometry of the task: n elements; row-local: column steps D[]; blocks: nl lines of the free dimension from l0
+  uint32_t n = 0, adv = 0, key = 0x1000u + lane, vi = ues, l0 = 0, nl = 0;
+  uint32_t D[SK_RL_E] = {0, 0, 0, 0};
+  if (valid) {
+    key = rowrel;
+    if (kind <= K_HORIZ) {
+      const uint32_t j0 = SINGLE ? 0u : k * SK_RL_E;
+      n = SINGLE ? usize : min((uint32_t)SK_RL_E, usize - j0);
+      vi = ues + j0;
+      if ((KM >> K_HORIZ & 1) && kind == K_HORIZ) {
 #pragma unroll
-          for (int i = 0; i < SK_RL_E; i++) D[i] = delta;
-          if (first) D[0] = C;
-        } else {   // element j of a delta unit adds body[j - 1]; the unit's first element adds ucol instead (delta_tmpl.c)
-          const uint32_t w = delta;   // bytes per delta
-          if (first) {
-            uint32_t Rw[SK_RL_E] = {0, 0, 0, 0};
-            if (usize > 1) sk_deltas4<KM>(cbase + ((B >> 8) & 0x1fffu), kind, Rw);
-            D[0] = C; D[1] = Rw[0]; D[2] = Rw[1]; D[3] = Rw[2];
-          } else {
-            sk_deltas4<KM>(cbase + ((B >> 8) & 0x1fffu) + (j0 - 1) * w, kind, D);
-          }
+        for (int i = 0; i < SK_RL_E; i++) D[i] = delta;
+        if (first) D[0] = C;
+      } else {   // element j of a delta unit adds body[j - 1]; the unit's first element adds ucol instead (delta_tmpl.c)
+        const uint8_t *bp = c.cbase + ((B >> 8) & 0x1fffu);
+        if (first) {
+          uint32_t Rw[SK_RL_E] = {0, 0, 0, 0};
+          if (usize > 1) sk_deltas4<KM>(bp, kind, Rw);
+          D[0] = C; D[1] = Rw[0]; D[2] = Rw[1]; D[3] = Rw[2];
+        } else {
+          sk_deltas4<KM>(bp + (j0 - 1) * delta, kind, D);   // delta = bytes per step
         }
-#pragma unroll
-        for (int i = 0; i < SK_RL_E; i++) adv += (uint32_t)i < n ? D[i] : 0u;
-      } else if ((KM & SKM_BROW) && kind == K_BROW) {   // align rows x delta columns, values column-major; task = column range
-        l0 = k * tpar; nl = min(tpar, delta - l0);
-        n = nl * align; vi = ues + l0 * align;
-        if (first) adv = C;
-      } else if ((KM & SKM_BCOL) && kind == K_BCOL) {   // delta rows x align columns, values row-major; task = row range
-        l0 = k * tpar; nl = min(tpar, delta - l0);
-        n = nl * align; vi = ues + l0 * align;
-        key = rowrel + l0;
-        if (first) adv = C;
-      } else {   // table unit: moves the cursor to its start column
-        adv = C;
       }
+#pragma unroll
+      for (int i = 0; i < SK_RL_E; i++) adv += (uint32_t)i < n ? D[i] : 0u;
+    } else if ((KM & SKM_BROW) && kind == K_BROW) {   // align rows x delta columns, values column-major; task = column range
+      if (BRC > 0) { l0 = k * BRC; nl = BRC; n = BRC * R; vi = ues + l0 * R; }
+      else { l0 = k * tpar; nl = min(tpar, delta - l0); n = nl * align; vi = ues + l0 * align; }
+      if (first) adv = C;
+    } else if ((KM & SKM_BCOL) && kind == K_BCOL) {   // delta rows x align columns, values row-major; task = row range
+      if (BC > 0) { l0 = k * R; nl = R; n = R * BC; vi = ues + l0 * BC; }
+      else { l0 = k * tpar; nl = min(tpar, delta - l0); n = nl * align; vi = ues + l0 * align; }
+      key = rowrel + l0;
+      if (first) adv = C;
+    } else {   // table unit: moves the cursor to its start column
+      adv = C;
     }
-    const bool reset = valid && first && ((B >> 21) & 1u);
-    // column cursor before every task: inclusive scan of the advances, restarted where the cursor restarts
-    uint32_t incl = adv;
-    const uint32_t rmask = __ballot_sync(FULL, reset) & lemask;   // restarts at or before this lane
-    const int rseg = 31 - __clz(rmask);                            // lane of the last restart (-1: none)
+  }
+  const bool reset = valid && first && ((B >> 21) & 1u);
+  // column cursor before every task: inclusive scan of the advances, restarted where the cursor restarts; as many
+  // steps as the longest run of tasks behind a restart needs
+  uint32_t incl = adv;
+  {
+    const uint32_t rmask = __ballot_sync(FULL, reset) & c.lemask;   // restarts at or before this lane
+    const int rseg = 31 - __clz(rmask);                              // lane of the last restart (-1: none)
+    const uint32_t maxd = __reduce_max_sync(FULL, valid ? (uint32_t)(lane - max(rseg, 0)) : 0u);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
+      if ((uint32_t)o > maxd) break;
       const uint32_t a = __shfl_up_sync(FULL, incl, o);
       if (lane - o >= rseg && lane >= o) incl += a;
     }
     if (rseg < 0) incl += carry;
-    carry = __shfl_sync(FULL, incl, 31);
-    uint32_t col = incl - adv;   // cursor before this task (0 at a restart)
+    carry = __shfl_sync(FULL, incl, (int)nvalid - 1);   // idle lanes behind the last task did not take part
+  }
+  uint32_t col = incl - adv;   // cursor before this task (0 at a restart)
 
-    // ---- elements ----
-    double acc[R];
+  // ---- elements ----
+  double acc[R];
 #pragma unroll
-    for (int a = 0; a < R; a++) acc[a] = 0.0;
-    if (kind <= K_HORIZ) {
-      if (n) {
-        uint32_t cl[SK_RL_E];
+  for (int a = 0; a < R; a++) acc[a] = 0.0;
+  if (kind <= K_HORIZ) {
+    if (n) {
+      uint32_t cl[SK_RL_E];
 #pragma unroll
-        for (int i = 0; i < SK_RL_E; i++) { col += D[i]; cl[i] = col; }
-        if (DECODE) {
-#pragma unroll
-          for (int i = 0; i < SK_RL_E; i++)
-            if ((uint32_t)i < n) { drows[val_off + vi + i] = (int)(P.row_start + wrow + rowrel); dcols[val_off + vi + i] = (int)cl[i]; }
-        } else {
-          double v[SK_RL_E], xv[SK_RL_E];
-#pragma unroll
-          for (int i = 0; i < SK_RL_E; i++) {
-            v[i] = 0.0; xv[i] = 0.0;
-            if ((uint32_t)i < n) { v[i] = __ldg(values + vi + i); xv[i] = __ldg(x + cl[i]); }
-          }
-#pragma unroll
-          for (int i = 0; i < SK_RL_E; i++) acc[0] += v[i] * xv[i];
-        }
-      }
-    } else if ((KM & SKM_BROW) && kind == K_BROW) {
-      const uint32_t c0 = col + (first ? C : 0u) + l0;   // first column of the task
+      for (int i = 0; i < SK_RL_E; i++) { col += D[i]; cl[i] = col; }
       if (DECODE) {
-        for (uint32_t e = 0; e < n; e++) {
-          drows[val_off + vi + e] = (int)(P.row_start + wrow + rowrel + e % align);
-          dcols[val_off + vi + e] = (int)(c0 + e / align);
-        }
+#pragma unroll
+        for (int i = 0; i < SK_RL_E; i++)
+          if ((uint32_t)i < n) { c.drows[vi + i] = (int)(c.grow0 + rowrel); c.dcols[vi + i] = (int)cl[i]; }
       } else {
+        double v[SK_RL_E], xv[SK_RL_E];
 #pragma unroll
-        for (int j = 0; j < SK_BLK_LINES; j++) {
-          if ((uint32_t)j < nl) {
-            const double xv = __ldg(x + c0 + j);   // x once per column (block_row_tmpl.c)
-#pragma unroll
-            for (int a = 0; a < R; a++)
-              if ((uint32_t)a < align) acc[a] += __ldg(values + vi + j * align + a) * xv;
-          }
+        for (int i = 0; i < SK_RL_E; i++) {
+          v[i] = 0.0; xv[i] = 0.0;
+          if ((uint32_t)i < n) { v[i] = __ldg(c.values + vi + i); xv[i] = __ldg(c.x + cl[i]); }
         }
+#pragma unroll
+        for (int i = 0; i < SK_RL_E; i++) acc[0] += v[i] * xv[i];
       }
-    } else if ((KM & SKM_BCOL) && kind == K_BCOL) {
-      const uint32_t c0 = col + (first ? C : 0u);
-      if (DECODE) {
-        for (uint32_t e = 0; e < n; e++) {
-          drows[val_off + vi + e] = (int)(P.row_start + wrow + key + e / align);
-          dcols[val_off + vi + e] = (int)(c0 + e % align);
-        }
-      } else {
+    }
+  } else if ((KM & SKM_BROW) && kind == K_BROW) {
+    const uint32_t c0 = col + (first ? C : 0u) + l0;   // first column of the task
+    if (DECODE) {
+      for (uint32_t e = 0; e < n; e++) {
+        c.drows[vi + e] = (int)(c.grow0 + rowrel + e % align);
+        c.dcols[vi + e] = (int)(c0 + e / align);
+      }
+    } else if (BRC > 0) {
+      if (valid) {
+        double xv[BRC > 0 ? BRC : 1], v[BRC > 0 ? BRC * R : 1];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          if ((uint32_t)j < align) {
-            const double xv = __ldg(x + c0 + j);   // x once per column (block_col_tmpl.c)
+        for (int j = 0; j < BRC; j++) xv[j] = __ldg(c.x + c0 + j);   // x once per column (block_row_tmpl.c)
 #pragma unroll
-            for (int a = 0; a < R && a < SK_BLK_LINES; a++)
-              if ((uint32_t)a < nl) acc[a] += __ldg(values + vi + a * align + j) * xv;
-          }
+        for (int e = 0; e < BRC * R; e++) v[e] = __ldg(c.values + vi + e);
+#pragma unroll
+        for (int j = 0; j < BRC; j++)
+#pragma unroll
+          for (int a = 0; a < R; a++) acc[a] += v[j * R + a] * xv[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < SK_BLK_LINES; j++) {
+        if ((uint32_t)j < nl) {
+          const double xv = __ldg(c.x + c0 + j);
+#pragma unroll
+          for (int a = 0; a < R; a++)
+            if ((uint32_t)a < align) acc[a] += __ldg(c.values + vi + j * align + a) * xv;
         }
       }
     }
-    if (DECODE) continue;
-
-    // ---- row sums: tasks that start in the same row are neighbours; the last lane of a run adds into the window ----
-    const uint32_t kprev = __shfl_up_sync(FULL, key, 1);
-    const uint32_t heads = __ballot_sync(FULL, lane == 0 || kprev != key);
-    const int seg = 31 - __clz(heads & lemask);
-    const bool last = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
-#pragma unroll
-    for (int a = 0; a < R; a++) {
-      double s = acc[a];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double tv = __shfl_up_sync(FULL, s, o);
-        if (lane - o >= seg) s += tv;
+  } else if ((KM & SKM_BCOL) && kind == K_BCOL) {
+    const uint32_t c0 = col + (first ? C : 0u);
+    if (DECODE) {
+      for (uint32_t e = 0; e < n; e++) {
+        c.drows[vi + e] = (int)(c.grow0 + key + e / align);
+        c.dcols[vi + e] = (int)(c0 + e % align);
       }
-      bool add = last;
-      if (R > 1 && multib) {
-        // runs of different block-column tasks can end in the same row: the first lane of such a group adds the others
-        const uint32_t target = last ? key + a : 0x2000u + lane;
-        const uint32_t peers = __match_any_sync(FULL, target);
-        uint32_t others = peers & ~(1u << lane);
-        add = last && (peers & ((1u << lane) - 1u)) == 0;
-        const double s0 = s;
-        while (__any_sync(FULL, others != 0)) {
-          const int src = others ? __ffs((int)others) - 1 : lane;
-          const double ov = __shfl_sync(FULL, s0, src);
-          if (others) { s += ov; others &= others - 1; }
+    } else if (BC > 0) {
+      if (valid) {
+        double xv[BC > 0 ? BC : 1], v[BC > 0 ? BC * R : 1];
+#pragma unroll
+        for (int j = 0; j < BC; j++) xv[j] = __ldg(c.x + c0 + j);   // x once per column (block_col_tmpl.c)
+#pragma unroll
+        for (int e = 0; e < BC * R; e++) v[e] = __ldg(c.values + vi + e);
+#pragma unroll
+        for (int a = 0; a < R; a++)
+#pragma unroll
+          for (int j = 0; j < BC; j++) acc[a] += v[a * BC + j] * xv[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if ((uint32_t)j < align) {
+          const double xv = __ldg(c.x + c0 + j);
+#pragma unroll
+          for (int a = 0; a < R && a < SK_BLK_LINES; a++)
+            if ((uint32_t)a < nl) acc[a] += __ldg(c.values + vi + a * align + j) * xv;
         }
       }
-      if (add) sacc[key + a] += s;
-      __syncwarp();
     }
   }
   if (DECODE) return;
 
+  // ---- row sums: tasks that start in the same row are neighbours; the last lane of a run adds into the window ----
+  const uint32_t kprev = __shfl_up_sync(FULL, key, 1);
+  const uint32_t heads = __ballot_sync(FULL, lane == 0 || kprev != key);
+  const int seg = 31 - __clz(heads & c.lemask);
+  const bool last = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+  const uint32_t maxrun = __reduce_max_sync(FULL, valid ? (uint32_t)(lane - seg) : 0u);
+#pragma unroll
+  for (int a = 0; a < R; a++) {
+    double s = acc[a];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      if ((uint32_t)o > maxrun) break;
+      const double tv = __shfl_up_sync(FULL, s, o);
+      if (lane - o >= seg) s += tv;
+    }
+    bool add = last;
+    if (R > 1 && c.multib) {
+      // runs of different block-column tasks can end in the same row: the first lane of such a group adds the others
+      const uint32_t target = last ? key + a : 0x2000u + lane;
+      const uint32_t peers = __match_any_sync(FULL, target);
+      uint32_t others = peers & ~(1u << lane);
+      add = last && (peers & ((1u << lane) - 1u)) == 0;
+      const double s0 = s;
+      while (__any_sync(FULL, others != 0)) {
+        const int src = others ? __ffs((int)others) - 1 : lane;
+        const double ov = __shfl_sync(FULL, s0, src);
+        if (others) { s += ov; others &= others - 1; }
+      }
+    }
+    if (add) c.sacc[key + a] += s;
+    __syncwarp();
+  }
+}
+
+// One chunk = up to SK_MAX_ROUNDS rounds of 32 units.  DECODE: parity aid — store the decoded (row, column) of every
+// value instead of multiplying.
+template <int R, uint32_t KM, int BC, int BRC, bool DECODE>
+__device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, double *sacc, const uint4 *sid, const int lane,
+                                         const double *__restrict__ x, double *__restrict__ y, const double alpha, const double beta,
+                                         const int overwrite, int *drows, int *dcols) {
+  const uint4 *q = P.sk_chunks + 2 * (size_t)ch;
+  const uint4 qa = __ldg(q), qb = __ldg(q + 1);
+  const uint32_t cursor0 = qa.z;
+  const int wrow = (int)qa.w;
+  const uint32_t c6 = qb.z, c7 = qb.w;
+  const uint32_t nunits = (c6 & 0xffu) + 1u, row0rel = (c6 >> 8) & 0xffu, f_lo = (c6 >> 16) & 0xffu;
+  const bool headf = (c6 >> 30) & 1u;
+  const uint32_t f_hi = c7 & 0x1ffu, t_hi = (c7 >> 9) & 0x1ffu;
+  SkCtx c;
+  c.cbase = P.ctl + ((uint64_t)qa.x | ((uint64_t)((c6 >> 24) & 0x3fu) << 32));
+  c.values = P.values + P.val_base + qa.y;
+  c.x = x; c.sacc = sacc; c.sid = sid; c.lane = lane;
+  c.lemask = 0xffffffffu >> (31 - lane);
+  c.multib = (c6 >> 31) & 1u;
+  c.grow0 = P.row_start + wrow;
+  c.drows = DECODE ? drows + qa.y : nullptr; c.dcols = DECODE ? dcols + qa.y : nullptr;
+  if (!DECODE) {   // the window rows this chunk adds into start from zero
+    const uint32_t zn = max(f_hi, t_hi);
+    if (lane < (int)zn) sacc[lane] = 0.0;
+    for (uint32_t i = lane + 32; i < zn; i += 32) sacc[i] = 0.0;
+    __syncwarp();
+  }
+
+  uint32_t carry = 0;         // column cursor behind the last task walked so far
+  uint32_t rowbase = row0rel; // window row of the last unit of the previous round
+  const uint16_t *uo = P.sk_uoffs + qb.x;
+  for (uint32_t u0 = 0; u0 < nunits; u0 += 32) {
+    const uint32_t nu = min(32u, nunits - u0);
+    // ---- 1. unit heads, one per lane ----------------------------------------------------------------------------
+    uint32_t size = 0, nt = 0, rowinc = 0, ucol = 0, body = 0, id = 0;
+    bool ureset = false, rjmp = false;
+    uint4 ie = make_uint4(0, 0, 1, 65536);
+    if ((uint32_t)lane < nu) {
+      const uint32_t off = __ldg(uo + u0 + lane);
+      const uint8_t *hp = c.cbase + off;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(hp);
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+      const uint32_t sh = (uint32_t)(a & 3) * 8;
+      const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+      const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+      const uint32_t flags = b0 & 0xffu;
+      size = (b0 >> 8) & 0xffu;
+      id = flags & 0x3fu;
+      uint64_t win = (uint64_t)__funnelshift_r(b0, b1, 16) | ((uint64_t)__funnelshift_r(b1, b2, 16) << 32);   // bytes 2..9
+      uint32_t hl = 2;
+      const bool nr = (flags & 0x80u) != 0;
+      const bool chunk_first = (u0 | (uint32_t)lane) == 0;
+      if (nr) {   // csx_spmv_tmpl.c:86-91; the row of the chunk's first unit comes from the chunk entry
+        uint32_t jmp = 1;
+        if (flags & 0x40u) {
+          uint32_t len;
+          jmp = sk_varint(win, hp + hl, len);
+          hl += len;
+          win = len >= 8 ? 0 : win >> (8 * len);
+          rjmp = true;
+        }
+        if (!chunk_first) rowinc = jmp;
+      }
+      if (P.full_colind) { ucol = hl == 2 ? (uint32_t)win : sk_ld32(hp + hl); hl += 4; }
+      else {
+        uint32_t len;
+        ucol = hl <= 6 ? sk_varint(win, hp + hl, len) : sk_varint(sk_ld32(hp + hl) | ((uint64_t)sk_ld32(hp + hl + 4) << 32), hp + hl, len);
+        hl += len;
+      }
+      ureset = chunk_first || nr || P.full_colind;   // the column cursor restarts at this unit
+      if (chunk_first && !P.full_colind) ucol += cursor0;
+      body = off + hl;
+      ie = sid[id];
+      nt = sk_unit_tasks(ie.x & 0xffu, size, ie.y, ie.z, ie.w);
+    }
+    // inclusive scans over the units: elements | tasks << 16, rows
+    uint32_t et = size | (nt << 16), rs = rowinc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a = __shfl_up_sync(FULL, et, o);
+      if (lane >= o) et += a;
+    }
+    if (__any_sync(FULL, rjmp)) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t b = __shfl_up_sync(FULL, rs, o);
+        if (lane >= o) rs += b;
+      }
+    } else {
+      rs = (uint32_t)__popc(__ballot_sync(FULL, rowinc != 0) & c.lemask);
+    }
+    const uint32_t tot = __shfl_sync(FULL, et, 31);
+    const uint32_t ntasks = tot >> 16;
+    const uint32_t ts = (et >> 16) - nt, es = (et & 0xffffu) - size;
+    // unit record: A = first task | first element << 8 | size << 18 | id << 26, B = row | body offset << 8 | restart << 21, C = ucol
+    const uint32_t recA = ts | (es << 8) | (size << 18) | (id << 26);
+    const uint32_t recB = (rowbase + rs) | (body << 8) | ((uint32_t)ureset << 21);
+    rowbase += __shfl_sync(FULL, rs, 31);
+
+    // ---- 2. tasks, 32 at a time -----------------------------------------------------------------------------------
+    if (ntasks == nu) {   // every unit is one task: lane = unit
+      sk_window<R, KM, BC, BRC, DECODE, true>(c, recA, recB, ucol, ie, 0u, nu, carry);
+    } else {
+      for (uint32_t t0 = 0; t0 < ntasks; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const uint32_t rel = ts - t0;
+        const uint32_t bit = ((uint32_t)lane < nu && rel < 32u) ? 1u << rel : 0u;
+        const uint32_t M = __reduce_or_sync(FULL, bit);
+        const uint32_t nb = (uint32_t)__popc(__ballot_sync(FULL, (uint32_t)lane < nu && ts < t0));
+        const int U = (int)(nb + (uint32_t)__popc(M & c.lemask)) - 1;
+        const uint32_t A = __shfl_sync(FULL, recA, U), B = __shfl_sync(FULL, recB, U), C = __shfl_sync(FULL, ucol, U);
+        sk_window<R, KM, BC, BRC, DECODE, false>(c, A, B, C, sid[A >> 26], t - (A & 0xffu), min(32u, ntasks - t0), carry);
+      }
+    }
+    c.values += tot & 0xffffu;
+    if (DECODE) { c.drows += tot & 0xffffu; c.dcols += tot & 0xffffu; }
+  }
+  if (DECODE) return;
+
   // ---- 3. the chunk's rows leave the window ---------------------------------------------------------------------
-  for (uint32_t i = f_lo + lane; i < f_hi; i += 32) {
-    const double v = sacc[i];
-    double *yp = y + (P.row_start + wrow + i);
-    *yp = overwrite ? alpha * v : alpha * v + beta * *yp;
+  {
+    uint32_t i = f_lo + lane;
+    if (i < f_hi) {
+      double *yp = y + (c.grow0 + i);
+      const double v = alpha * sacc[i];
+      *yp = overwrite ? v : v + beta * *yp;
+    }
+    for (i += 32; i < f_hi; i += 32) {
+      double *yp = y + (c.grow0 + i);
+      const double v = alpha * sacc[i];
+      *yp = overwrite ? v : v + beta * *yp;
+    }
   }
   if (headf | (t_hi > f_hi)) {   // rows of other chunks: to the scratch array
     double *sc = P.sk_scratch + qb.y;

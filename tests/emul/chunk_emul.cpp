@@ -114,6 +114,7 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
   static double sacc[SK_WIN];
   static uint4 sid[64];
   std::vector<bool> streamed(L.parts.size(), false);
+  int inst = 0;
   for (size_t i = 0; i < L.parts.size() && !M.symmetric; i++) {
     const PartLayout &pl = L.parts[i];
     const PartDev &P = pdev[i];
@@ -123,25 +124,16 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     for (uint32_t ch = 0; ch < P.sk_c1; ch++) {
       for (int k = 0; k < SK_WIN; k++) sacc[k] = std::nan("");   // the kernel must clear what it uses
       warp_emul::run_warp([&](int lane) {
-        sk_chunk<8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, true>(P, ch, sacc, sid, lane, nullptr, nullptr, 0.0, 0.0, 1, dec_rows + P.val_base, dec_cols + P.val_base);
+        sk_chunk<8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL, 0, 0, true>(P, ch, sacc, sid, lane, nullptr, nullptr, 0.0, 0.0, 1, dec_rows + P.val_base, dec_cols + P.val_base);
       });
-      const uint32_t km = pl.sk_kmask;
-      const int r = pl.sk_rows;
       bool done = false;
-#define SK_TRY(RR, KK)                                                                                              \
-  if (!done && r <= RR && (km & ~(uint32_t)(KK)) == 0) {                                                            \
+#define SK_TRY(RR, KK, BCC, BRR)                                                                                    \
+  if (!done && sk_instance_serves(RR, (KK), BCC, BRR, pl.sk_kmask, pl.sk_rows, pl.sk_bc, pl.sk_brc)) {              \
     done = true;                                                                                                    \
-    warp_emul::run_warp([&](int lane) { sk_chunk<RR, (KK), false>(P, ch, sacc, sid, lane, x, y, alpha, 0.0, 1, nullptr, nullptr); }); \
+    inst = RR * 1000 + BCC * 100 + BRR * 10;                                                                        \
+    warp_emul::run_warp([&](int lane) { sk_chunk<RR, (KK), BCC, BRR, false>(P, ch, sacc, sid, lane, x, y, alpha, 0.0, 1, nullptr, nullptr); }); \
   }
-      SK_TRY(1, SKM_DELTA)
-      SK_TRY(1, SKM_ROWLOCAL)
-      SK_TRY(2, SKM_ROWLOCAL | SKM_BCOL)
-      SK_TRY(3, SKM_ROWLOCAL | SKM_BCOL)
-      SK_TRY(4, SKM_ROWLOCAL | SKM_BCOL)
-      SK_TRY(2, SKM_ROWLOCAL | SKM_BROW)
-      SK_TRY(3, SKM_ROWLOCAL | SKM_BROW)
-      SK_TRY(4, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
-      SK_TRY(8, SKM_ROWLOCAL | SKM_BROW | SKM_BCOL)
+      SK_INSTANCES(SK_TRY)
 #undef SK_TRY
       if (!done) { put_err(err, errlen, "no stream kernel instantiation"); return -1; }
     }
@@ -212,6 +204,6 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     }
   }
   for (size_t i = 0; i < M.parts.size(); i++) M.parts[i].nrows = saved[i];
-  if (stats) { stats[0] = nchunks; stats[1] = nunits; stats[2] = nxd; }
+  if (stats) { stats[0] = nchunks; stats[1] = nunits; stats[2] = nxd; stats[3] = inst; }
   return 0;
 }

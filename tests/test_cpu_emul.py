@@ -84,3 +84,55 @@ def test_emulated_chunk_kernel_config_shapes():
     for o in ({"spx.preproc.xform": "none"}, {"spx.preproc.xform": "none", "spx.b200.slice": 32},
               {"spx.preproc.xform": "none", "spx.rt.nr_threads": 5}):
         _check(rp, ci, va, n, n, o)
+
+
+def _blocks(nbr, r, c, per_row, seed, ncols_b):
+    from tests.matrices import _csr_from_coo
+    rng = np.random.default_rng(seed)
+    S = set()
+    for I in range(nbr):
+        for J in rng.choice(ncols_b, size=per_row, replace=False):
+            for a in range(r):
+                for b in range(c):
+                    S.add((I * r + a, int(J) * c + b))
+        S.add((I * r, int(rng.integers(ncols_b * c))))
+    a = np.array(sorted(S))
+    rp, ci, va = _csr_from_coo(a[:, 0], a[:, 1], rng.standard_normal(a.shape[0]), nbr * r, ncols_b * c)
+    return rp, ci, va, nbr * r, ncols_b * c
+
+
+def test_emulated_stream_kernel_shaped_instantiations():
+    """The pattern-set instantiations with compile-time block shapes (stream_kernel.cuh: SK_INSTANCES) are the ones
+    the dispatcher picks for uniform blocks, and they multiply correctly (stats[3] = R*1000 + BC*100 + BRC*10)."""
+    want = {(3, 3, "bc"): 3300, (2, 2, "bc"): 2200, (4, 2, "bc"): 4200, (2, 4, "br"): 2040, (3, 8, "br"): 3040, (3, 3, "br"): 4000}
+    for (r, c, xf), inst in want.items():
+        rp, ci, va, n, m = _blocks(200, r, c, 3, 1, 150)
+        st = _check(rp, ci, va, n, m, {"spx.preproc.xform": xf, "spx.preproc.sampling": "none"})
+        assert st[3] == inst, ((r, c, xf), st[3])
+
+
+def test_emulated_stream_kernel_long_rows_gaps_tall_blocks():
+    """Rows longer than a chunk (fix-ups), runs of empty rows longer than the row window (gaps), tall block columns
+    cut into several tasks, rounds of 32 units with the cursor carried across them."""
+    from tests.matrices import _csr_from_coo
+    for seed in range(2):
+        r = np.random.default_rng(seed)
+        n, m = 2000, 3200
+        S = set()
+        for row in (3, 700, 701, 1500):
+            for c in r.choice(m, size=int(r.integers(2200, 3000)), replace=False):
+                S.add((row, int(c)))
+        for _ in range(200):
+            S.add((int(r.integers(n)), int(r.integers(m))))
+        for _ in range(6):
+            r0, c0, h = int(r.integers(n - 40)), int(r.integers(m - 4)), int(r.integers(5, 30))
+            for i in range(h):
+                for j in range(3):
+                    S.add((r0 + i, c0 + j))
+        a = np.array(sorted(S))
+        rp, ci, va = _csr_from_coo(a[:, 0], a[:, 1], r.standard_normal(a.shape[0]), n, m)
+        for xf in ("none", "all", "br,bc", "h,bc"):
+            for fc in ("false", "true"):
+                st = _check(rp, ci, va, n, m, {"spx.preproc.xform": xf, "spx.matrix.full_colind": fc, "spx.preproc.sampling": "none",
+                                              "spx.rt.nr_threads": 1 + seed * 2})
+                assert st[4] > 0 and st[5] > 0   # fix-up entries and gaps present

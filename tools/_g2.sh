@@ -1,0 +1,7 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest2.log 2>&1; tail -3 gpurun_out/r2_pytest2.log
+timeout 900 python tools/wbench.py c3b c4n c4s c5s > gpurun_out/r2_wbench2.log 2>&1; cat gpurun_out/r2_wbench2.log
+for w in c5s c3b c4n; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:csx_stream_kernel -s 3 -c 1 -o gpurun_out/r2_${w}_stream_v2 -f python tools/wbench.py $w > gpurun_out/r2_ncu_$w.log 2>&1; tail -2 gpurun_out/r2_ncu_$w.log
+done
