@@ -33,6 +33,8 @@ struct PartDev {
   uint32_t sk_c0, sk_c1;       // chunks of this launch
   uint32_t sk_f0, sk_f1;       // fix rows of this launch
   uint32_t sk_g0, sk_g1;       // gaps of this launch
+  const uint8_t *ctl_end;      // end of the device-wide ctl / values arrays (bounds of the L2 prefetches)
+  const double *values_end;
   IdEntry idtab[64];
 };
 

@@ -537,6 +537,8 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     if (!hp.ctl.empty()) CUDA_TRY(cudaMemcpy((uint8_t *)dc + pl.ctl_base, hp.ctl.data(), hp.ctl.size(), cudaMemcpyHostToDevice));
     P.ctl = (const uint8_t *)dc + pl.ctl_base;
     P.values = m->d_values;
+    P.ctl_end = (const uint8_t *)dc + std::max<uint64_t>(L.total_ctl, 16);
+    P.values_end = m->d_values + std::max<uint64_t>(L.total_values, 1);
     uint32_t *tx = nullptr; XDesc *xd = nullptr; ChunkEntry *ch = nullptr; uint16_t *uo = nullptr;
     if (dev_copy(m, pl.chunks.data(), pl.chunks.size(), &ch)) return -1;
     if (dev_copy(m, pl.uoffs.data(), pl.uoffs.size(), &uo)) return -1;

@@ -142,17 +142,21 @@ struct SkUnit {
   int64_t val;              // partition-relative index of its first value
   int64_t cursor_before;    // column cursor before the unit (0 when it starts a row)
   bool multi_bcol;          // block-column unit cut into several tasks
+  bool round_end;           // last unit of its round (set by SkBuilder)
 };
 
 class SkBuilder {
  public:
   SkBuilder(PartLayout &L, int64_t nrows) : L_(L), nrows_(nrows) {}
-  void add(const SkUnit &u) {
+  void add(const SkUnit &u0) {
+    SkUnit u = u0;
+    u.round_end = false;
     while (!open_.empty() && !fits(u)) {
       std::vector<SkUnit> rest = split(u);   // units behind the cut: their rounds change, so they are added again
       for (const SkUnit &w : rest) add(w);
     }
-    if (open_.empty()) wrow_ = (first_ && u.row + u.reach <= 64) ? 0 : u.row;
+    if (open_.empty()) { wrow_ = (first_ && u.row + u.reach <= 64) ? 0 : u.row; rounds_ = 1; round_start_ = 0; }
+    else if (round_closes(u)) { open_.back().round_end = true; rounds_++; round_start_ = open_.size(); }
     open_.push_back(u);
   }
   void finish() {
@@ -174,13 +178,21 @@ class SkBuilder {
   }
 
  private:
+  // The current round ends before `u`: it is full, or its last window of 32 tasks is well filled, `u` would open
+  // another window and the units still missing to 32 would fill less than a quarter of that one (rounds of small units
+  // then walk one full window instead of one full and one nearly empty one).
+  bool round_closes(const SkUnit &u) const {
+    const size_t units = open_.size() - round_start_;
+    uint32_t tasks = 0, elems = 0;
+    for (size_t i = round_start_; i < open_.size(); i++) { tasks += open_[i].ntasks; elems += open_[i].size; }
+    if (units == (size_t)SK_ROUND_UNITS || tasks + u.ntasks > (uint32_t)SK_MAX_TASKS || elems + u.size > (uint32_t)SK_MAX_ELEMS) return true;
+    if (units < 16 || tasks == 0) return false;
+    const uint32_t fill = tasks - 32 * ((tasks - 1) / 32);   // tasks in the round's last window
+    return fill >= 24 && fill + u.ntasks > 32 && (SK_ROUND_UNITS - units) * tasks < 8 * units;
+  }
   bool fits(const SkUnit &u) const {
-    const size_t n = open_.size();
-    if (n == (size_t)SK_MAX_UNITS) return false;
-    uint32_t tasks = u.ntasks, elems = u.size;   // of the round the unit would join
-    for (size_t i = n / SK_ROUND_UNITS * SK_ROUND_UNITS; i < n; i++) { tasks += open_[i].ntasks; elems += open_[i].size; }
-    return tasks <= (uint32_t)SK_MAX_TASKS && elems <= (uint32_t)SK_MAX_ELEMS &&
-           u.end - open_.front().off <= (uint64_t)SK_MAX_BYTES && u.row + u.reach - wrow_ <= SK_WROWS - 1 &&
+    if (rounds_ == SK_MAX_ROUNDS && round_closes(u)) return false;
+    return u.end - open_.front().off <= (uint64_t)SK_MAX_BYTES && u.row + u.reach - wrow_ <= SK_WROWS - 1 &&
            u.row - wrow_ <= SK_WROWS - 2;
   }
   // The open chunk cannot take `next`: close it, preferably at the start of its last row when `next` continues
@@ -225,7 +237,16 @@ class SkBuilder {
              ((uint32_t)head << 30) | ((uint32_t)multib << 31);
     e.w[7] = (uint32_t)f_hi | ((uint32_t)t_hi << 9);
     L_.sk_chunks.push_back(e);
-    for (size_t i = 0; i < b; i++) L_.sk_uoffs.push_back((uint16_t)(open_[i].off - off0));
+    {   // layout statistics
+      uint32_t rt = 0;
+      for (size_t i = 0; i < b; i++) {
+        rt += open_[i].ntasks;
+        L_.sk_stat[2] += open_[i].ntasks; L_.sk_stat[3] += open_[i].size;
+        if (open_[i].round_end || i + 1 == b) { L_.sk_stat[0]++; L_.sk_stat[1] += (rt + 31) / 32; rt = 0; }
+      }
+    }
+    for (size_t i = 0; i < b; i++)   // bit 15: last unit of its round
+      L_.sk_uoffs.push_back((uint16_t)((open_[i].off - off0) | ((open_[i].round_end || i + 1 == b) ? 0x8000u : 0u)));
     L_.sk_first_row.push_back((int32_t)wrow_);
     L_.sk_last_row.push_back((int32_t)std::max(touch_hi, wrow_ + f_hi - 1));
     L_.sk_cmin.push_back(cmin == INT64_MAX ? INT32_MAX : (int32_t)cmin);
@@ -238,6 +259,8 @@ class SkBuilder {
   std::vector<SkUnit> open_;
   std::vector<std::pair<int32_t, uint32_t>> fixes_;   // (row, scratch slot), in chunk order
   int64_t wrow_ = 0, prev_own_hi_ = 0;
+  int rounds_ = 1;
+  size_t round_start_ = 0;   // first unit of the open round
   bool first_ = true;
 };
 

@@ -95,9 +95,9 @@ struct ChunkEntry {
 };
 
 // ---- stream kernel (kernel 2 of non-symmetric partitions; stream_kernel.cuh) ---------------------------------
-// The ctl stream is cut at unit boundaries into chunks of up to SK_MAX_ROUNDS rounds of 32 units (every round but
-// the last is full; a round holds at most SK_MAX_TASKS lane tasks and SK_MAX_ELEMS non-zeros), at most SK_MAX_BYTES
-// ctl bytes, whose rows fit a window of SK_WROWS rows.  A warp parses one
+// The ctl stream is cut at unit boundaries into chunks of up to SK_MAX_ROUNDS rounds of at most 32 units (a round
+// holds at most SK_MAX_TASKS lane tasks and SK_MAX_ELEMS non-zeros; bit 15 of a unit's entry in the offset table
+// marks the last unit of a round), at most SK_MAX_BYTES ctl bytes, whose rows fit a window of SK_WROWS rows.  A warp parses one
 // unit head per lane, cuts the units into tasks (at most SK_RL_E consecutive elements of a delta / horizontal
 // unit; a column range of a block-row unit or a row range of a block-column unit with all its rows in register
 // accumulators) and walks 32 tasks at a time.  Row sums are combined across lanes with a segmented shuffle
@@ -111,9 +111,9 @@ struct ChunkEntry {
 constexpr int SK_ROUND_UNITS = 32;
 constexpr int SK_MAX_ROUNDS = 4;
 constexpr int SK_MAX_UNITS = SK_ROUND_UNITS * SK_MAX_ROUNDS;
-constexpr int SK_MAX_TASKS = 128;
+constexpr int SK_MAX_TASKS = 224;      // per round (8-bit task offsets)
 constexpr int SK_MAX_ELEMS = 1023;
-constexpr int SK_MAX_BYTES = 8191;
+constexpr int SK_MAX_BYTES = 8191;     // 13-bit offsets of unit bodies inside a chunk
 constexpr int SK_WROWS = 256;        // rows of the per-warp y window
 constexpr int SK_RL_E = 4;           // elements per task of a row-local unit
 constexpr int SK_BLK_E = 12;         // element budget of a block task
@@ -150,6 +150,7 @@ struct PartLayout {
   int sk_rows = 1;                       // register accumulators a task needs (rows of a block task)
   int sk_bc = 0;                         // > 0: every block-column task is exactly sk_rows rows x sk_bc columns
   int sk_brc = 0;                        // > 0: every block-row task is exactly sk_rows rows x sk_brc columns
+  int64_t sk_stat[4] = {0, 0, 0, 0};     // rounds, windows of 32 tasks, tasks, elements (layout statistics)
   // host side only (slabs of the pipelined host-buffer SpMV): per chunk the window base row, the last row it
   // touches and the columns it reads
   std::vector<int32_t> sk_first_row, sk_last_row, sk_cmin, sk_cmax;

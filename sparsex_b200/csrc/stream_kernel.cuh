@@ -38,6 +38,20 @@ struct SkIO {
   double *vec[2];
 };
 
+// Bulk prefetch of [p, p + bytes) into L2 (cp.async.bulk.prefetch: one instruction, no registers, no LSU wavefronts),
+// clipped to `end`.  The stream kernel's loads form a dependent chain (chunk entry -> unit offsets -> heads -> deltas ->
+// x); with the stream already in L2 every link costs an L2 hit instead of a DRAM access.
+__device__ __forceinline__ void sk_prefetch_l2(const void *p, uint32_t bytes, const void *end) {
+#ifndef CSXB_EMUL
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(15), e = reinterpret_cast<uintptr_t>(end) & ~uintptr_t(15);
+  if (a + bytes > e) bytes = a < e ? (uint32_t)(e - a) : 0u;
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+#endif
+}
+constexpr uint32_t SK_PF_CTL = 2048, SK_PF_VAL = 4096;   // bytes prefetched for the first round of a far chunk
+constexpr uint32_t SK_PF_CTL_NEXT = 1024, SK_PF_VAL_NEXT = 2048;   // ... and behind the current round
+constexpr uint32_t SK_PF_DIST = 148 * 32;                 // chunks in flight on the device: prefetch that far ahead
+
 // 32 bits at any byte address (ctl is readable CTL_PAD bytes past its end)
 __device__ __forceinline__ uint32_t sk_ld32(const uint8_t *p) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -141,6 +155,7 @@ __device__ __forceinline__ void sk_window(const SkCtx &c, const uint32_t A, cons
   // geometry of the task: n elements; row-local: column steps D[]; blocks: nl lines of the free dimension from l0
   uint32_t n = 0, adv = 0, key = 0x1000u + lane, vi = ues, l0 = 0, nl = 0;
   uint32_t D[SK_RL_E] = {0, 0, 0, 0};
+  double vrl[SK_RL_E] = {0.0, 0.0, 0.0, 0.0};   // values of a row-local task
   if (valid) {
     key = rowrel;
     if (kind <= K_HORIZ) {
@@ -163,6 +178,11 @@ __device__ __forceinline__ void sk_window(const SkCtx &c, const uint32_t A, cons
       }
 #pragma unroll
       for (int i = 0; i < SK_RL_E; i++) adv += (uint32_t)i < n ? D[i] : 0u;
+      if (!DECODE) {   // the values do not wait for the column cursor
+#pragma unroll
+        for (int i = 0; i < SK_RL_E; i++)
+          if ((uint32_t)i < n) vrl[i] = __ldg(c.values + vi + i);
+      }
     } else if ((KM & SKM_BROW) && kind == K_BROW) {   // align rows x delta columns, values column-major; task = column range
       if (BRC > 0) { l0 = k * BRC; nl = BRC; n = BRC * R; vi = ues + l0 * R; }
       else { l0 = k * tpar; nl = min(tpar, delta - l0); n = nl * align; vi = ues + l0 * align; }
@@ -209,14 +229,14 @@ __device__ __forceinline__ void sk_window(const SkCtx &c, const uint32_t A, cons
         for (int i = 0; i < SK_RL_E; i++)
           if ((uint32_t)i < n) { c.drows[vi + i] = (int)(c.grow0 + rowrel); c.dcols[vi + i] = (int)cl[i]; }
       } else {
-        double v[SK_RL_E], xv[SK_RL_E];
+        double xv[SK_RL_E];
 #pragma unroll
         for (int i = 0; i < SK_RL_E; i++) {
-          v[i] = 0.0; xv[i] = 0.0;
-          if ((uint32_t)i < n) { v[i] = __ldg(c.values + vi + i); xv[i] = __ldg(c.x + cl[i]); }
+          xv[i] = 0.0;
+          if ((uint32_t)i < n) xv[i] = __ldg(c.x + cl[i]);
         }
 #pragma unroll
-        for (int i = 0; i < SK_RL_E; i++) acc[0] += v[i] * xv[i];
+        for (int i = 0; i < SK_RL_E; i++) acc[0] += vrl[i] * xv[i];
       }
     }
   } else if ((KM & SKM_BROW) && kind == K_BROW) {
@@ -345,17 +365,22 @@ __device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, do
     __syncwarp();
   }
 
+  // the chunk a later CTA starts with: its entry is loaded now and its first round is prefetched below
+  uint4 pq = make_uint4(0, 0, 0, 0), pq2 = make_uint4(0, 0, 0, 0);
+  const bool pf_far = !DECODE && lane == 0 && ch + SK_PF_DIST < P.sk_c1;
+  if (pf_far) { pq = __ldg(q + 2 * (size_t)SK_PF_DIST); pq2 = __ldg(q + 2 * (size_t)SK_PF_DIST + 1); }
   uint32_t carry = 0;         // column cursor behind the last task walked so far
   uint32_t rowbase = row0rel; // window row of the last unit of the previous round
   const uint16_t *uo = P.sk_uoffs + qb.x;
-  for (uint32_t u0 = 0; u0 < nunits; u0 += 32) {
-    const uint32_t nu = min(32u, nunits - u0);
-    // ---- 1. unit heads, one per lane ----------------------------------------------------------------------------
+  for (uint32_t u0 = 0, nu; u0 < nunits; u0 += nu) {
+    // ---- 1. unit heads, one per lane; the round ends at the first unit whose offset carries the end mark ----------
+    const uint32_t oraw = u0 + lane < nunits ? __ldg(uo + u0 + lane) : 0x8000u;
+    nu = (uint32_t)__ffs((int)__ballot_sync(FULL, (oraw & 0x8000u) != 0));
     uint32_t size = 0, nt = 0, rowinc = 0, ucol = 0, body = 0, id = 0;
     bool ureset = false, rjmp = false;
     uint4 ie = make_uint4(0, 0, 1, 65536);
     if ((uint32_t)lane < nu) {
-      const uint32_t off = __ldg(uo + u0 + lane);
+      const uint32_t off = oraw & 0x7fffu;
       const uint8_t *hp = c.cbase + off;
       const uintptr_t a = reinterpret_cast<uintptr_t>(hp);
       const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
@@ -415,6 +440,15 @@ __device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, do
     const uint32_t recA = ts | (es << 8) | (size << 18) | (id << 26);
     const uint32_t recB = (rowbase + rs) | (body << 8) | ((uint32_t)ureset << 21);
     rowbase += __shfl_sync(FULL, rs, 31);
+    if (!DECODE && (uint32_t)lane == nu - 1) {   // what the next round reads: ctl and values behind this round
+      sk_prefetch_l2(c.cbase + body + 64, SK_PF_CTL_NEXT, P.ctl_end);
+      sk_prefetch_l2(c.values + es + size, SK_PF_VAL_NEXT, P.values_end);
+    }
+    if (pf_far && u0 == 0) {
+      sk_prefetch_l2(P.ctl + ((uint64_t)pq.x | ((uint64_t)((pq2.z >> 24) & 0x3fu) << 32)), SK_PF_CTL, P.ctl_end);
+      sk_prefetch_l2(P.values + P.val_base + pq.y, SK_PF_VAL, P.values_end);
+      sk_prefetch_l2(P.sk_uoffs + pq2.x, 256, P.sk_uoffs + pq2.x + 128);
+    }
 
     // ---- 2. tasks, 32 at a time -----------------------------------------------------------------------------------
     if (ntasks == nu) {   // every unit is one task: lane = unit

@@ -101,6 +101,7 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     P.sk_c0 = 0; P.sk_c1 = (uint32_t)pl.sk_chunks.size();
     nchunks += (int64_t)pl.sk_chunks.size();
     nunits += (int64_t)pl.sk_uoffs.size();
+    if (stats) for (int k = 0; k < 4; k++) stats[8 + k] += pl.sk_stat[k];
     if (stats) { stats[4] += (int64_t)pl.sk_fix_idx.size(); stats[5] += (int64_t)pl.sk_gaps.size(); stats[6] = pl.sk_rows; stats[7] = pl.sk_kmask; }
     P.full_colind = L.full_colind;
     P.rpt = pl.rpt;
@@ -111,6 +112,7 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     if (stats) stats[3] = pl.slice;
   }
   // non-symmetric partitions with stream units: stream kernel (writes y), fix-up, then kernel 1 adds (engine.cu: run_partition)
+  if (getenv("CSXB_EMUL_LAYOUT_ONLY")) { if (stats) { stats[0] = nchunks; stats[1] = nunits; } return 0; }
   static double sacc[SK_WIN];
   static uint4 sid[64];
   std::vector<bool> streamed(L.parts.size(), false);

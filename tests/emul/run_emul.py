@@ -33,7 +33,7 @@ def emul_spmv(rp, ci, va, nrows, ncols, opts, alpha, x):
     nnz = int(rp[-1])
     dr = np.full(nnz + 1, -2, np.int32)
     dc = np.full(nnz + 1, -2, np.int32)
-    stats = np.zeros(8, np.int64)
+    stats = np.zeros(16, np.int64)
     err = C.create_string_buffer(1024)
     o = ";".join("%s=%s" % kv for kv in (opts or {}).items()).encode()
     rc = lib().emul_spmv(rp.ctypes.data, ci.ctypes.data, va.ctypes.data, nrows, ncols, o, alpha, x.ctypes.data,
