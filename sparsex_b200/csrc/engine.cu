@@ -1,17 +1,17 @@
 // CUDA kernels (sm_100a) and the csxb_* C-ABI of the B200 CSX SpMV engine.
 //
-// Execution model (see gpu_layout.hpp for the tables), two kernels per SpMV on one stream:
-//   1. csx_spmv_kernel   one CTA per tile of 256 / 1024 rows; every thread owns rows and gathers the
-//                        contributions of the long cross-row units (vertical, diagonal, anti-diagonal)
-//                        listed for its tile, then writes y = alpha*acc + beta*y once per row.
-//                        No atomics, deterministic, streams values with coalesced loads.
-//   2. csx_chunk_kernel  (chunk_kernel.cuh) one warp per chunk of the ctl stream: ctl bytes and values are staged in
-//                        shared memory, one unit head per lane is parsed, units are cut into slices and every
-//                        lane walks one slice per round (columns from the deltas or from the unit geometry);
-//                        row sums are combined with segmented shuffle reductions and added to y with fp64 red
-//                        operations.
+// Execution model (see gpu_layout.hpp for the tables), up to three kernels per partition on one stream:
+//   1. csx_stream_kernel  (stream_kernel.cuh) one warp per chunk of the ctl stream: unit heads parsed one per lane,
+//                        units cut into lane tasks (elements of a delta / horizontal unit, block tasks with register
+//                        accumulators), row sums combined with segmented shuffle reductions in a shared-memory window
+//                        of y rows and written with plain stores (y = alpha*sum + beta*y).  Instantiated per pattern set.
+//   2. csx_stream_fixup_kernel  adds what chunks contributed to rows of other chunks, clears long runs of empty rows.
+//   3. csx_spmv_kernel   (gather_kernel.cuh) one CTA per tile of 256 / 1024 rows; every thread owns rows and gathers
+//                        the contributions of the table units (vertical, diagonal, anti-diagonal; under CSX-Sym also
+//                        the transposed image of every unit) listed for its tile, then adds them to y (or writes y
+//                        when the partition has no stream units).  No atomics anywhere: results are bit-reproducible.
 // Host-buffer calls are slab-pipelined (csxb_spmv_host); repeated SpMV across GPUs exchanges the halo rows from
-// inside kernel 1 over CUDA-IPC peer memory (csxb_xchg_*, csx_spmv_xe_kernel).
+// inside kernel 3 over CUDA-IPC peer memory (csxb_xchg_*, csx_spmv_xe_kernel).
 // SpMV is HBM-bound fp64 work: no tensor cores; every value and ctl byte is read once.
 //
 // Reference semantics reproduced: src/templates/csx_spmv_tmpl.c:66-101 and the
@@ -32,7 +32,7 @@
 #include "../../include/csx_b200.h"
 #include "csx_host.hpp"
 #include "gpu_layout.hpp"
-#include "chunk_kernel.cuh"
+#include "part_dev.cuh"
 #include "stream_kernel.cuh"
 
 #include "gather_kernel.cuh"
@@ -152,33 +152,6 @@ __global__ void csx_xchg_sync_kernel(const __grid_constant__ XchgDev X, int dbg)
   }
 }
 
-template <bool SYM, class XP = NoXchg>
-__global__ void __launch_bounds__(CHUNK_WARPS * 32, 9) csx_chunk_kernel(const __grid_constant__ PartDev P,
-                                                                     const double *__restrict__ x,
-                                                                     double *__restrict__ y, double alpha,
-                                                                     const __grid_constant__ XP X) {
-  __shared__ ChunkSmem smem[CHUNK_WARPS];
-  if constexpr (!std::is_same<XP, NoXchg>::value) {   // vectors by step parity (kernel 1 of this step has waited)
-    const unsigned long long xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
-    x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ch = P.chunk0 + blockIdx.x * CHUNK_WARPS + warp;
-  if (ch >= P.nchunks) return;
-  SpmvChunkOp<SYM> op;
-  op.x = x; op.y = y; op.vals = smem[warp].vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
-  process_chunk(P, ch, smem[warp], lane, op);
-}
-
-__global__ void __launch_bounds__(CHUNK_WARPS * 32) csx_decode_chunk_kernel(const __grid_constant__ PartDev P, int *rows,
-                                                                            int *cols) {
-  __shared__ ChunkSmem smem[CHUNK_WARPS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ch = blockIdx.x * CHUNK_WARPS + warp;
-  if (ch >= P.nchunks) return;
-  DecodeChunkOp op{rows + P.val_base, cols + P.val_base, P.row_start, 0};
-  process_chunk(P, ch, smem[warp], lane, op);
-}
 struct DecodeGatherOp {
   int *rows, *cols;   // device-wide
   int myrow;
@@ -530,7 +503,8 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
   m->pdev.resize(L.parts.size());
   for (size_t i = 0; i < L.parts.size(); i++) {
     PartLayout &pl = L.parts[i];
-    CsxPartition &hp = H.parts[i];
+    static CsxPartition no_part;   // the CSX-Sym halo pseudo-partition has tables only
+    CsxPartition &hp = pl.is_halo ? no_part : H.parts[i];
     PartDev &P = m->pdev[i];
     memset(&P, 0, sizeof(P));
     if (hp.nnz) CUDA_TRY(cudaMemcpy(m->d_values + pl.val_base, hp.values.data(), (size_t)hp.nnz * 8, cudaMemcpyHostToDevice));
@@ -539,13 +513,18 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     P.values = m->d_values;
     P.ctl_end = (const uint8_t *)dc + std::max<uint64_t>(L.total_ctl, 16);
     P.values_end = m->d_values + std::max<uint64_t>(L.total_values, 1);
-    uint32_t *tx = nullptr; XDesc *xd = nullptr; ChunkEntry *ch = nullptr; uint16_t *uo = nullptr;
-    if (dev_copy(m, pl.chunks.data(), pl.chunks.size(), &ch)) return -1;
-    if (dev_copy(m, pl.uoffs.data(), pl.uoffs.size(), &uo)) return -1;
-    P.uoffs = uo;
+    uint32_t *tx = nullptr; XDesc *xd = nullptr;
     if (dev_copy(m, pl.tile_xoff.data(), pl.tile_xoff.size(), &tx)) return -1;
     if (dev_copy(m, pl.xdesc.data(), pl.xdesc.size(), &xd)) return -1;
-    P.chunks = ch; P.nchunks = (uint32_t)pl.chunks.size();
+    if (!pl.bimg.empty()) {   // CSX-Sym block image table
+      uint32_t *bp = nullptr; BlockImage *bi = nullptr;
+      if (dev_copy(m, pl.bimg_ptr.data(), pl.bimg_ptr.size(), &bp)) return -1;
+      if (dev_copy(m, pl.bimg.data(), pl.bimg.size(), &bi)) return -1;
+      static_assert(sizeof(BlockImage) == sizeof(uint2), "block image layout");
+      P.bimg_ptr = bp; P.bimg = (const uint2 *)bi; P.bimg_j0 = pl.bimg_j0;
+      P.bimg_align = L.bimg_align; P.bimg_rows = L.bimg_rows;
+      tables += (int64_t)pl.bimg_ptr.size() * 4 + (int64_t)pl.bimg.size() * 8;
+    }
     if (!pl.sk_chunks.empty()) {   // stream kernel tables
       SkEntry *se = nullptr; uint16_t *so = nullptr; int32_t *fr = nullptr; uint32_t *fp = nullptr, *fi = nullptr; long long *gp = nullptr;
       if (dev_copy(m, pl.sk_chunks.data(), pl.sk_chunks.size(), &se)) return -1;
@@ -568,7 +547,7 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
                 (int64_t)pl.sk_fix_rows.size() * 8 + (int64_t)pl.sk_fix_idx.size() * 4 + (int64_t)pl.sk_scratch * 16;
     }
     P.tile_xoff = tx; P.xdesc = (const uint4 *)xd; P.ktab = d_ktab;
-    if (H.symmetric) {
+    if (H.symmetric && !pl.is_halo) {
       double *dd = nullptr;
       if (dev_copy(m, hp.dvalues.data(), hp.dvalues.size(), &dd)) return -1;
       P.dvalues = dd;
@@ -578,23 +557,18 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     P.full_colind = L.full_colind;
     P.rpt = pl.rpt;
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
-    nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;
+    nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;   // halo rows are written too
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
-    tables += (int64_t)pl.chunks.size() * (int64_t)sizeof(ChunkEntry) + (int64_t)pl.uoffs.size() * 2;
     if (pl.nrows) {
       if (!pl.sk_chunks.empty())
         launches += 1 + ((pl.sk_fix_rows.empty() && pl.sk_gaps.empty()) ? 0 : 1) + (pl.xdesc.empty() ? 0 : 1);
-      else launches += 1 + (pl.chunks.empty() ? 0 : 1);
+      else launches += 1;
     }
-    m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
-    if (free_host) std::vector<double>().swap(hp.values);
+    if (!pl.is_halo) m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
+    if (free_host && !pl.is_halo) std::vector<double>().swap(hp.values);
   }
-  if (H.symmetric && (int)H.parts.size() != H.nparts_total && !H.parts.empty()) {
-    // transposed updates of the local lower triangle reach rows [col_min, first local row) of lower ranks
-    int64_t first_row = H.parts.front().row_start, lo = first_row;
-    for (auto &p : H.parts) if (p.col_max >= p.col_min) lo = std::min(lo, p.col_min);
-    m->sym_halo_lo = lo; m->sym_halo_hi = first_row;
-  }
+  // CSX-Sym, partial device: transposed updates of the local lower triangle reach rows of lower ranks (gpu_layout.cpp)
+  m->sym_halo_lo = L.halo_lo; m->sym_halo_hi = L.halo_hi;
   if (!H.symmetric) build_slabs(m);
   m->bytes[CSXB_B_VALUES] = nnz_stored * 8;
   m->bytes[CSXB_B_CTL] = ctl_bytes;
@@ -666,18 +640,6 @@ static void launch_gather_xe(const PartDev &P0, const PartLayout &pl, const doub
     else csx_spmv_xe_kernel<false, 1, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
   }
 }
-// Launches kernel 2 over chunks [c0, c1) of one partition.
-template <class XP>
-static void launch_chunks(const PartDev &P0, bool sym, uint32_t c0, uint32_t c1, const double *x, double *y, double alpha,
-                          cudaStream_t s, const XP &X) {
-  if (c1 <= c0) return;
-  PartDev P = P0;
-  P.chunk0 = c0; P.nchunks = c1;
-  const unsigned grid = (unsigned)((c1 - c0 + CHUNK_WARPS - 1) / CHUNK_WARPS);
-  if (sym) csx_chunk_kernel<true, XP><<<grid, CHUNK_WARPS * 32, 0, s>>>(P, x, y, alpha, X);
-  else csx_chunk_kernel<false, XP><<<grid, CHUNK_WARPS * 32, 0, s>>>(P, x, y, alpha, X);
-}
-
 // Launches the stream kernel over chunks [c0, c1) of one partition: the instantiation is chosen by the partition's
 // pattern set (kinds of units, rows of a block task) — the counterpart of the per-partition JIT (CsxJit.hpp:359-732).
 static int launch_stream(const PartDev &P0, const PartLayout &pl, uint32_t c0, uint32_t c1, const SkIO &io, double alpha, double beta,
@@ -707,16 +669,20 @@ static void launch_fixup(const PartDev &P0, uint32_t f0, uint32_t f1, uint32_t g
 }
 // One partition of a non-symmetric matrix, whole: stream kernel (writes y), fix-up, then the gather over the table,
 // which adds (beta = 1).  Without stream chunks the gather kernel alone writes y.
-template <class XP>
+// CSX-Sym: the stream kernel and the direct table units are phase 1 (every partition writes its own rows), the
+// images of all units — gathered by the owners of the rows they update — and the diagonal are phase 2; both
+// phases of a row are the work of the thread that owns it, so there is nothing to reduce on one device.
+template <bool SYM, class XP>
 static int run_partition(const PartDev &P, const PartLayout &pl, const SkIO &io, double alpha, double beta, int overwrite,
                          cudaStream_t s, const XP &X) {
   if (pl.sk_chunks.empty()) {
-    launch_gather<false>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, beta, overwrite, s, X);
+    launch_gather<SYM>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, beta, overwrite, s, X);
     return 0;
   }
   if (launch_stream(P, pl, 0, (uint32_t)pl.sk_chunks.size(), io, alpha, beta, overwrite, s)) return -1;
   launch_fixup(P, 0, (uint32_t)pl.sk_fix_rows.size(), 0, (uint32_t)pl.sk_gaps.size(), 0, pl.nrows, io, alpha, beta, overwrite, s);
-  if (!pl.xdesc.empty()) launch_gather<false>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, 1.0, 0, s, X);
+  // CSX-Sym: the gather kernel always runs (diagonal, images)
+  if (SYM || !pl.xdesc.empty()) launch_gather<SYM>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, 1.0, 0, s, X);
   return 0;
 }
 
@@ -726,22 +692,16 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
   cudaStream_t s = (cudaStream_t)stream;
   const bool sym = m->host.symmetric;
-  if (m->sym_halo_hi > m->sym_halo_lo)   // halo rows owned by other devices: start from zero, the caller reduces them
-    CUDA_TRY(cudaMemsetAsync(d_y + m->sym_halo_lo, 0, (size_t)(m->sym_halo_hi - m->sym_halo_lo) * 8, s));
-  // kernel 1 of every partition first: it initialises y, and under CSX-Sym the chunk kernel of one
-  // partition adds into rows that another partition owns
-  if (!sym) {
-    SkIO io;
-    io.x = d_x; io.y = d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
-    for (size_t i = 0; i < m->pdev.size(); i++)
-      if (run_partition(m->pdev[i], m->layout.parts[i], io, alpha, beta, overwrite, s, NoXchg())) return fail("no stream kernel for the partition's pattern set");
-  } else {
-    for (size_t i = 0; i < m->pdev.size(); i++) {
-      const PartLayout &pl = m->layout.parts[i];
-      launch_gather<true>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, beta, overwrite, s, NoXchg());
-    }
-    for (size_t i = 0; i < m->pdev.size(); i++)
-      launch_chunks(m->pdev[i], sym, 0, (uint32_t)m->layout.parts[i].chunks.size(), d_x, d_y, alpha, s, NoXchg());
+  SkIO io;
+  io.x = d_x; io.y = d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
+  for (size_t i = 0; i < m->pdev.size(); i++) {
+    const PartLayout &pl = m->layout.parts[i];
+    int rc;
+    // CSX-Sym halo rows (owned by other devices): this device's updates of them, for the caller to reduce
+    if (pl.is_halo) { launch_gather<true>(m->pdev[i], pl, 0, pl.ntiles, d_x, d_y, alpha, 0.0, 1, s, NoXchg()); rc = 0; }
+    else if (sym) rc = run_partition<true>(m->pdev[i], pl, io, alpha, beta, overwrite, s, NoXchg());
+    else rc = run_partition<false>(m->pdev[i], pl, io, alpha, beta, overwrite, s, NoXchg());
+    if (rc) return fail("no stream kernel for the partition's pattern set");
   }
   // rows after the last partition's last non-empty row belong to nobody; VecInit(y,0) clears them (CsxKernels.cpp:93)
   if (overwrite && m->host.part_lo + (int)m->host.parts.size() == m->host.nparts_total && m->covered_rows_end < m->host.nrows)
@@ -866,7 +826,7 @@ csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world) {
   unsigned long long *ctrl = (unsigned long long *)((char *)h->base + 2 * vb);
   h->dev.step = ctrl; h->dev.error = ctrl + 1; h->dev.started = ctrl + 2; h->dev.bdone = ctrl + 3; h->dev.flags = ctrl + 16;
   h->dev.rank = rank;
-  for (auto &pl : m->layout.parts) if (!pl.chunks.empty() || !pl.sk_chunks.empty()) h->fused_push = false;
+  for (auto &pl : m->layout.parts) if (!pl.sk_chunks.empty()) h->fused_push = false;
   if (world == 1) {
     xchg_choose_mode(h, 0, (int64_t)h->n);
     h->connected = true;
@@ -984,7 +944,7 @@ int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
     if (X.mode == 1) launch_gather_xe(m->pdev[i], pl, X.vec[h->parity], X.vec[h->parity ^ 1], alpha, h->parity ^ 1, s, X);
-    else if (run_partition(m->pdev[i], pl, io, alpha, 0.0, 1, s, X)) return fail("no stream kernel for the partition's pattern set");
+    else if (run_partition<false>(m->pdev[i], pl, io, alpha, 0.0, 1, s, X)) return fail("no stream kernel for the partition's pattern set");
   }
   if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 4, 256, 0, s>>>(h->dev);
   if (h->tail_hi > h->tail_lo)
@@ -1163,8 +1123,6 @@ int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t
   CUDA_TRY(cudaMemset(dr, 0xff, std::max<size_t>(n, 1) * 4));
   CUDA_TRY(cudaMemset(dcl, 0xff, std::max<size_t>(n, 1) * 4));
   if (pl.ntiles && !pl.xdesc.empty()) csx_decode_gather_kernel<<<(unsigned)pl.ntiles, CTA_THREADS>>>(m->pdev[part], dr, dcl);
-  if (!pl.chunks.empty())
-    csx_decode_chunk_kernel<<<(unsigned)((pl.chunks.size() + CHUNK_WARPS - 1) / CHUNK_WARPS), CHUNK_WARPS * 32>>>(m->pdev[part], dr, dcl);
   if (!pl.sk_chunks.empty())
     csx_stream_decode_kernel<<<(unsigned)((pl.sk_chunks.size() + SK_WARPS - 1) / SK_WARPS), SK_WARPS * 32>>>(m->pdev[part], dr, dcl);
   CUDA_TRY(cudaGetLastError());

@@ -3,9 +3,10 @@
 // fibre emulation of the warp intrinsics (CSXB_EMUL; generic instantiations only — the PTX block of the
 // 4-rows-per-thread diagonal variant is device-only).  Test infrastructure never ships in the product library.
 #pragma once
-#include "chunk_kernel.cuh"
+#include "part_dev.cuh"
 
-// Table units are vertical / diagonal / anti-diagonal runs (gpu_layout.hpp: goes_to_xdt).
+// Table units are vertical / diagonal / anti-diagonal runs (gpu_layout.hpp: goes_to_xdt); under CSX-Sym the table
+// also lists the transposed image of every unit, stream units included (horizontal runs, blocks, single elements).
 // Op::add(device-wide value index, x index) for every element of descriptor d that contributes to `myrow`.
 template <bool SYM, class Op>
 __device__ __forceinline__ void gather_desc(const uint4 d, const KindEntry *__restrict__ ktab, int myrow, Op &op) {
@@ -24,6 +25,22 @@ __device__ __forceinline__ void gather_desc(const uint4 d, const KindEntry *__re
     // vert_sym_tmpl.c: cur[x_indx] += sum v_k x[y_indx + k*delta]
     if (myrow != c) return;
     for (uint32_t k = 0; k < size; k++) op.add(voff + k, r + (int)(k * delta));
+  } else if (kind == K_HORIZ) {   // horiz_sym_tmpl.c: element k at (r, c + k*delta) adds v_k * x[r] to y[c + k*delta]
+    const int u = myrow - c;
+    if (u < 0) return;
+    const uint32_t k = (uint32_t)u / delta;
+    if (k * delta != (uint32_t)u || k >= size) return;
+    op.add(voff + k, r);
+  } else if (kind == K_BCOL) {    // block_col_sym_tmpl.c: rows x align block, row-major; y[c + j] += sum_a v[a][j] * x[r + a]
+    const uint32_t align = (__ldg(&ktab[meta & 0xffff].kind_align) >> 8) & 0xff;
+    const uint32_t j = (uint32_t)(myrow - c);
+    if (myrow < c || j >= align) return;
+    for (uint32_t a = 0; a * align < size; a++) op.add(voff + a * align + j, r + (int)a);
+  } else if (kind == K_BROW) {    // block_row_sym_tmpl.c: align x cols block, column-major; y[c + j] += sum_a v[j][a] * x[r + a]
+    const uint32_t align = (__ldg(&ktab[meta & 0xffff].kind_align) >> 8) & 0xff;
+    const uint32_t j = (uint32_t)(myrow - c);
+    if (myrow < c || j * align >= size) return;
+    for (uint32_t a = 0; a < align; a++) op.add(voff + j * align + a, r + (int)a);
   } else {  // diag_sym_tmpl.c, rdiag_sym_tmpl.c
     const int u = kind == K_DIAG ? myrow - c : c - myrow;
     if (u < 0) return;
@@ -43,8 +60,12 @@ __device__ __forceinline__ bool desc_touches(const uint4 d, const KindEntry *__r
   int lo, hi;
   if (!SYM || !(meta & XD_TRANSPOSED)) { lo = r; hi = r + span; }
   else if (kind == K_VERT) { lo = hi = c; }
-  else if (kind == K_DIAG) { lo = c; hi = c + span; }
-  else { lo = c - span; hi = c; }
+  else if (kind == K_DIAG || kind == K_HORIZ) { lo = c; hi = c + span; }
+  else if (kind == K_ADIAG) { lo = c - span; hi = c; }
+  else {   // block image: its columns
+    const uint32_t align = (__ldg(&ktab[meta & 0xffff].kind_align) >> 8) & 0xff;
+    lo = c; hi = c + (int)(kind == K_BCOL ? align : size / align) - 1;
+  }
   return lo <= row_hi && hi >= row_lo;
 }
 
@@ -64,7 +85,7 @@ __device__ __forceinline__ bool linear_probe(const uint4 d, const KindEntry *__r
   }
   if (k >= size) return false;
   vi = d.x + k;
-  xi = !tr ? (kind == K_VERT ? c : (kind == K_DIAG ? c + t : c - t)) : r + t;
+  xi = !tr ? (kind == K_VERT ? c : (kind == K_DIAG ? c + t : c - t)) : (kind == K_HORIZ ? r : r + t);
   return true;
 }
 
@@ -189,9 +210,9 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
           for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
           continue;
         }
-        // one element per row, except the transposed image of a vertical unit, which folds the whole
-        // unit into the single row of its column
-        if (!(SYM && ((d.w >> 24) & 0xf) == K_VERT && (d.w & XD_TRANSPOSED))) {
+        // one element per row, except the transposed images of vertical and block units, which fold several
+        // elements into one row
+        if (!(SYM && (d.w & XD_TRANSPOSED) && (((d.w >> 24) & 0xf) == K_VERT || ((d.w >> 24) & 0xf) >= K_BROW))) {
           double v[RPT], xv[RPT];  // issue all RPT value / x loads of this unit before using them
 #pragma unroll
           for (int k = 0; k < RPT; k++) {
@@ -213,13 +234,33 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
     }
   }
 
+  if (SYM && P.bimg_ptr) {
+    // images of block-column units of the dominant shape: every row finds the units that update it through its aligned
+    // block row; y[c + j] += sum_a v[a][j] * x[r + a] (block_col_sym_tmpl.c), entries in source order
+    const int BA = P.bimg_align, BR = P.bimg_rows;
+    const double *__restrict__ values = P.values;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const long long lrow = lrow0 + k * 32 + lane;
+      if (lrow < P.nrows) {
+        const long long g = P.row_start + lrow, J = g / BA;
+        const int j = (int)(g - J * BA);
+        const uint32_t e0 = __ldg(P.bimg_ptr + (J - P.bimg_j0)), e1 = __ldg(P.bimg_ptr + (J - P.bimg_j0) + 1);
+        for (uint32_t e = e0; e < e1; e++) {
+          const uint2 b = __ldg(P.bimg + e);
+          for (int a = 0; a < BR; a++) acc[k] += __ldg(values + b.x + a * BA + j) * __ldg(x + (int)b.y + a);
+        }
+      }
+    }
+  }
+
 #pragma unroll
   for (int k = 0; k < RPT; k++) {
     const long long lrow = lrow0 + k * 32 + lane;
     if (lrow < P.nrows) {
       const long long g = P.row_start + lrow;
       double a = acc[k];
-      if (SYM) a += __ldg(P.dvalues + lrow) * __ldg(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
+      if (SYM && P.dvalues) a += __ldg(P.dvalues + lrow) * __ldg(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
       const double r = overwrite ? alpha * a : alpha * a + beta * y[g];
       y[g] = r;
       if constexpr (PUSH) {   // the exchange: rows another rank's partition reads go straight into its next x.

@@ -62,77 +62,6 @@ struct Pending { int64_t part; int64_t tile; XDesc d; };
 // rows per thread of a partition's tiles (a later partition's value is needed while an earlier one is decoded)
 inline int tile_rpt(int64_t nrows, int forced) { return forced ? forced : (nrows >= (int64_t(1) << 20) ? 4 : 1); }
 
-// Walks the unit heads once and picks the slice length of the chunk kernel for this partition: every lane of
-// a warp handles one slice per round, a round lasts as long as its longest slice, and every slice carries a
-// fixed cost (setup, cursor scan, row reduction) of about C0 loop iterations.
-std::string choose_slice(const CsxPartition &cp, const CsxMatrix &m, size_t nid, PartLayout &L) {
-  std::vector<uint64_t> hist(64 * 256, 0);
-  const uint8_t *ctl = cp.ctl.data();
-  uint64_t p = 0, end = cp.ctl.size();
-  while (p < end) {
-    if (p + 2 > end) return "ctl stream truncated";
-    const uint8_t flags = ctl[p++], size = ctl[p++];
-    if ((flags & 0x80) && (flags & 0x40)) get_varint(ctl, p);
-    if (m.full_colind) p += 4; else get_varint(ctl, p);
-    const uint32_t id = flags & 0x3f;
-    if (id >= nid) return "ctl stream uses an unmapped unit id";
-    const uint32_t kind = L.idtab[id].kind_align & 0xff;
-    if (size == 0) return "ctl unit of size 0";
-    if (kind <= K_DELTA64) p += (uint64_t)(size - 1) * L.idtab[id].delta;
-    if (p > end) return "ctl stream truncated";
-    if (!goes_to_xdt(kind, size)) hist[id * 256 + size]++;
-  }
-  static const int cand[] = {4, 8, 12, 16, 24, 32};
-  const double C0 = 12.0;
-  int best = 16;
-  double best_cost = -1.0;
-  for (int S : cand) {
-    if (m.slice_elems && S != cand[0]) break;
-    if (m.slice_elems) S = m.slice_elems;
-    IdEntry tab[64];
-    for (size_t id = 0; id < nid; id++) {
-      tab[id] = L.idtab[id];
-      const uint32_t kind = tab[id].kind_align & 0xff, align = (tab[id].kind_align >> 8) & 0xff;
-      uint32_t sl = (kind == K_BROW || kind == K_BCOL) ? std::max<uint32_t>(1, (uint32_t)S / align) : (uint32_t)S;
-      tab[id].sl = sl;
-      tab[id].recip = (65536 + sl - 1) / sl;
-    }
-    double slices = 0.0;
-    std::vector<std::pair<uint32_t, double>> lens;   // (slice length, number of such slices)
-    for (size_t id = 0; id < nid; id++) {
-      const uint32_t kind = tab[id].kind_align & 0xff, align = (tab[id].kind_align >> 8) & 0xff;
-      for (uint32_t size = 1; size < 256; size++) {
-        const uint64_t n = hist[id * 256 + size];
-        if (!n) continue;
-        const uint32_t nsl = unit_slices(kind, size, tab[id].delta, tab[id]);
-        const uint32_t len = (kind == K_BROW || kind == K_BCOL) ? std::min<uint32_t>(size, tab[id].sl * align)
-                                                               : std::min<uint32_t>(size, tab[id].sl);
-        slices += (double)n * nsl;
-        lens.push_back(std::make_pair(len, (double)n * nsl));
-      }
-    }
-    // longest slice among those that are not rare (a round is as long as its longest slice)
-    std::sort(lens.begin(), lens.end());
-    double tail = 0.0;
-    uint32_t lmax = 1;
-    for (size_t i = lens.size(); i-- > 0;) {
-      tail += lens[i].second;
-      if (tail >= 0.02 * slices) { lmax = lens[i].first; break; }
-    }
-    const double cost = slices * (C0 + (double)((lmax + 3) / 4 * 4));
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = S; }
-  }
-  L.slice = best;
-  for (size_t id = 0; id < nid; id++) {
-    const uint32_t kind = L.idtab[id].kind_align & 0xff, align = (L.idtab[id].kind_align >> 8) & 0xff;
-    const uint32_t sl = (kind == K_BROW || kind == K_BCOL) ? std::max<uint32_t>(1, (uint32_t)best / align) : (uint32_t)best;
-    L.idtab[id].sl = sl;
-    L.idtab[id].recip = (65536 + sl - 1) / sl;
-  }
-  return "";
-}
-
-
 // ---- stream kernel chunking (see gpu_layout.hpp) -----------------------------------------------------------
 struct SkUnit {
   uint64_t off, end;        // ctl offsets of the unit head and of the byte behind the unit
@@ -270,39 +199,80 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
   out = DeviceLayout();
   out.symmetric = m.symmetric;
   out.full_colind = m.full_colind;
-  size_t np = m.parts.size();
-  out.parts.resize(np);
-  std::map<std::pair<uint32_t, uint32_t>, uint32_t> kindex;
-  std::vector<Pending> pend;
-
-  // global row -> (local partition, tile); partitions are contiguous and ordered
+  const size_t np = m.parts.size();
+  // CSX-Sym with only some partitions on this device: the transposed updates of the local lower triangle reach rows
+  // [col_min, first local row) of lower ranks.  Those rows get a pseudo-partition of their own, so that their updates
+  // are gathered like every other row's; the caller reduces them across devices (the cross-device form of the
+  // reference's local vectors + map reduction, CsxSpmv.cpp:37-50).
+  if (m.symmetric && np && (int)np != m.nparts_total) {
+    const int64_t first_row = m.parts.front().row_start;
+    int64_t lo = first_row;
+    for (auto &p : m.parts) if (p.col_max >= p.col_min) lo = std::min(lo, p.col_min);
+    out.halo_lo = lo; out.halo_hi = first_row;
+  }
+  const bool has_halo = out.halo_hi > out.halo_lo;
+  const size_t nq = np + (has_halo ? 1 : 0);   // row owners on this device
+  out.parts.resize(nq);
+  auto q_start = [&](size_t q) { return q < np ? m.parts[q].row_start : out.halo_lo; };
+  auto q_rows = [&](size_t q) { return q < np ? m.parts[q].nrows : out.halo_hi - out.halo_lo; };
+  auto q_tile = [&](size_t q) { return (int64_t)CTA_THREADS * tile_rpt(q_rows(q), m.rows_per_thread); };
+  // global row -> owner on this device; partitions are contiguous and ordered
   auto owner_of = [&](int64_t grow) -> int64_t {
-    for (size_t q = 0; q < np; q++)
-      if (grow >= m.parts[q].row_start && grow < m.parts[q].row_start + m.parts[q].nrows) return (int64_t)q;
+    for (size_t q = 0; q < nq; q++)
+      if (grow >= q_start(q) && grow < q_start(q) + q_rows(q)) return (int64_t)q;
     return -1;
   };
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> kindex;
+  auto kind_index = [&](const KindEntry &ke) -> int64_t {
+    auto key = std::make_pair(ke.kind_align, ke.delta);
+    auto it = kindex.find(key);
+    if (it == kindex.end()) {
+      if (out.ktab.size() >= 65535) return -1;
+      it = kindex.insert(std::make_pair(key, (uint32_t)out.ktab.size())).first;
+      out.ktab.push_back(ke);
+    }
+    return it->second;
+  };
+  std::vector<Pending> pend;
+  // descriptor `d` under every tile of the owners of global rows [lo, hi]
+  auto list_rows = [&](const XDesc &d, int64_t lo, int64_t hi, std::vector<Pending> &to) -> bool {
+    int64_t g = lo;
+    while (g <= hi) {
+      const int64_t q = owner_of(g);
+      if (q < 0) return false;
+      const int64_t rel = g - q_start((size_t)q), qt = q_tile((size_t)q);
+      to.push_back(Pending{q, rel / qt, d});
+      g = std::min(q_start((size_t)q) + (rel / qt + 1) * qt, q_start((size_t)q) + q_rows((size_t)q));   // next tile or next owner
+    }
+    return true;
+  };
+  // CSX-Sym: images of block units wait until the device's dominant block-column shape is known
+  struct BlockTmp { XDesc d; uint32_t kind, align, other; int64_t cmin, cmax; };
+  std::vector<BlockTmp> blocks;
 
   uint64_t vbase = 0, cbase = 0;
-  for (size_t pi = 0; pi < np; pi++) {
-    const CsxPartition &cp = m.parts[pi];
+  for (size_t pi = 0; pi < nq; pi++) {
     PartLayout &L = out.parts[pi];
-    L.nrows = cp.nrows; L.row_start = cp.row_start; L.nnz = cp.nnz; L.ctl_size = (int64_t)cp.ctl.size();
+    L.nrows = q_rows(pi); L.row_start = q_start(pi);
     L.val_base = vbase; L.ctl_base = cbase;
-    vbase += (uint64_t)cp.nnz;
-    cbase += ((uint64_t)cp.ctl.size() + CTL_PAD + 15) & ~uint64_t(15);
     // big partitions: 4 rows per thread (more loads in flight per thread, fewer carry-in descriptors)
-    L.rpt = tile_rpt(cp.nrows, m.rows_per_thread);
+    L.rpt = tile_rpt(L.nrows, m.rows_per_thread);
     const int64_t TILE_ROWS = L.tile_rows();
-    L.ntiles = (cp.nrows + TILE_ROWS - 1) / TILE_ROWS;
+    L.ntiles = (L.nrows + TILE_ROWS - 1) / TILE_ROWS;
     L.tile_xoff.assign((size_t)L.ntiles + 1, 0);
     L.tile_cmin.assign((size_t)L.ntiles, INT32_MAX);
     L.tile_cmax.assign((size_t)L.ntiles, -1);
+    memset(L.idtab, 0, sizeof(L.idtab));
+    if (pi >= np) { L.is_halo = true; continue; }
+    const CsxPartition &cp = m.parts[pi];
+    L.nnz = cp.nnz; L.ctl_size = (int64_t)cp.ctl.size();
+    vbase += (uint64_t)cp.nnz;
+    cbase += ((uint64_t)cp.ctl.size() + CTL_PAD + 15) & ~uint64_t(15);
     if (m.symmetric)   // the diagonal term reads x at the row itself
       for (int64_t t = 0; t < L.ntiles; t++) {
         L.tile_cmin[t] = (int32_t)(cp.row_start + t * TILE_ROWS);
         L.tile_cmax[t] = (int32_t)(cp.row_start + std::min<int64_t>(cp.nrows, (t + 1) * TILE_ROWS) - 1);
       }
-    memset(L.idtab, 0, sizeof(L.idtab));
     uint32_t id2k[64];
     size_t nid = 0;
     for (; nid < cp.id_map.size() && cp.id_map[nid] != -1; nid++) {
@@ -310,41 +280,28 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       KindEntry ke;
       if (!classify(cp.id_map[nid], ke)) return "unsupported pattern id " + std::to_string(cp.id_map[nid]);
       L.idtab[nid] = IdEntry{ke.kind_align, ke.delta, 1, 65536};
-      auto key = std::make_pair(ke.kind_align, ke.delta);
-      auto it = kindex.find(key);
-      if (it == kindex.end()) {
-        if (out.ktab.size() >= 65535) return "too many distinct unit kinds on one device";
-        it = kindex.insert(std::make_pair(key, (uint32_t)out.ktab.size())).first;
-        out.ktab.push_back(ke);
-      }
-      id2k[nid] = it->second;
+      const int64_t ki = kind_index(ke);
+      if (ki < 0) return "too many distinct unit kinds on one device";
+      id2k[nid] = (uint32_t)ki;
     }
-
-    const uint8_t *ctl = cp.ctl.data();
-    uint64_t p = 0, end = cp.ctl.size();
-    int64_t row = 0, col = 0, v = 0;
-    bool first = true;
-    std::string serr = choose_slice(cp, m, nid, L);
-    if (!serr.empty()) return serr;
-    SkBuilder sk(L, cp.nrows);
-    if (!m.symmetric) {   // task shapes of the stream kernel (sk_unit_tasks)
-      for (size_t id = 0; id < nid; id++) {
-        IdEntry &ie = L.idtab[id];
-        const uint32_t kind = ie.kind_align & 0xff, align = (ie.kind_align >> 8) & 0xff;
-        uint32_t sl = 1;
-        if (kind <= K_HORIZ) sl = SK_RL_E;
-        else if (kind == K_BROW) { sl = std::min<uint32_t>(SK_BLK_LINES, std::max<uint32_t>(1, SK_BLK_E / align)); L.sk_rows = std::max<int>(L.sk_rows, (int)align); }
-        else if (kind == K_BCOL) {   // rows of the unit spread evenly over its tasks
-          const uint32_t tmax = std::min<uint32_t>(SK_BLK_LINES, std::max<uint32_t>(1, SK_BLK_E / align));
-          const uint32_t nt = (ie.delta + tmax - 1) / tmax;
-          sl = (ie.delta + nt - 1) / nt;
-          L.sk_rows = std::max<int>(L.sk_rows, (int)sl);
-        }
-        ie.sl = sl;
-        ie.recip = (65536 + sl - 1) / sl;
-        if (kind <= K_HORIZ || kind >= K_BROW) L.sk_kmask |= 1u << kind;
+    // task shapes of the stream kernel (sk_unit_tasks)
+    for (size_t id = 0; id < nid; id++) {
+      IdEntry &ie = L.idtab[id];
+      const uint32_t kind = ie.kind_align & 0xff, align = (ie.kind_align >> 8) & 0xff;
+      uint32_t sl = 1;
+      if (kind <= K_HORIZ) sl = SK_RL_E;
+      else if (kind == K_BROW) { sl = std::min<uint32_t>(SK_BLK_LINES, std::max<uint32_t>(1, SK_BLK_E / align)); L.sk_rows = std::max<int>(L.sk_rows, (int)align); }
+      else if (kind == K_BCOL) {   // rows of the unit spread evenly over its tasks
+        const uint32_t tmax = std::min<uint32_t>(SK_BLK_LINES, std::max<uint32_t>(1, SK_BLK_E / align));
+        const uint32_t nt = (ie.delta + tmax - 1) / tmax;
+        sl = (ie.delta + nt - 1) / nt;
+        L.sk_rows = std::max<int>(L.sk_rows, (int)sl);
       }
-      // block tasks of one compile-time shape (the kernel is instantiated for the common ones)
+      ie.sl = sl;
+      ie.recip = (65536 + sl - 1) / sl;
+      if (kind <= K_HORIZ || kind >= K_BROW) L.sk_kmask |= 1u << kind;
+    }
+    {   // block tasks of one compile-time shape (the kernel is instantiated for the common ones)
       int bc = -1, brc = -1;
       for (size_t id = 0; id < nid; id++) {
         const IdEntry &ie = L.idtab[id];
@@ -359,24 +316,28 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       }
       L.sk_bc = std::max(bc, 0); L.sk_brc = std::max(brc, 0);
     }
-    // A partition whose chunk-kernel share is tiny (stencil matrices: a few boundary elements next to
+
+    const uint8_t *ctl = cp.ctl.data();
+    uint64_t p = 0, end = cp.ctl.size();
+    int64_t row = 0, col = 0, v = 0;
+    bool first = true;
+    SkBuilder sk(L, cp.nrows);
+    // A partition whose stream-kernel share is tiny (stencil matrices: a few boundary elements next to
     // millions of diagonal units) gets those elements as one-element table units instead; that saves the
     // second kernel launch.  Coordinates are collected while the share stays under the cap.
     struct Single { int64_t row, col, v; };
     std::vector<Single> singles;
     const size_t single_cap = (size_t)(cp.nnz / 256);
     bool singles_ok = true;
-    // open chunk of consecutive chunk-kernel units
-    bool open = false;
-    int64_t ch_elems = 0, ch_units = 0, ch_slices = 0;
-    uint64_t ch_start = 0;
-    auto close_chunk = [&](uint64_t at) {
-      if (open) {
-        L.chunks.back().counts = (uint32_t)(at - ch_start) | ((uint32_t)ch_elems << 12) | ((uint32_t)ch_units << 22);
-        open = false;
-      }
-    };
+    // CSX-Sym: images of this partition's stream units (dropped again if the units are folded into the table)
+    std::vector<Pending> simg;
+    const size_t blocks_before = blocks.size();
+    KindEntry ke_single{K_DIAG, 1};
+    const int64_t k_single = kind_index(ke_single);
+    if (k_single < 0) return "too many distinct unit kinds on one device";
+    int64_t ecols[256];
     while (p < end) {
+      if (p + 2 > end) return "ctl stream truncated";
       uint64_t unit_off = p;
       uint8_t flags = ctl[p++], size = ctl[p++];
       bool nr = (flags & 0x80) != 0;
@@ -400,11 +361,13 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       // geometry: rows spanned below the first one, column range
       int64_t span = 0, cmin = start_col, cmax = start_col;
       if (kind <= K_DELTA64) {
+        ecols[0] = col;
         for (int k = 1; k < size; k++) {
           uint64_t d = 0;
           memcpy(&d, ctl + p, delta);   // little-endian fixed-width deltas
           p += delta;
           col += (int64_t)d;
+          ecols[k] = col;
         }
         cmax = col;
       } else if (kind == K_HORIZ) { col += (int64_t)(size - 1) * delta; cmax = col; }
@@ -429,60 +392,36 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         }
       }
 
-      // CSX-Sym with only some partitions on this device: a unit whose transposed image reaches rows of
-      // another device cannot be gathered by a local owner; the chunk kernel adds it to those rows of the
-      // local y instead and the caller reduces the halo across devices.
-      const bool image_local = !m.symmetric || (owner_of(cmin) >= 0 && owner_of(cmax) >= 0);
-      // non-symmetric partitions: every vertical / diagonal / anti-diagonal unit is a table unit, everything else
-      // belongs to the stream kernel, which also parses the heads of the table units (they move the cursor)
-      const bool to_table = m.symmetric ? (goes_to_xdt(kind, size) && image_local) : (kind >= K_VERT && kind <= K_ADIAG);
-      if (!m.symmetric) {
+      // Vertical / diagonal / anti-diagonal units are table units; everything else belongs to the stream kernel,
+      // which also parses the heads of the table units (they move the column cursor).
+      const bool to_table = goes_to_xdt(kind);
+      {
         const IdEntry &ie = L.idtab[id];
         SkUnit su;
         su.off = unit_off; su.end = p; su.size = size;
         su.ntasks = sk_unit_tasks(kind, size, delta, ie.sl, ie.recip);
-        su.row = row; su.reach = span; su.cmin = cmin; su.cmax = cmax; su.val = v; su.cursor_before = cursor_before;
+        su.row = row; su.reach = to_table ? 0 : span;   // the stream kernel adds nothing for a table unit
+        su.cmin = cmin; su.cmax = cmax; su.val = v; su.cursor_before = cursor_before;
         su.multi_bcol = kind == K_BCOL && su.ntasks > 1;
+        su.round_end = false;
         if (L.sk_uoffs.size() >= 0xfffffff0ull) return "unit-offset table too large";
         sk.add(su);
       }
+      XDesc d;
+      d.voff = (uint32_t)(L.val_base + (uint64_t)v);
+      d.row = (int32_t)(cp.row_start + row);
+      d.col = (int32_t)start_col;
+      d.meta = id2k[id] | ((uint32_t)size << 16) | (kind << 24);
+      if (delta == 1) d.meta |= XD_DELTA1;
       if (!to_table) {
-        if (m.symmetric) {
-        // chunk kernel: extend the open chunk or start a new one at this unit
-        uint64_t ubytes = p - unit_off;
-        const int64_t nsl = unit_slices(kind, size, delta, L.idtab[id]);
-        if (open && (ch_elems + size > CHUNK_MAX_ELEMS || ch_units + 1 > CHUNK_MAX_UNITS ||
-                     ch_slices + nsl > CHUNK_MAX_SLICES ||
-                     (unit_off - ch_start) + ubytes > (uint64_t)CHUNK_MAX_BYTES))
-          close_chunk(unit_off);
-        if (!open) {
-          if (ubytes > (uint64_t)CHUNK_MAX_BYTES || nsl > CHUNK_MAX_SLICES) return "ctl unit exceeds the chunk limits";
-          if (L.uoffs.size() >= 0xffffffffull) return "unit-offset table too large";
-          ChunkEntry ce;
-          ce.ctl_off = unit_off; ce.val_off = (uint32_t)v; ce.cursor = (uint32_t)cursor_before;
-          ce.row = (int32_t)row; ce.counts = 0; ce.uoff = (uint32_t)L.uoffs.size(); ce.pad = 0;
-          L.chunks.push_back(ce);
-          L.chunk_last_row.push_back((int32_t)row);
-          open = true; ch_elems = 0; ch_units = 0; ch_slices = 0; ch_start = unit_off;
-        }
-        L.chunk_last_row.back() = std::max<int32_t>(L.chunk_last_row.back(), (int32_t)(row + span));
-        L.uoffs.push_back((uint16_t)(unit_off - ch_start));
-        ch_elems += size; ch_units += 1; ch_slices += nsl;
-        }
         L.has_flat = true;
         L.flat_elems += size;
-        if (singles_ok && image_local && singles.size() + size <= single_cap) {
-          // element coordinates of this unit (same geometry as the chunk kernel)
-          int64_t cc = start_col;
+        if (singles_ok && singles.size() + size <= single_cap) {
+          // element coordinates of this unit (same geometry as the stream kernel)
           for (int k = 0; k < size; k++) {
             int64_t er = row, ec = start_col;
-            if (kind <= K_DELTA64) {
-              if (k) { uint64_t d = 0; memcpy(&d, ctl + (p - body) + (uint64_t)(k - 1) * delta, delta); cc += (int64_t)d; }
-              ec = cc;
-            } else if (kind == K_HORIZ) ec = start_col + (int64_t)k * delta;
-            else if (kind == K_VERT) er = row + (int64_t)k * delta;
-            else if (kind == K_DIAG) { er = row + (int64_t)k * delta; ec = start_col + (int64_t)k * delta; }
-            else if (kind == K_ADIAG) { er = row + (int64_t)k * delta; ec = start_col - (int64_t)k * delta; }
+            if (kind <= K_DELTA64) ec = ecols[k];
+            else if (kind == K_HORIZ) ec = start_col + (int64_t)k * delta;
             else if (kind == K_BROW) { er = row + k % (int)align; ec = start_col + k / (int)align; }
             else { er = row + k / (int)align; ec = start_col + k % (int)align; }
             singles.push_back(Single{er, ec, v + k});
@@ -490,74 +429,111 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         } else {
           singles_ok = false;
         }
+        if (m.symmetric) {   // transposed image of a stream unit: y[col] += v * x[row], gathered by the owners of its columns
+          XDesc td = d;
+          td.meta |= XD_TRANSPOSED;
+          if (kind <= K_DELTA64) {   // irregular columns: one single-element image per element
+            for (int k = 0; k < size; k++) {
+              XDesc e;
+              e.voff = d.voff + (uint32_t)k; e.row = d.row; e.col = (int32_t)ecols[k];
+              e.meta = (uint32_t)k_single | (1u << 16) | ((uint32_t)K_DIAG << 24) | XD_DELTA1 | XD_TRANSPOSED;
+              if (!list_rows(e, ecols[k], ecols[k], simg)) return "symmetric update targets a row that is not on this device";
+            }
+          } else if (kind == K_HORIZ) {
+            if (!list_rows(td, cmin, cmax, simg)) return "symmetric update targets a row that is not on this device";
+          } else {
+            blocks.push_back(BlockTmp{td, kind, align, delta, cmin, cmax});
+          }
+        }
       } else {
-        close_chunk(unit_off);   // the chunk kernel never sees table units
-        XDesc d;
-        d.voff = (uint32_t)(L.val_base + (uint64_t)v);
-        d.row = (int32_t)(cp.row_start + row);
-        d.col = (int32_t)start_col;
-        d.meta = id2k[id] | ((uint32_t)size << 16) | (kind << 24);
-        if (delta == 1) d.meta |= XD_DELTA1;
         for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) pend.push_back(Pending{(int64_t)pi, t, d});
         if (m.symmetric) {  // transposed image, listed under the tiles of its columns
           XDesc td = d;
           td.meta |= XD_TRANSPOSED;
-          int64_t g = cmin;
-          while (g <= cmax) {
-            int64_t q = owner_of(g);
-            if (q < 0) return "symmetric update targets a row that is not on this device";
-            int64_t rel = g - m.parts[q].row_start;
-            const int64_t qt = (int64_t)CTA_THREADS * tile_rpt(m.parts[q].nrows, m.rows_per_thread);
-            pend.push_back(Pending{q, rel / qt, td});
-            // first row of the next tile, or of the next partition if that comes first
-            g = std::min(m.parts[q].row_start + (rel / qt + 1) * qt, m.parts[q].row_start + m.parts[q].nrows);
-          }
+          if (!list_rows(td, cmin, cmax, pend)) return "symmetric update targets a row that is not on this device";
         }
       }
       v += size;
     }
-    close_chunk(end);
     if (v != cp.nnz) return "ctl stream covers " + std::to_string(v) + " values, expected " + std::to_string(cp.nnz);
-    if (!m.symmetric) { if (L.has_flat) sk.finish(); else sk.discard(); }
+    if (L.has_flat) sk.finish(); else sk.discard();
     if (L.has_flat && singles_ok && (int64_t)singles.size() == L.flat_elems) {
-      // fold the few chunk-kernel elements into the table as diagonal units of one element
-      KindEntry ke{K_DIAG, 1};
-      auto key = std::make_pair(ke.kind_align, ke.delta);
-      auto it = kindex.find(key);
-      if (it == kindex.end()) { it = kindex.insert(std::make_pair(key, (uint32_t)out.ktab.size())).first; out.ktab.push_back(ke); }
+      // fold the few stream-kernel elements into the table as diagonal units of one element
       for (const Single &sg : singles) {
         XDesc d;
         d.voff = (uint32_t)(L.val_base + (uint64_t)sg.v);
         d.row = (int32_t)(cp.row_start + sg.row);
         d.col = (int32_t)sg.col;
-        d.meta = it->second | (1u << 16) | ((uint32_t)K_DIAG << 24) | XD_DELTA1;
+        d.meta = (uint32_t)k_single | (1u << 16) | ((uint32_t)K_DIAG << 24) | XD_DELTA1;
         pend.push_back(Pending{(int64_t)pi, sg.row / TILE_ROWS, d});
         if (m.symmetric) {
           XDesc td = d;
           td.meta |= XD_TRANSPOSED;
-          int64_t q = owner_of(sg.col);
-          if (q < 0) return "symmetric update targets a row that is not on this device";
-          const int64_t qt = (int64_t)CTA_THREADS * tile_rpt(m.parts[q].nrows, m.rows_per_thread);
-          pend.push_back(Pending{q, (sg.col - m.parts[q].row_start) / qt, td});
+          if (!list_rows(td, sg.col, sg.col, pend)) return "symmetric update targets a row that is not on this device";
         }
       }
-      L.chunks.clear();
-      L.chunk_last_row.clear();
-      L.uoffs.clear();
       sk.discard();
+      simg.clear();
+      blocks.resize(blocks_before);
       L.has_flat = false;
       L.flat_elems = 0;
     }
+    pend.insert(pend.end(), simg.begin(), simg.end());
   }
   out.total_values = vbase;
   out.total_ctl = cbase;
   if (vbase >= (uint64_t(1) << 32)) return "more than 2^32 values on one device";
 
-  // distribute the descriptors: stable counting sort by (partition, tile)
-  std::vector<std::vector<uint32_t>> cnt(np);
-  for (size_t q = 0; q < np; q++) cnt[q].assign((size_t)out.parts[q].ntiles + 1, 0);
+  // CSX-Sym block images: block-column units of the most frequent shape go to the compact tables (one 8-byte
+  // entry per unit, found through the aligned block row it updates), all other block units get descriptors
+  struct FastEnt { int64_t q, jrel; BlockImage b; };
+  std::vector<FastEnt> fast;
+  if (!blocks.empty()) {
+    std::map<std::pair<uint32_t, uint32_t>, size_t> shapes;
+    for (const BlockTmp &b : blocks) if (b.kind == K_BCOL) shapes[std::make_pair(b.align, b.other)]++;
+    size_t best = 0;
+    for (auto &kv : shapes) if (kv.second > best) { best = kv.second; out.bimg_align = (int)kv.first.first; out.bimg_rows = (int)kv.first.second; }
+    for (const BlockTmp &b : blocks) {
+      if (b.kind == K_BCOL && (int)b.align == out.bimg_align && (int)b.other == out.bimg_rows) {
+        const int64_t A = out.bimg_align;   // block-column units start at columns that are multiples of their width
+        if (b.cmin % A) {
+          if (!list_rows(b.d, b.cmin, b.cmax, pend)) return "symmetric update targets a row that is not on this device";
+          continue;
+        }
+        for (int64_t g = b.cmin; g <= b.cmax;) {
+          const int64_t q = owner_of(g);
+          if (q < 0) return "symmetric update targets a row that is not on this device";
+          fast.push_back(FastEnt{q, g / A - q_start((size_t)q) / A, BlockImage{b.d.voff, b.d.row}});
+          g = std::min(b.cmax + 1, q_start((size_t)q) + q_rows((size_t)q));   // the rest belongs to the next owner
+        }
+      } else if (!list_rows(b.d, b.cmin, b.cmax, pend)) return "symmetric update targets a row that is not on this device";
+    }
+  }
+  for (size_t q = 0; q < nq && out.bimg_align; q++) {
+    PartLayout &L = out.parts[q];
+    if (!L.nrows) continue;
+    const int64_t A = out.bimg_align;
+    L.bimg_j0 = L.row_start / A;
+    const int64_t nj = (L.row_start + L.nrows - 1) / A - L.bimg_j0 + 1;
+    L.bimg_ptr.assign((size_t)nj + 1, 0);
+  }
+  for (const FastEnt &e : fast) out.parts[e.q].bimg_ptr[(size_t)e.jrel + 1]++;
+  for (size_t q = 0; q < nq; q++) {
+    PartLayout &L = out.parts[q];
+    for (size_t j = 1; j < L.bimg_ptr.size(); j++) L.bimg_ptr[j] += L.bimg_ptr[j - 1];
+    if (!L.bimg_ptr.empty()) L.bimg.resize(L.bimg_ptr.back());
+  }
+  {
+    std::vector<std::vector<uint32_t>> at(nq);
+    for (size_t q = 0; q < nq; q++) at[q].assign(out.parts[q].bimg_ptr.begin(), out.parts[q].bimg_ptr.end());
+    for (const FastEnt &e : fast) out.parts[e.q].bimg[at[e.q][(size_t)e.jrel]++] = e.b;   // source order: deterministic sums
+  }
+
+  // distribute the descriptors: stable counting sort by (owner, tile)
+  std::vector<std::vector<uint32_t>> cnt(nq);
+  for (size_t q = 0; q < nq; q++) cnt[q].assign((size_t)out.parts[q].ntiles + 1, 0);
   for (const Pending &e : pend) cnt[e.part][e.tile + 1]++;
-  for (size_t q = 0; q < np; q++) {
+  for (size_t q = 0; q < nq; q++) {
     PartLayout &L = out.parts[q];
     for (int64_t t = 0; t < L.ntiles; t++) cnt[q][t + 1] += cnt[q][t];
     if (cnt[q][L.ntiles] >= 0x80000000u) return "cross-row unit table too large";

@@ -2,35 +2,26 @@
 //
 // The ctl stream and the values array go to HBM verbatim.  What the reference
 // gets from sequential execution on one core per partition
-// (src/templates/csx_spmv_tmpl.c:66-101) the GPU gets from two side tables
-// built once at tune time by decoding ctl on the host:
+// (src/templates/csx_spmv_tmpl.c:66-101) the GPU gets from side tables built
+// once at tune time by decoding ctl on the host:
 //
-//   * chunk table — the ctl stream is cut at unit boundaries into chunks of
-//     at most 256 non-zeros / 64 units / 128 slices / 2 KB of ctl ("warp-segmented ctl
-//     chunks").  An entry holds the byte offset of the chunk's first unit, the
-//     index of its first value, the row it belongs to and the column cursor at
-//     that point (the decoder state a warp needs to start there), plus its
-//     byte / element / unit counts.  A second table holds the 16-bit offset of
-//     every unit head inside its chunk, so no warp has to walk the heads
-//     serially.  A warp copies the chunk's ctl bytes and values into shared
-//     memory (asynchronous copies), parses one unit head per lane, cuts the
-//     units into slices of at most `slice` elements and then gives every lane
-//     one slice: delta bodies are summed per slice, a segmented warp prefix sum
-//     over the slice totals yields each slice's column cursor, and the lane
-//     walks its slice (columns from the deltas or from the unit geometry).
-//     Row sums of row-local units are combined across lanes with a segmented
-//     shuffle reduction and added to y with fp64 red operations (a row may
-//     span chunks); block and short cross-row units add once per block row.
-//
-//   * cross-row unit table (XDT) — long vertical / diagonal / anti-diagonal
-//     units (>= XDT_MIN_SIZE elements) are better served by a gather: each gets
-//     a 16-byte descriptor (value offset, start row, start column, kind/size)
-//     listed under every row tile (256 or 1024 rows) it touches, including
-//     tiles after the one it starts in ("carry-in").  The thread that owns a
-//     row gathers its contributions from the descriptors of its tile: conflict
-//     free, no atomics.  For CSX-Sym the transposed image of such a unit is
-//     listed under the tiles of its *columns*, so the symmetric update of
-//     those units is a gather as well.  The chunk kernel skips these units.
+//   * stream-kernel chunk table ("warp-segmented ctl chunks", see below) for
+//     delta, horizontal and block units;
+//   * cross-row unit table (XDT) — vertical / diagonal / anti-diagonal units
+//     are better served by a gather: each gets a 16-byte descriptor (value
+//     offset, start row, start column, kind/size) listed under every row tile
+//     (256 or 1024 rows) it touches, including tiles after the one it starts
+//     in ("carry-in").  The thread that owns a row gathers its contributions
+//     from the descriptors of its tile: conflict free, no atomics;
+//   * CSX-Sym: the transposed update y[col] += v * x[row] of every stored
+//     element is a gather as well — the transposed image of every unit is
+//     listed under the tiles of its *columns* (a descriptor with the
+//     XD_TRANSPOSED flag; block-column units of the dominant shape go to a
+//     compact table indexed by the aligned block row they update).  Phase 1
+//     (stream kernel + direct table units) computes the lower triangle's own
+//     rows, phase 2 (gather kernel) adds the images: no write conflicts, no
+//     atomics, bit-reproducible — the counterpart of the reference's
+//     per-thread local vectors and map reduction (CsxSpmv.cpp:37-50).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -48,11 +39,6 @@ namespace spxb {
 
 constexpr int CTA_THREADS = 256;      // gather kernel: threads per CTA; a tile has CTA_THREADS * rpt rows
 constexpr int CTL_PAD = 32;           // readable bytes past the end of ctl
-constexpr int XDT_MIN_SIZE = 8;       // linear cross-row units at least this long go to the XDT
-constexpr int CHUNK_MAX_ELEMS = 256;  // chunk limits (chunk kernel shared-memory budget: 5.7 KB per warp)
-constexpr int CHUNK_MAX_UNITS = 64;
-constexpr int CHUNK_MAX_BYTES = 2048;
-constexpr int CHUNK_MAX_SLICES = 128;
 
 // unit kinds as the kernels see them
 enum Kind : uint32_t {
@@ -60,7 +46,7 @@ enum Kind : uint32_t {
   K_VERT = 5, K_DIAG = 6, K_ADIAG = 7, K_BROW = 8, K_BCOL = 9                // cross-row
 };
 inline bool kind_row_local(uint32_t k) { return k <= K_HORIZ; }
-inline bool goes_to_xdt(uint32_t kind, uint32_t size) { return kind >= K_VERT && kind <= K_ADIAG && size >= (uint32_t)XDT_MIN_SIZE; }
+inline bool goes_to_xdt(uint32_t kind) { return kind >= K_VERT && kind <= K_ADIAG; }   // table units
 
 // 16-byte cross-row unit descriptor (device layout: uint4)
 struct XDesc {
@@ -73,28 +59,12 @@ constexpr uint32_t XD_TRANSPOSED = 1u << 28;
 constexpr uint32_t XD_DELTA1 = 1u << 29;
 
 struct KindEntry { uint32_t kind_align; uint32_t delta; };  // kind | align << 8 ; stride or free block dim
-// ctl unit id -> kind as the chunk kernel sees it.  `sl` is the slice parameter of this kind: elements per
-// slice for row-local and linear units, columns per slice for block-row units, rows per slice for block-column
-// units; `recip` = ceil(2^16 / sl), so that n / sl == (n * recip) >> 16 for n < 256.
+// ctl unit id -> kind as the stream kernel sees it.  `sl` is the task parameter of this kind: elements per task for
+// row-local units, columns per task for block-row units, rows per task for block-column units; `recip` = ceil(2^16 / sl),
+// so that n / sl == (n * recip) >> 16 for n < 256.
 struct IdEntry { uint32_t kind_align; uint32_t delta; uint32_t sl; uint32_t recip; };
-// number of slices a unit of `size` elements is cut into (same arithmetic on host and device)
-SPXB_HD inline uint32_t unit_slices(uint32_t kind, uint32_t size, uint32_t delta, const IdEntry &ie) {
-  const uint32_t n = (kind == K_BROW || kind == K_BCOL) ? delta : size;   // columns / rows / elements to distribute
-  return ((n + ie.sl - 1) * ie.recip) >> 16;
-}
 
-// 32-byte chunk entry (device layout: 2 x uint4)
-struct ChunkEntry {
-  uint64_t ctl_off;   // byte offset of the chunk's first unit head (partition relative)
-  uint32_t val_off;   // index of its first value (partition relative, XDT units included)
-  uint32_t cursor;    // column cursor before that unit (0 when the unit starts a row)
-  int32_t row;        // partition-relative row of that unit
-  uint32_t counts;    // ctl bytes [0:12) | elements [12:22) | units [22:30)
-  uint32_t uoff;      // index of the chunk's first entry in the unit-offset table
-  uint32_t pad;
-};
-
-// ---- stream kernel (kernel 2 of non-symmetric partitions; stream_kernel.cuh) ---------------------------------
+// ---- stream kernel (stream_kernel.cuh) ---------------------------------
 // The ctl stream is cut at unit boundaries into chunks of up to SK_MAX_ROUNDS rounds of at most 32 units (a round
 // holds at most SK_MAX_TASKS lane tasks and SK_MAX_ELEMS non-zeros; bit 15 of a unit's entry in the offset table
 // marks the last unit of a round), at most SK_MAX_BYTES ctl bytes, whose rows fit a window of SK_WROWS rows.  A warp parses one
@@ -136,6 +106,8 @@ SPXB_HD inline uint32_t sk_unit_tasks(uint32_t kind, uint32_t size, uint32_t del
   return 1;                                                       // table units: one empty task
 }
 
+struct BlockImage { uint32_t voff; int32_t urow; };   // first value (device wide), global row of the unit's first row
+
 struct PartLayout {
   int64_t nrows = 0, row_start = 0, nnz = 0, ctl_size = 0;
   // stream kernel tables (non-symmetric partitions)
@@ -155,22 +127,23 @@ struct PartLayout {
   // touches and the columns it reads
   std::vector<int32_t> sk_first_row, sk_last_row, sk_cmin, sk_cmax;
   uint64_t val_base = 0, ctl_base = 0;   // offsets into the device-wide arrays
-  bool has_flat = false;                 // some unit is handled by the chunk kernel
+  bool has_flat = false;                 // some unit is handled by the stream kernel
+  bool is_halo = false;                  // CSX-Sym pseudo-partition: rows of other devices that local units update
   bool xd_diag1_only = true;             // every descriptor of this partition's table is a direct diagonal unit of stride 1
   int64_t ntiles = 0;
   int rpt = 1;                           // rows per thread (1 or 4): tile_rows = CTA_THREADS * rpt
   int64_t tile_rows() const { return (int64_t)CTA_THREADS * rpt; }
-  IdEntry idtab[64];                     // ctl unit id -> kind and slice parameter
-  int slice = 0;                         // elements per slice the chunk kernel was laid out for
-  std::vector<ChunkEntry> chunks;
-  std::vector<uint16_t> uoffs;           // offset of every chunk-kernel unit head inside its chunk
-  // host-side only (pipelined host-buffer SpMV, csxb_spmv_host): last row a chunk touches, and per tile the
-  // global column window its units read (CSX-Sym: the rows themselves included, x[row] is read too)
-  std::vector<int32_t> chunk_last_row;
+  IdEntry idtab[64];                     // ctl unit id -> kind and task parameter
+  // host-side only (pipelined host-buffer SpMV, csxb_spmv_host): per tile the global column window its units read
+  // (CSX-Sym: the rows themselves included, x[row] is read too)
   std::vector<int32_t> tile_cmin, tile_cmax;
   std::vector<uint32_t> tile_xoff;       // ntiles + 1
   std::vector<XDesc> xdesc;
-  int64_t flat_elems = 0;                // non-zeros handled by the chunk kernel
+  int64_t flat_elems = 0;                // non-zeros handled by the stream kernel
+  // CSX-Sym: transposed images of block-column units of the device's dominant shape, by the aligned block row they update
+  std::vector<uint32_t> bimg_ptr;        // block rows + 1
+  std::vector<BlockImage> bimg;
+  int64_t bimg_j0 = 0;                   // global index of the partition's first aligned block row
 };
 
 struct DeviceLayout {
@@ -178,6 +151,11 @@ struct DeviceLayout {
   std::vector<PartLayout> parts;
   uint64_t total_values = 0, total_ctl = 0;
   bool symmetric = false, full_colind = false;
+  // CSX-Sym: shape of the block-column units whose images live in the bimg tables (0: none)
+  int bimg_align = 0, bimg_rows = 0;
+  // CSX-Sym with only some partitions on this device: rows [halo_lo, halo_hi) of lower ranks that local units
+  // update; parts.back() is their pseudo-partition (is_halo)
+  int64_t halo_lo = 0, halo_hi = 0;
 };
 
 // Decodes every local partition's ctl stream and fills the tables.

@@ -21,7 +21,7 @@
 // kinds): the counterpart of the reference's per-partition JIT (CsxJit.hpp:359-732), which emits one loop per unit
 // kind of the partition's id_map.
 #pragma once
-#include "chunk_kernel.cuh"
+#include "part_dev.cuh"
 
 constexpr uint32_t SKM_DELTA = (1u << K_DELTA8) | (1u << K_DELTA16) | (1u << K_DELTA32);
 constexpr uint32_t SKM_ROWLOCAL = SKM_DELTA | (1u << K_DELTA64) | (1u << K_HORIZ);

@@ -1,6 +1,6 @@
 // Host emulation of both SpMV kernels (test infrastructure): tunes a CSR matrix with the product encoder, builds
 // the product's GPU layout and then executes sparsex_b200/csrc/gather_kernel.cuh (kernel 1, generic instantiations)
-// and chunk_kernel.cuh (kernel 2) — the same text nvcc compiles — warp by warp on the fibre emulation of
+// and part_dev.cuh (kernel 2) — the same text nvcc compiles — warp by warp on the fibre emulation of
 // warp_emul.hpp.  Lets the CPU test suite check the traversal logic of the kernels against the CSR input without
 // a GPU.
 #include "warp_emul.hpp"
@@ -59,7 +59,6 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
   for (int64_t i = 0; i < nrows; i++) y[i] = i < covered ? std::nan("") : 0.0;
   for (int64_t i = 0; i < (int64_t)L.total_values; i++) { dec_rows[i] = -1; dec_cols[i] = -1; }
   int64_t nchunks = 0, nunits = 0, nxd = 0;
-  static ChunkSmem smem;
   std::vector<PartDev> pdev;
   std::vector<std::vector<double>> scratch(L.parts.size());
   for (size_t i = 0; i < L.parts.size(); i++) {
@@ -84,14 +83,19 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     memset(&P, 0, sizeof(P));
     P.ctl = ctl.data() + pl.ctl_base;
     P.values = vals.data();
-    P.chunks = pl.chunks.data();
-    P.uoffs = pl.uoffs.data();
     P.tile_xoff = pl.tile_xoff.data();
     P.xdesc = reinterpret_cast<const uint4 *>(pl.xdesc.data());
     P.ktab = L.ktab.data();
     P.dvalues = hp.dvalues.data();
     P.nrows = pl.nrows; P.row_start = pl.row_start; P.val_base = (uint32_t)pl.val_base;
-    P.nchunks = (uint32_t)pl.chunks.size();
+    P.full_colind = L.full_colind;
+    P.rpt = pl.rpt;
+    memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
+    if (!pl.bimg.empty()) {
+      P.bimg_ptr = pl.bimg_ptr.data(); P.bimg = reinterpret_cast<const uint2 *>(pl.bimg.data()); P.bimg_j0 = pl.bimg_j0;
+      P.bimg_align = L.bimg_align; P.bimg_rows = L.bimg_rows;
+      if (stats) stats[12] += (int64_t)pl.bimg.size();
+    }
     P.sk_chunks = reinterpret_cast<const uint4 *>(pl.sk_chunks.data());
     P.sk_uoffs = pl.sk_uoffs.data();
     scratch[i].assign(pl.sk_scratch + 2, std::nan(""));
@@ -103,21 +107,14 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     nunits += (int64_t)pl.sk_uoffs.size();
     if (stats) for (int k = 0; k < 4; k++) stats[8 + k] += pl.sk_stat[k];
     if (stats) { stats[4] += (int64_t)pl.sk_fix_idx.size(); stats[5] += (int64_t)pl.sk_gaps.size(); stats[6] = pl.sk_rows; stats[7] = pl.sk_kmask; }
-    P.full_colind = L.full_colind;
-    P.rpt = pl.rpt;
-    memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
     pdev.push_back(P);
-    nchunks += (int64_t)pl.chunks.size();
-    nunits += (int64_t)pl.uoffs.size();
-    if (stats) stats[3] = pl.slice;
   }
-  // non-symmetric partitions with stream units: stream kernel (writes y), fix-up, then kernel 1 adds (engine.cu: run_partition)
   if (getenv("CSXB_EMUL_LAYOUT_ONLY")) { if (stats) { stats[0] = nchunks; stats[1] = nunits; } return 0; }
   static double sacc[SK_WIN];
   static uint4 sid[64];
   std::vector<bool> streamed(L.parts.size(), false);
   int inst = 0;
-  for (size_t i = 0; i < L.parts.size() && !M.symmetric; i++) {
+  for (size_t i = 0; i < L.parts.size(); i++) {
     const PartLayout &pl = L.parts[i];
     const PartDev &P = pdev[i];
     if (pl.sk_chunks.empty()) continue;
@@ -154,7 +151,7 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     const PartLayout &pl = L.parts[i];
     const PartDev &P = pdev[i];
     const bool xd = !pl.xdesc.empty(), diag1 = !M.symmetric && pl.xd_diag1_only && xd;
-    if (streamed[i] && !xd) continue;
+    if (streamed[i] && !xd && !M.symmetric) continue;
     const double beta = streamed[i] ? 1.0 : 0.0;
     const int ow = streamed[i] ? 0 : 1;
     for (int64_t t = 0; t < pl.ntiles; t++)
@@ -180,31 +177,6 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
       }
   }
   warp_emul::warp_in_cta() = 0;
-  for (size_t i = 0; i < L.parts.size(); i++) {
-    const PartDev &P = pdev[i];
-    for (uint32_t ch = 0; ch < P.nchunks; ch++) {
-      for (int pass = 0; pass < 2; pass++) {
-        if (pass == 0) {
-          warp_emul::run_warp([&](int lane) {
-            DecodeChunkOp op{dec_rows + P.val_base, dec_cols + P.val_base, P.row_start, 0};
-            process_chunk(P, ch, smem, lane, op);
-          });
-        } else if (M.symmetric) {
-          warp_emul::run_warp([&](int lane) {
-            SpmvChunkOp<true> op;
-            op.x = x; op.y = y; op.vals = smem.vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
-            process_chunk(P, ch, smem, lane, op);
-          });
-        } else {
-          warp_emul::run_warp([&](int lane) {
-            SpmvChunkOp<false> op;
-            op.x = x; op.y = y; op.vals = smem.vals; op.row_start = P.row_start; op.alpha = alpha; op.lane = lane;
-            process_chunk(P, ch, smem, lane, op);
-          });
-        }
-      }
-    }
-  }
   for (size_t i = 0; i < M.parts.size(); i++) M.parts[i].nrows = saved[i];
   if (stats) { stats[0] = nchunks; stats[1] = nunits; stats[2] = nxd; stats[3] = inst; }
   return 0;

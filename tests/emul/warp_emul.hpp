@@ -19,6 +19,7 @@
 #define __align__(n) alignas(n)
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 using std::min;
 using std::max;
