@@ -48,7 +48,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 // Edge CTA of the edge-tiles-first protocol (XchgDev.mode 1): waits for the neighbours' edge tiles of the previous
 // step, computes and pushes its tile, and the last edge CTA of the step publishes it.  Kept out of line so that
 // the interior path of the kernel keeps the register allocation of the plain kernel.
-template <bool XD, bool SYM, int RPT, int KSET, int VAR>
+template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool BT>
 __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, double *y, double alpha, long long tile,
                                            long long row_block, const XchgDev &X, int ypar) {
   // only the edge CTAs use the device-resident step number (the flags count steps across graph replays)
@@ -64,7 +64,7 @@ __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, do
   }
   __syncthreads();
   // spmv_tile pushes into push_vec[p][(k & 1) ^ 1]: hand it a step number with the parity of the target buffer
-  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev>(P, x, y, alpha, 0.0, 1, tile, row_block, X, (unsigned long long)(ypar ^ 1));
+  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev, BT>(P, x, y, alpha, 0.0, 1, tile, row_block, X, (unsigned long long)(ypar ^ 1));
   // Every edge CTA orders its stores before its count at device scope; the last one then issues the single
   // system-scope fence (cumulative over everything that happened before it) and the release stores of the flags.
   __threadfence();
@@ -77,7 +77,7 @@ __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, do
   }
 }
 
-template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0, class XP = NoXchg>
+template <bool XD, bool SYM, int RPT, int KSET, int MINB = 8, int VAR = 0, class XP = NoXchg, bool BT = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __grid_constant__ PartDev P,
                                                                   const double *__restrict__ x,
                                                                   double *__restrict__ y, double alpha, double beta,
@@ -89,14 +89,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_kernel(const __gri
     xk = *reinterpret_cast<const volatile unsigned long long *>(X.step);
     x = X.vec[xk & 1]; y = X.vec[(xk & 1) ^ 1];
   }
-  spmv_tile<XD, SYM, RPT, KSET, VAR, XCHG, XP>(P, x, y, alpha, beta, overwrite, tile, tile, X, xk);
+  spmv_tile<XD, SYM, RPT, KSET, VAR, XCHG, XP, BT>(P, x, y, alpha, beta, overwrite, tile, tile, X, xk);
 }
 
 // Kernel 1 under the edge-tiles-first protocol (XchgDev.mode 1): CTAs [0, nb) take the tiles at both ends of the
 // partition (out of line: wait, compute, push, publish), the others the interior tiles, which touch no other rank
 // and run exactly the plain tile code.  x / y are the step's source and target vectors (the host alternates them,
 // so a captured graph must hold an even number of steps); `ypar` is the index of y among the ping-pong vectors.
-template <bool XD, int RPT, int KSET, int MINB = 8, int VAR = 0>
+template <bool XD, int RPT, int KSET, int MINB = 8, int VAR = 0, bool BT = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_xe_kernel(const __grid_constant__ PartDev P,
                                                                      const double *__restrict__ x, double *__restrict__ y,
                                                                      double alpha, int ypar, const __grid_constant__ XchgDev X) {
@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_xe_kernel(const __
     constexpr int SPLIT = RPT == 4 ? 4 : 1;
     const int bt = b / SPLIT, sub = b % SPLIT;
     const long long tile = bt < X.edge_lo_end ? bt : X.edge_hi_begin + (bt - X.edge_lo_end);
-    spmv_edge_cta<XD, false, 1, KSET, 0>(P, x, y, alpha, tile, tile * SPLIT + sub, X, ypar);
+    spmv_edge_cta<XD, false, 1, KSET, 0, BT>(P, x, y, alpha, tile, tile * SPLIT + sub, X, ypar);
   } else {
     const long long tile = (long long)X.edge_lo_end + (b - X.nb);
-    spmv_tile<XD, false, RPT, KSET, VAR, false, NoXchg>(P, x, y, alpha, 0.0, 1, tile, tile, NoXchg(), 0ull);
+    spmv_tile<XD, false, RPT, KSET, VAR, false, NoXchg, BT>(P, x, y, alpha, 0.0, 1, tile, tile, NoXchg(), 0ull);
   }
 }
 
@@ -157,6 +157,22 @@ struct DecodeGatherOp {
   int myrow;
   __device__ __forceinline__ void add(uint32_t vi, int col) { rows[vi] = myrow; cols[vi] = col; }
 };
+// decoded coordinates of the block-table units (their own rows; images repeat the same values)
+__global__ void __launch_bounds__(CTA_THREADS) csx_decode_bt_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
+  const long long lrow = (long long)blockIdx.x * CTA_THREADS + threadIdx.x;
+  if (lrow >= P.nrows) return;
+  const long long g = P.row_start + lrow;
+  for (int c = 0; c < P.nbt; c++) {
+    const BtDev &T = P.bt[c];
+    if (T.image) continue;
+    const long long J = g / T.G;
+    const int f = (int)(g - J * T.G) * T.sf;
+    for (uint32_t e = T.ptr[J - T.j0]; e < T.ptr[J - T.j0 + 1]; e++) {
+      const uint2 b = T.ent[e];
+      for (int l = 0; l < T.nloop; l++) { rows[b.x + f + l * T.sl] = (int)g; cols[b.x + f + l * T.sl] = (int)b.y + l; }
+    }
+  }
+}
 __global__ void __launch_bounds__(CTA_THREADS) csx_decode_gather_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
   const long long tile = blockIdx.x;
   const uint32_t b = __ldg(P.tile_xoff + tile), e = __ldg(P.tile_xoff + tile + 1);
@@ -516,15 +532,16 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     uint32_t *tx = nullptr; XDesc *xd = nullptr;
     if (dev_copy(m, pl.tile_xoff.data(), pl.tile_xoff.size(), &tx)) return -1;
     if (dev_copy(m, pl.xdesc.data(), pl.xdesc.size(), &xd)) return -1;
-    if (!pl.bimg.empty()) {   // CSX-Sym block image table
+    for (size_t t = 0; t < pl.bt.size(); t++) {   // block tables
+      const BlockTable &T = pl.bt[t];
       uint32_t *bp = nullptr; BlockImage *bi = nullptr;
-      if (dev_copy(m, pl.bimg_ptr.data(), pl.bimg_ptr.size(), &bp)) return -1;
-      if (dev_copy(m, pl.bimg.data(), pl.bimg.size(), &bi)) return -1;
-      static_assert(sizeof(BlockImage) == sizeof(uint2), "block image layout");
-      P.bimg_ptr = bp; P.bimg = (const uint2 *)bi; P.bimg_j0 = pl.bimg_j0;
-      P.bimg_align = L.bimg_align; P.bimg_rows = L.bimg_rows;
-      tables += (int64_t)pl.bimg_ptr.size() * 4 + (int64_t)pl.bimg.size() * 8;
+      if (dev_copy(m, T.ptr.data(), T.ptr.size(), &bp)) return -1;
+      if (dev_copy(m, T.ent.data(), T.ent.size(), &bi)) return -1;
+      static_assert(sizeof(BlockImage) == sizeof(uint2), "block table entry layout");
+      P.bt[t] = BtDev{bp, (const uint2 *)bi, (long long)T.j0, T.G, T.nloop, T.sf, T.sl, T.image};
+      tables += (int64_t)T.ptr.size() * 4 + (int64_t)T.ent.size() * 8;
     }
+    P.nbt = (int)pl.bt.size();
     if (!pl.sk_chunks.empty()) {   // stream kernel tables
       SkEntry *se = nullptr; uint16_t *so = nullptr; int32_t *fr = nullptr; uint32_t *fp = nullptr, *fi = nullptr; long long *gp = nullptr;
       if (dev_copy(m, pl.sk_chunks.data(), pl.sk_chunks.size(), &se)) return -1;
@@ -561,7 +578,7 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
     if (pl.nrows) {
       if (!pl.sk_chunks.empty())
-        launches += 1 + ((pl.sk_fix_rows.empty() && pl.sk_gaps.empty()) ? 0 : 1) + (pl.xdesc.empty() ? 0 : 1);
+        launches += 1 + ((pl.sk_fix_rows.empty() && pl.sk_gaps.empty()) ? 0 : 1) + ((pl.xdesc.empty() && pl.bt.empty() && !H.symmetric) ? 0 : 1);
       else launches += 1;
     }
     if (!pl.is_halo) m->covered_rows_end = std::max<int64_t>(m->covered_rows_end, pl.row_start + pl.nrows);
@@ -598,6 +615,11 @@ template <bool SYM, int RPT, int KSET, class XP>
 static void launch_gather_k(const PartDev &P, const PartLayout &pl, unsigned nt, const double *x, double *y, double alpha,
                             double beta, int overwrite, cudaStream_t s, const XP &X) {
   dim3 grid(nt), block(CTA_THREADS);
+  if (!pl.bt.empty()) {   // block tables: the generic instantiation with the table loop (64 registers)
+    if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET_ANY, 4, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+    else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, 4, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+    return;
+  }
   // descriptors can also come from other partitions (transposed images under CSX-Sym)
   if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET, 8, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
   else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, 8, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
@@ -610,7 +632,7 @@ static void launch_gather(const PartDev &P0, const PartLayout &pl, int64_t t0, i
   P.tile0 = (uint32_t)t0;
   const unsigned nt = (unsigned)(t1 - t0);
   // kernels are pre-compiled per (tile shape, unit-kind set) — the counterpart of the per-partition JIT (CsxJit.hpp)
-  const bool diag1 = !SYM && pl.xd_diag1_only && !pl.xdesc.empty();
+  const bool diag1 = !SYM && pl.xd_diag1_only && !pl.xdesc.empty() && pl.bt.empty();
   if (pl.rpt == 4) {
     if (diag1) {  // the instantiation the stencil configs run: loads of a unit issued as one PTX block
       dim3 grid(nt), block(CTA_THREADS);
@@ -629,7 +651,17 @@ static void launch_gather_xe(const PartDev &P0, const PartLayout &pl, const doub
   PartDev P = P0;
   P.tile0 = 0;
   dim3 grid((unsigned)(X.nb + (X.edge_hi_begin - X.edge_lo_end))), block(CTA_THREADS);   // edge CTAs first, then the interior tiles
-  const bool xd = !pl.xdesc.empty(), diag1 = pl.xd_diag1_only && xd;
+  const bool xd = !pl.xdesc.empty(), diag1 = pl.xd_diag1_only && xd && pl.bt.empty();
+  if (!pl.bt.empty()) {
+    if (pl.rpt == 4) {
+      if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+      else csx_spmv_xe_kernel<false, 4, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    } else {
+      if (xd) csx_spmv_xe_kernel<true, 1, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+      else csx_spmv_xe_kernel<false, 1, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    }
+    return;
+  }
   if (pl.rpt == 4) {
     if (diag1) csx_spmv_xe_kernel<true, 4, KSET_DIAG1, 8, 1><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
     else if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
@@ -682,7 +714,7 @@ static int run_partition(const PartDev &P, const PartLayout &pl, const SkIO &io,
   if (launch_stream(P, pl, 0, (uint32_t)pl.sk_chunks.size(), io, alpha, beta, overwrite, s)) return -1;
   launch_fixup(P, 0, (uint32_t)pl.sk_fix_rows.size(), 0, (uint32_t)pl.sk_gaps.size(), 0, pl.nrows, io, alpha, beta, overwrite, s);
   // CSX-Sym: the gather kernel always runs (diagonal, images)
-  if (SYM || !pl.xdesc.empty()) launch_gather<SYM>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, 1.0, 0, s, X);
+  if (SYM || !pl.xdesc.empty() || !pl.bt.empty()) launch_gather<SYM>(P, pl, 0, pl.ntiles, io.x, io.y, alpha, 1.0, 0, s, X);
   return 0;
 }
 
@@ -770,7 +802,7 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
         io.x = m->d_x; io.y = m->d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
         if (launch_stream(m->pdev[sl.part], pl, sl.chunk0, sl.chunk1, io, alpha, beta, overwrite, m->s_run)) return fail("no stream kernel for the partition's pattern set");
         launch_fixup(m->pdev[sl.part], sl.f0, sl.f1, sl.g0, sl.g1, sl.row_lo - pl.row_start, sl.row_hi - pl.row_start, io, alpha, beta, overwrite, m->s_run);
-        if (!pl.xdesc.empty()) launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, 1.0, 0, m->s_run, NoXchg());
+        if (!pl.xdesc.empty() || !pl.bt.empty()) launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, 1.0, 0, m->s_run, NoXchg());
       }
       CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k + 1], m->s_run));
       if (sl.y_hi > sl.y_lo) {
@@ -1123,6 +1155,7 @@ int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t
   CUDA_TRY(cudaMemset(dr, 0xff, std::max<size_t>(n, 1) * 4));
   CUDA_TRY(cudaMemset(dcl, 0xff, std::max<size_t>(n, 1) * 4));
   if (pl.ntiles && !pl.xdesc.empty()) csx_decode_gather_kernel<<<(unsigned)pl.ntiles, CTA_THREADS>>>(m->pdev[part], dr, dcl);
+  if (!pl.bt.empty()) csx_decode_bt_kernel<<<(unsigned)((pl.nrows + CTA_THREADS - 1) / CTA_THREADS), CTA_THREADS>>>(m->pdev[part], dr, dcl);
   if (!pl.sk_chunks.empty())
     csx_stream_decode_kernel<<<(unsigned)((pl.sk_chunks.size() + SK_WARPS - 1) / SK_WARPS), SK_WARPS * 32>>>(m->pdev[part], dr, dcl);
   CUDA_TRY(cudaGetLastError());

@@ -137,13 +137,14 @@ struct NoXchg {};
 //   KSET_ANY    vertical / diagonal / anti-diagonal units of any stride, CSX-Sym images included
 //   KSET_DIAG1  only diagonal units of stride 1 (what the stencil matrices of the baseline configs encode to)
 // The kernel is bandwidth-bound and latency-sensitive: compiled for 8 resident CTAs per SM (32 registers).
+// BT: the partition has block tables (block units; gpu_layout.hpp: BlockTable).
 // VAR = 1 (4-rows-per-thread diagonal instantiation) issues the eight loads of a unit as one inline-PTX block so
 // that all of them are in flight before the first FMA; ptxas otherwise interleaves loads and FMAs at 32 registers.
 enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
 // The work of one warp of one CTA: rows [row_block * CTA_THREADS * RPT, +CTA_THREADS * RPT) with the descriptor list of
 // layout tile `tile` (the same number, unless an edge CTA of the exchange walks a quarter of a 4-rows-per-thread tile
 // with one row per thread).  PUSH: rows that other ranks read are also stored into their vectors (exchange).
-template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool PUSH, class XP>
+template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool PUSH, class XP, bool BT = false>
 __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__restrict__ x, double *__restrict__ y, double alpha,
                                           double beta, int overwrite, const long long tile, const long long row_block, const XP &X,
                                           const unsigned long long xk) {
@@ -234,21 +235,23 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
     }
   }
 
-  if (SYM && P.bimg_ptr) {
-    // images of block-column units of the dominant shape: every row finds the units that update it through its aligned
-    // block row; y[c + j] += sum_a v[a][j] * x[r + a] (block_col_sym_tmpl.c), entries in source order
-    const int BA = P.bimg_align, BR = P.bimg_rows;
+  // block tables: every row finds the sub-blocks that add to it through its aligned group of rows (gpu_layout.hpp:
+  // BlockTable; block_row_tmpl.c, block_col_tmpl.c, block_*_sym_tmpl.c); entries in source order
+  for (int c = 0; BT && c < P.nbt; c++) {
+    const BtDev &T = P.bt[c];
     const double *__restrict__ values = P.values;
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
       const long long lrow = lrow0 + k * 32 + lane;
       if (lrow < P.nrows) {
-        const long long g = P.row_start + lrow, J = g / BA;
-        const int j = (int)(g - J * BA);
-        const uint32_t e0 = __ldg(P.bimg_ptr + (J - P.bimg_j0)), e1 = __ldg(P.bimg_ptr + (J - P.bimg_j0) + 1);
+        const long long g = P.row_start + lrow, J = g / T.G;
+        const int f = (int)(g - J * T.G) * T.sf;
+        const uint32_t e0 = __ldg(T.ptr + (J - T.j0)), e1 = __ldg(T.ptr + (J - T.j0) + 1);
         for (uint32_t e = e0; e < e1; e++) {
-          const uint2 b = __ldg(P.bimg + e);
-          for (int a = 0; a < BR; a++) acc[k] += __ldg(values + b.x + a * BA + j) * __ldg(x + (int)b.y + a);
+          const uint2 b = __ldg(T.ent + e);
+          const double *__restrict__ vp = values + b.x + f;
+          const double *__restrict__ xp = x + (int)b.y;
+          for (int l = 0; l < T.nloop; l++) acc[k] += __ldg(vp + l * T.sl) * __ldg(xp + l);
         }
       }
     }

@@ -246,7 +246,74 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     }
     return true;
   };
-  // CSX-Sym: images of block units wait until the device's dominant block-column shape is known
+  // ---- which block units go to the block tables (gpu_layout.hpp: BlockTable) -------------------------------------
+  // One pass over the unit heads: per block kind the dominant width / height, and the largest sub-block size that
+  // divides every unit of that kind and (block-column units) every start row.
+  {
+    std::map<uint32_t, int64_t> bc_elems, br_elems;          // align -> elements
+    std::map<uint32_t, int64_t> bc_gcd, br_gcd;              // align -> gcd of the free dimension (and of the start rows)
+    std::map<uint32_t, bool> bc_colok, br_rowok;
+    auto gcd64 = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
+    for (size_t pi = 0; pi < np; pi++) {
+      const CsxPartition &cp = m.parts[pi];
+      KindEntry tab[64];
+      size_t nid = 0;
+      bool any = false;
+      for (; nid < cp.id_map.size() && cp.id_map[nid] != -1 && nid < 64; nid++) {
+        if (!classify(cp.id_map[nid], tab[nid])) return "unsupported pattern id " + std::to_string(cp.id_map[nid]);
+        any |= (tab[nid].kind_align & 0xff) >= K_BROW;
+      }
+      if (!any) continue;
+      const uint8_t *ctl = cp.ctl.data();
+      uint64_t p = 0, end = cp.ctl.size();
+      int64_t row = 0, col = 0;
+      while (p + 2 <= end) {
+        const uint8_t flags = ctl[p++], size = ctl[p++];
+        if (flags & 0x80) { row += (flags & 0x40) ? (int64_t)get_varint(ctl, p) : 1; col = 0; }
+        if (m.full_colind) { uint32_t c; memcpy(&c, ctl + p, 4); p += 4; col = c; }
+        else col = (int64_t)((uint64_t)col + get_varint(ctl, p));
+        const uint32_t id = flags & 0x3f;
+        if (id >= nid || size == 0) return "ctl stream uses an unmapped unit id";
+        const uint32_t kind = tab[id].kind_align & 0xff, align = (tab[id].kind_align >> 8) & 0xff, delta = tab[id].delta;
+        if (kind <= K_DELTA64) {
+          for (int k = 1; k < size; k++) { uint64_t d = 0; memcpy(&d, ctl + p, delta); p += delta; col += (int64_t)d; }
+        } else if (kind == K_HORIZ) col += (int64_t)(size - 1) * delta;
+        else if (kind == K_BCOL) {
+          bc_elems[align] += size;
+          bc_gcd[align] = gcd64(gcd64(bc_gcd[align], delta), cp.row_start + row);
+          if (!bc_colok.count(align)) bc_colok[align] = true;
+          if (col % align) bc_colok[align] = false;
+        } else if (kind == K_BROW) {
+          br_elems[align] += size;
+          br_gcd[align] = gcd64(br_gcd[align], delta);
+          if (!br_rowok.count(align)) br_rowok[align] = true;
+          if ((cp.row_start + row) % align) br_rowok[align] = false;
+        }
+      }
+    }
+    int64_t best = 0;
+    for (auto &kv : bc_elems)
+      if (kv.second > best && bc_gcd[kv.first] >= 2 && bc_gcd[kv.first] * kv.first >= 4 && (!m.symmetric || bc_colok[kv.first])) {
+        best = kv.second; out.bc_align = (int)kv.first; out.bc_rows = (int)std::min<int64_t>(bc_gcd[kv.first], 127);
+      }
+    if (out.bc_align && bc_gcd[out.bc_align] > 127) {   // keep the sub-block a divisor
+      int64_t g = bc_gcd[out.bc_align];
+      int r = 127;
+      while (g % r) r--;
+      out.bc_rows = r;
+      if (r < 2) out.bc_align = out.bc_rows = 0;
+    }
+    best = 0;
+    for (auto &kv : br_elems)
+      if (kv.second > best && br_rowok[kv.first] && br_gcd[kv.first] * kv.first >= 4) {
+        best = kv.second; out.br_align = (int)kv.first; out.br_cols = (int)br_gcd[kv.first];
+      }
+    if (getenv("CSXB_NO_BLOCK_TABLES")) out.bc_align = out.bc_rows = out.br_align = out.br_cols = 0;   // tuning aid
+  }
+  // tables of a partition: 0 block-column own rows, 1 block-column images (CSX-Sym), 2 block-row own rows
+  struct BtEnt { int64_t q; int tab; int64_t grp; BlockImage b; };
+  std::vector<BtEnt> btents;
+  // CSX-Sym: images of the block units that stay with the stream kernel get descriptors
   struct BlockTmp { XDesc d; uint32_t kind, align, other; int64_t cmin, cmax; };
   std::vector<BlockTmp> blocks;
 
@@ -274,12 +341,18 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         L.tile_cmax[t] = (int32_t)(cp.row_start + std::min<int64_t>(cp.nrows, (t + 1) * TILE_ROWS) - 1);
       }
     uint32_t id2k[64];
+    KindEntry truetab[64];     // what the units are; L.idtab is what the stream kernel treats them as
+    bool in_table[64];         // block units that live in the block tables
     size_t nid = 0;
     for (; nid < cp.id_map.size() && cp.id_map[nid] != -1; nid++) {
       if (nid >= 64) return "too many unit kinds";
       KindEntry ke;
       if (!classify(cp.id_map[nid], ke)) return "unsupported pattern id " + std::to_string(cp.id_map[nid]);
-      L.idtab[nid] = IdEntry{ke.kind_align, ke.delta, 1, 65536};
+      truetab[nid] = ke;
+      const uint32_t kd = ke.kind_align & 0xff, al = (ke.kind_align >> 8) & 0xff;
+      in_table[nid] = (kd == K_BCOL && (int)al == out.bc_align) || (kd == K_BROW && (int)al == out.br_align);
+      // to the stream kernel a unit of the block tables is a table unit: it only moves the column cursor
+      L.idtab[nid] = in_table[nid] ? IdEntry{K_VERT, 1, 1, 65536} : IdEntry{ke.kind_align, ke.delta, 1, 65536};
       const int64_t ki = kind_index(ke);
       if (ki < 0) return "too many distinct unit kinds on one device";
       id2k[nid] = (uint32_t)ki;
@@ -352,8 +425,8 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       first = false;
       uint32_t id = flags & 0x3f;
       if (id >= nid) return "ctl stream uses an unmapped unit id";
-      uint32_t kind = L.idtab[id].kind_align & 0xff, align = (L.idtab[id].kind_align >> 8) & 0xff;
-      uint32_t delta = L.idtab[id].delta;
+      uint32_t kind = truetab[id].kind_align & 0xff, align = (truetab[id].kind_align >> 8) & 0xff;
+      uint32_t delta = truetab[id].delta;
       if (size == 0) return "ctl unit of size 0";
       const int64_t start_col = col;
       uint64_t body = kind <= K_DELTA64 ? (uint64_t)(size - 1) * delta : 0;
@@ -394,12 +467,12 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
 
       // Vertical / diagonal / anti-diagonal units are table units; everything else belongs to the stream kernel,
       // which also parses the heads of the table units (they move the column cursor).
-      const bool to_table = goes_to_xdt(kind);
+      const bool to_table = goes_to_xdt(kind) || in_table[id];
       {
         const IdEntry &ie = L.idtab[id];
         SkUnit su;
         su.off = unit_off; su.end = p; su.size = size;
-        su.ntasks = sk_unit_tasks(kind, size, delta, ie.sl, ie.recip);
+        su.ntasks = sk_unit_tasks(ie.kind_align & 0xff, size, ie.delta, ie.sl, ie.recip);
         su.row = row; su.reach = to_table ? 0 : span;   // the stream kernel adds nothing for a table unit
         su.cmin = cmin; su.cmax = cmax; su.val = v; su.cursor_before = cursor_before;
         su.multi_bcol = kind == K_BCOL && su.ntasks > 1;
@@ -445,6 +518,33 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
             blocks.push_back(BlockTmp{td, kind, align, delta, cmin, cmax});
           }
         }
+      } else if (in_table[id]) {
+        // block tables: one entry per sub-block under the group of rows it adds to (own rows here, images at the owners
+        // of its columns)
+        const int64_t grow = cp.row_start + row;
+        if (kind == K_BCOL) {
+          const int64_t A = out.bc_align, R0 = out.bc_rows;
+          for (int64_t k = 0; k * R0 < (int64_t)delta; k++) {
+            const uint32_t vo = d.voff + (uint32_t)(k * R0 * A);
+            btents.push_back(BtEnt{(int64_t)pi, 0, (grow + k * R0) / R0, BlockImage{vo, (int32_t)start_col}});
+            if (m.symmetric)
+              for (int64_t g = cmin; g <= cmax;) {   // columns owned by one partition, or cut by a partition boundary
+                const int64_t q = owner_of(g);
+                if (q < 0) return "symmetric update targets a row that is not on this device";
+                btents.push_back(BtEnt{q, 1, g / A, BlockImage{vo, (int32_t)(grow + k * R0)}});
+                g = std::min(cmax + 1, q_start((size_t)q) + q_rows((size_t)q));
+              }
+          }
+        } else {
+          const int64_t A = out.br_align, C0 = out.br_cols;
+          for (int64_t k = 0; k * C0 < (int64_t)delta; k++)
+            btents.push_back(BtEnt{(int64_t)pi, 2, grow / A, BlockImage{d.voff + (uint32_t)(k * C0 * A), (int32_t)(start_col + k * C0)}});
+          if (m.symmetric) {   // image of a block-row unit: its columns are not aligned, a descriptor serves them
+            XDesc td = d;
+            td.meta |= XD_TRANSPOSED;
+            if (!list_rows(td, cmin, cmax, pend)) return "symmetric update targets a row that is not on this device";
+          }
+        }
       } else {
         for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) pend.push_back(Pending{(int64_t)pi, t, d});
         if (m.symmetric) {  // transposed image, listed under the tiles of its columns
@@ -484,49 +584,46 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
   out.total_ctl = cbase;
   if (vbase >= (uint64_t(1) << 32)) return "more than 2^32 values on one device";
 
-  // CSX-Sym block images: block-column units of the most frequent shape go to the compact tables (one 8-byte
-  // entry per unit, found through the aligned block row it updates), all other block units get descriptors
-  struct FastEnt { int64_t q, jrel; BlockImage b; };
-  std::vector<FastEnt> fast;
-  if (!blocks.empty()) {
-    std::map<std::pair<uint32_t, uint32_t>, size_t> shapes;
-    for (const BlockTmp &b : blocks) if (b.kind == K_BCOL) shapes[std::make_pair(b.align, b.other)]++;
-    size_t best = 0;
-    for (auto &kv : shapes) if (kv.second > best) { best = kv.second; out.bimg_align = (int)kv.first.first; out.bimg_rows = (int)kv.first.second; }
-    for (const BlockTmp &b : blocks) {
-      if (b.kind == K_BCOL && (int)b.align == out.bimg_align && (int)b.other == out.bimg_rows) {
-        const int64_t A = out.bimg_align;   // block-column units start at columns that are multiples of their width
-        if (b.cmin % A) {
-          if (!list_rows(b.d, b.cmin, b.cmax, pend)) return "symmetric update targets a row that is not on this device";
-          continue;
-        }
-        for (int64_t g = b.cmin; g <= b.cmax;) {
-          const int64_t q = owner_of(g);
-          if (q < 0) return "symmetric update targets a row that is not on this device";
-          fast.push_back(FastEnt{q, g / A - q_start((size_t)q) / A, BlockImage{b.d.voff, b.d.row}});
-          g = std::min(b.cmax + 1, q_start((size_t)q) + q_rows((size_t)q));   // the rest belongs to the next owner
-        }
-      } else if (!list_rows(b.d, b.cmin, b.cmax, pend)) return "symmetric update targets a row that is not on this device";
+  // CSX-Sym: images of the block units that stayed with the stream kernel
+  for (const BlockTmp &b : blocks)
+    if (!list_rows(b.d, b.cmin, b.cmax, pend)) return "symmetric update targets a row that is not on this device";
+  // block tables: counting sort of the entries by (owner, table, group); source order inside a group (deterministic sums)
+  if (!btents.empty()) {
+    for (size_t q = 0; q < nq; q++) {
+      PartLayout &L = out.parts[q];
+      if (!L.nrows) continue;
+      L.bt.resize(BT_MAX);
+      for (int t = 0; t < BT_MAX; t++) {
+        BlockTable &T = L.bt[t];
+        if (t == 0) { T.G = out.bc_rows; T.nloop = out.bc_align; T.sf = out.bc_align; T.sl = 1; }
+        else if (t == 1) { T.G = out.bc_align; T.nloop = out.bc_rows; T.sf = 1; T.sl = out.bc_align; T.image = 1; }
+        else { T.G = out.br_align; T.nloop = out.br_cols; T.sf = 1; T.sl = out.br_align; }
+        if (T.G <= 0) { T.G = 1; continue; }
+        T.j0 = L.row_start / T.G;
+        T.ptr.assign((size_t)((L.row_start + L.nrows - 1) / T.G - T.j0 + 1) + 1, 0);
+      }
     }
-  }
-  for (size_t q = 0; q < nq && out.bimg_align; q++) {
-    PartLayout &L = out.parts[q];
-    if (!L.nrows) continue;
-    const int64_t A = out.bimg_align;
-    L.bimg_j0 = L.row_start / A;
-    const int64_t nj = (L.row_start + L.nrows - 1) / A - L.bimg_j0 + 1;
-    L.bimg_ptr.assign((size_t)nj + 1, 0);
-  }
-  for (const FastEnt &e : fast) out.parts[e.q].bimg_ptr[(size_t)e.jrel + 1]++;
-  for (size_t q = 0; q < nq; q++) {
-    PartLayout &L = out.parts[q];
-    for (size_t j = 1; j < L.bimg_ptr.size(); j++) L.bimg_ptr[j] += L.bimg_ptr[j - 1];
-    if (!L.bimg_ptr.empty()) L.bimg.resize(L.bimg_ptr.back());
-  }
-  {
-    std::vector<std::vector<uint32_t>> at(nq);
-    for (size_t q = 0; q < nq; q++) at[q].assign(out.parts[q].bimg_ptr.begin(), out.parts[q].bimg_ptr.end());
-    for (const FastEnt &e : fast) out.parts[e.q].bimg[at[e.q][(size_t)e.jrel]++] = e.b;   // source order: deterministic sums
+    for (const BtEnt &e : btents) {
+      BlockTable &T = out.parts[e.q].bt[e.tab];
+      T.ptr[(size_t)(e.grp - T.j0) + 1]++;
+    }
+    std::vector<std::vector<uint32_t>> at(nq * BT_MAX);
+    for (size_t q = 0; q < nq; q++)
+      for (int t = 0; t < BT_MAX && !out.parts[q].bt.empty(); t++) {
+        BlockTable &T = out.parts[q].bt[t];
+        for (size_t j = 1; j < T.ptr.size(); j++) T.ptr[j] += T.ptr[j - 1];
+        if (!T.ptr.empty()) T.ent.resize(T.ptr.back());
+        at[q * BT_MAX + t].assign(T.ptr.begin(), T.ptr.end());
+      }
+    for (const BtEnt &e : btents) {
+      BlockTable &T = out.parts[e.q].bt[e.tab];
+      T.ent[at[(size_t)e.q * BT_MAX + e.tab][(size_t)(e.grp - T.j0)]++] = e.b;
+    }
+    for (size_t q = 0; q < nq; q++) {   // keep the tables that have entries
+      std::vector<BlockTable> keep;
+      for (BlockTable &T : out.parts[q].bt) if (!T.ent.empty()) keep.push_back(std::move(T));
+      out.parts[q].bt.swap(keep);
+    }
   }
 
   // distribute the descriptors: stable counting sort by (owner, tile)

@@ -16,8 +16,7 @@
 //   * CSX-Sym: the transposed update y[col] += v * x[row] of every stored
 //     element is a gather as well — the transposed image of every unit is
 //     listed under the tiles of its *columns* (a descriptor with the
-//     XD_TRANSPOSED flag; block-column units of the dominant shape go to a
-//     compact table indexed by the aligned block row they update).  Phase 1
+//     XD_TRANSPOSED flag, or an entry of a block table).  Phase 1
 //     (stream kernel + direct table units) computes the lower triangle's own
 //     rows, phase 2 (gather kernel) adds the images: no write conflicts, no
 //     atomics, bit-reproducible — the counterpart of the reference's
@@ -106,7 +105,24 @@ SPXB_HD inline uint32_t sk_unit_tasks(uint32_t kind, uint32_t size, uint32_t del
   return 1;                                                       // table units: one empty task
 }
 
-struct BlockImage { uint32_t voff; int32_t urow; };   // first value (device wide), global row of the unit's first row
+// Block tables: block-row and block-column units whose shape and alignment allow it are cut into sub-blocks of one
+// shape per table, and every sub-block gets an 8-byte entry in the list of the aligned group of G rows it adds to.
+// The thread that owns global row g (gather kernel) walks the entries of group g / G and adds
+//   sum over l < nloop of  values[voff + (g % G) * sf + l * sl] * x[other + l].
+//   block-column unit, own rows (rows x A, row-major):   G = sub-block rows, nloop = A, sf = A, sl = 1, other = first column
+//   block-column unit, CSX-Sym image (y[col] += v*x[row]): G = A, nloop = sub-block rows, sf = 1, sl = A, other = first row
+//   block-row unit, own rows (A x cols, column-major):   G = A, nloop = sub-block columns, sf = 1, sl = A, other = first column
+// No ctl decoding, no write conflicts; under CSX-Sym both uses of a value happen in the same kernel, close in time, so
+// the second one is an L2 hit.
+struct BlockImage { uint32_t voff; int32_t other; };   // first value of the sub-block (device wide), first column / row
+struct BlockTable {
+  int G = 1, nloop = 0, sf = 0, sl = 0;
+  int image = 0;                         // CSX-Sym images (y[col] += v*x[row]) rather than the units' own rows
+  int64_t j0 = 0;                        // global index of the partition's first group
+  std::vector<uint32_t> ptr;             // groups + 1
+  std::vector<BlockImage> ent;
+};
+constexpr int BT_MAX = 3;                // tables per partition
 
 struct PartLayout {
   int64_t nrows = 0, row_start = 0, nnz = 0, ctl_size = 0;
@@ -140,10 +156,7 @@ struct PartLayout {
   std::vector<uint32_t> tile_xoff;       // ntiles + 1
   std::vector<XDesc> xdesc;
   int64_t flat_elems = 0;                // non-zeros handled by the stream kernel
-  // CSX-Sym: transposed images of block-column units of the device's dominant shape, by the aligned block row they update
-  std::vector<uint32_t> bimg_ptr;        // block rows + 1
-  std::vector<BlockImage> bimg;
-  int64_t bimg_j0 = 0;                   // global index of the partition's first aligned block row
+  std::vector<BlockTable> bt;            // block tables (see BlockTable)
 };
 
 struct DeviceLayout {
@@ -151,8 +164,9 @@ struct DeviceLayout {
   std::vector<PartLayout> parts;
   uint64_t total_values = 0, total_ctl = 0;
   bool symmetric = false, full_colind = false;
-  // CSX-Sym: shape of the block-column units whose images live in the bimg tables (0: none)
-  int bimg_align = 0, bimg_rows = 0;
+  // block units that live in the block tables: block-column units of width bc_align cut into sub-blocks of bc_rows rows
+  // (0: none), block-row units of height br_align cut into sub-blocks of br_cols columns (0: none)
+  int bc_align = 0, bc_rows = 0, br_align = 0, br_cols = 0;
   // CSX-Sym with only some partitions on this device: rows [halo_lo, halo_hi) of lower ranks that local units
   // update; parts.back() is their pseudo-partition (is_halo)
   int64_t halo_lo = 0, halo_hi = 0;

@@ -8,6 +8,12 @@
 using namespace spxb;
 
 // ------------------------------------------------------------ device side --
+struct BtDev {                 // one block table (gpu_layout.hpp: BlockTable)
+  const uint32_t *ptr;
+  const uint2 *ent;            // {first value of the sub-block (device wide), first column / row}
+  long long j0;
+  int G, nloop, sf, sl, image;
+};
 struct PartDev {
   const uint8_t *ctl;          // this partition's ctl bytes (16-byte aligned, CTL_PAD readable bytes behind)
   const double *values;        // device-wide values array
@@ -20,12 +26,8 @@ struct PartDev {
   int full_colind;
   int rpt;                     // rows per thread: a tile has CTA_THREADS * rpt rows
   uint32_t tile0;              // first tile of this launch (a launch may cover a sub-range)
-  // CSX-Sym: images of block-column units of the device's dominant shape (bimg_rows x bimg_align), by the aligned
-  // block row they update (gpu_layout.hpp)
-  const uint32_t *bimg_ptr;
-  const uint2 *bimg;           // {first value (device wide), global row of the unit's first row}
-  long long bimg_j0;
-  int bimg_align, bimg_rows;
+  BtDev bt[BT_MAX];            // block tables (gpu_layout.hpp: BlockTable)
+  int nbt;
   // stream kernel (stream_kernel.cuh; non-symmetric partitions)
   const uint4 *sk_chunks;      // 32-byte chunk entries (SkEntry)
   const uint16_t *sk_uoffs;    // unit head offsets inside the chunks

@@ -91,11 +91,19 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     P.full_colind = L.full_colind;
     P.rpt = pl.rpt;
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
-    if (!pl.bimg.empty()) {
-      P.bimg_ptr = pl.bimg_ptr.data(); P.bimg = reinterpret_cast<const uint2 *>(pl.bimg.data()); P.bimg_j0 = pl.bimg_j0;
-      P.bimg_align = L.bimg_align; P.bimg_rows = L.bimg_rows;
-      if (stats) stats[12] += (int64_t)pl.bimg.size();
+    for (size_t t = 0; t < pl.bt.size(); t++) {
+      const BlockTable &T = pl.bt[t];
+      P.bt[t] = BtDev{T.ptr.data(), reinterpret_cast<const uint2 *>(T.ent.data()), (long long)T.j0, T.G, T.nloop, T.sf, T.sl, T.image};
+      if (stats) stats[12] += (int64_t)T.ent.size();
+      if (T.image) continue;   // decoded coordinates of the block-table units (csx_decode_bt_kernel)
+      for (int64_t lr = 0; lr < pl.nrows; lr++) {
+        const int64_t g = pl.row_start + lr, J = g / T.G;
+        const int f = (int)(g - J * T.G) * T.sf;
+        for (uint32_t e = T.ptr[J - T.j0]; e < T.ptr[J - T.j0 + 1]; e++)
+          for (int l = 0; l < T.nloop; l++) { dec_rows[T.ent[e].voff + f + l * T.sl] = (int32_t)g; dec_cols[T.ent[e].voff + f + l * T.sl] = T.ent[e].other + l; }
+      }
     }
+    P.nbt = (int)pl.bt.size();
     P.sk_chunks = reinterpret_cast<const uint4 *>(pl.sk_chunks.data());
     P.sk_uoffs = pl.sk_uoffs.data();
     scratch[i].assign(pl.sk_scratch + 2, std::nan(""));
@@ -151,7 +159,8 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     const PartLayout &pl = L.parts[i];
     const PartDev &P = pdev[i];
     const bool xd = !pl.xdesc.empty(), diag1 = !M.symmetric && pl.xd_diag1_only && xd;
-    if (streamed[i] && !xd && !M.symmetric) continue;
+    const bool bt = !pl.bt.empty();
+    if (streamed[i] && !xd && !bt && !M.symmetric) continue;
     const double beta = streamed[i] ? 1.0 : 0.0;
     const int ow = streamed[i] ? 0 : 1;
     for (int64_t t = 0; t < pl.ntiles; t++)
@@ -160,18 +169,18 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
         warp_emul::run_warp([&](int) {
           const NoXchg nx;
           if (M.symmetric) {
-            if (pl.rpt == 4) { if (xd) spmv_tile<true, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
-                               else spmv_tile<false, true, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0); }
-            else { if (xd) spmv_tile<true, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
-                   else spmv_tile<false, true, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0); }
+            if (pl.rpt == 4) { if (xd) (bt ? spmv_tile<true, true, 4, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<true, true, 4, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
+                               else (bt ? spmv_tile<false, true, 4, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<false, true, 4, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0); }
+            else { if (xd) (bt ? spmv_tile<true, true, 1, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<true, true, 1, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
+                   else (bt ? spmv_tile<false, true, 1, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<false, true, 1, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0); }
           } else if (pl.rpt == 4) {
-            if (diag1) spmv_tile<true, false, 4, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
-            else if (xd) spmv_tile<true, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
-            else spmv_tile<false, false, 4, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            if (diag1) (bt ? spmv_tile<true, false, 4, KSET_DIAG1, 0, false, NoXchg, true> : spmv_tile<true, false, 4, KSET_DIAG1, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else if (xd) (bt ? spmv_tile<true, false, 4, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<true, false, 4, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else (bt ? spmv_tile<false, false, 4, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<false, false, 4, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
           } else {
-            if (diag1) spmv_tile<true, false, 1, KSET_DIAG1, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
-            else if (xd) spmv_tile<true, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
-            else spmv_tile<false, false, 1, KSET_ANY, 0, false, NoXchg>(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            if (diag1) (bt ? spmv_tile<true, false, 1, KSET_DIAG1, 0, false, NoXchg, true> : spmv_tile<true, false, 1, KSET_DIAG1, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else if (xd) (bt ? spmv_tile<true, false, 1, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<true, false, 1, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
+            else (bt ? spmv_tile<false, false, 1, KSET_ANY, 0, false, NoXchg, true> : spmv_tile<false, false, 1, KSET_ANY, 0, false, NoXchg, false>)(P, x, y, alpha, beta, ow, t, t, nx, 0);
           }
         });
       }

@@ -101,14 +101,37 @@ def _blocks(nbr, r, c, per_row, seed, ncols_b):
     return rp, ci, va, nbr * r, ncols_b * c
 
 
-def test_emulated_stream_kernel_shaped_instantiations():
-    """The pattern-set instantiations with compile-time block shapes (stream_kernel.cuh: SK_INSTANCES) are the ones
-    the dispatcher picks for uniform blocks, and they multiply correctly (stats[3] = R*1000 + BC*100 + BRC*10)."""
+def test_emulated_stream_kernel_shaped_instantiations(monkeypatch):
+    """Block units that cannot live in the block tables stay with the stream kernel (here: tables switched off).  The
+    pattern-set instantiations with compile-time block shapes (stream_kernel.cuh: SK_INSTANCES) are the ones the
+    dispatcher picks for uniform blocks, and they multiply correctly (stats[3] = R*1000 + BC*100 + BRC*10)."""
+    monkeypatch.setenv("CSXB_NO_BLOCK_TABLES", "1")
     want = {(3, 3, "bc"): 3300, (2, 2, "bc"): 2200, (4, 2, "bc"): 4200, (2, 4, "br"): 2040, (3, 8, "br"): 3040, (3, 3, "br"): 4000}
     for (r, c, xf), inst in want.items():
         rp, ci, va, n, m = _blocks(200, r, c, 3, 1, 150)
         st = _check(rp, ci, va, n, m, {"spx.preproc.xform": xf, "spx.preproc.sampling": "none"})
-        assert st[3] == inst, ((r, c, xf), st[3])
+        assert st[3] == inst and st[12] == 0, ((r, c, xf), st[3])
+
+
+def test_emulated_block_tables():
+    """Aligned block units live in the block tables of the gather kernel (gpu_layout.hpp: BlockTable): own rows of
+    block-column and block-row units, CSX-Sym images of block-column units; unaligned ones stay with the stream kernel."""
+    for (r, c, xf) in ((3, 3, "bc"), (2, 2, "bc"), (6, 2, "bc"), (2, 4, "br"), (3, 8, "br"), (3, 3, "br,bc")):
+        rp, ci, va, n, m = _blocks(200, r, c, 3, 1, 150)
+        for nt in (1, 3):
+            st = _check(rp, ci, va, n, m, {"spx.preproc.xform": xf, "spx.preproc.sampling": "none", "spx.rt.nr_threads": nt})
+            assert st[12] > 0, ((r, c, xf), st)
+    from tests.matrices import sym_block_banded
+    rp, ci, va, n = sym_block_banded(1500, b=64)
+    for xf in ("bc", "br", "all"):
+        for nt in (1, 2, 5):
+            st = _check(rp, ci, va, n, n, {"spx.matrix.symmetric": "true", "spx.preproc.xform": xf, "spx.preproc.sampling": "none",
+                                          "spx.rt.nr_threads": nt}, sym=True)
+            assert st[12] > 0, (xf, nt, st)
+    # rows shifted by one: block-column units start at odd rows, no common sub-block -> stream kernel
+    rp, ci, va, n, m = _blocks(100, 2, 2, 3, 2, 80)
+    rp2 = np.concatenate([[0], rp]).astype(np.int32)
+    st = _check(rp2, ci, va, n + 1, m, {"spx.preproc.xform": "bc", "spx.preproc.sampling": "none"})
 
 
 def test_emulated_stream_kernel_long_rows_gaps_tall_blocks():
