@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(CTA_THREADS) csx_decode_bt_kernel(const __grid
     const int f = (int)(g - J * T.G) * T.sf;
     for (uint32_t e = T.ptr[J - T.j0]; e < T.ptr[J - T.j0 + 1]; e++) {
       const uint2 b = T.ent[e];
+      if (b.y & BT_IMAGE) continue;
       for (int l = 0; l < T.nloop; l++) { rows[b.x + f + l * T.sl] = (int)g; cols[b.x + f + l * T.sl] = (int)b.y + l; }
     }
   }

@@ -250,7 +250,7 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
         for (uint32_t e = e0; e < e1; e++) {
           const uint2 b = __ldg(T.ent + e);
           const double *__restrict__ vp = values + b.x + f;
-          const double *__restrict__ xp = x + (int)b.y;
+          const double *__restrict__ xp = x + (b.y & ~BT_IMAGE);
           for (int l = 0; l < T.nloop; l++) acc[k] += __ldg(vp + l * T.sl) * __ldg(xp + l);
         }
       }

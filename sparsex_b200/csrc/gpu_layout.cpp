@@ -310,7 +310,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       }
     if (getenv("CSXB_NO_BLOCK_TABLES")) out.bc_align = out.bc_rows = out.br_align = out.br_cols = 0;   // tuning aid
   }
-  // tables of a partition: 0 block-column own rows, 1 block-column images (CSX-Sym), 2 block-row own rows
+  // entries of the block tables (table numbers: gpu_layout.hpp)
   struct BtEnt { int64_t q; int tab; int64_t grp; BlockImage b; };
   std::vector<BtEnt> btents;
   // CSX-Sym: images of the block units that stay with the stream kernel get descriptors
@@ -398,9 +398,12 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     // A partition whose stream-kernel share is tiny (stencil matrices: a few boundary elements next to
     // millions of diagonal units) gets those elements as one-element table units instead; that saves the
     // second kernel launch.  Coordinates are collected while the share stays under the cap.
-    struct Single { int64_t row, col, v; };
+    // A larger minority (up to 40 % of the non-zeros; block stencils, the diagonal-block leftovers of a block-banded
+    // matrix) goes to the table of single elements instead (gpu_layout.hpp: BlockTable 4): 8 bytes per element, again
+    // no stream kernel.
+    struct Single { int32_t row, col; uint32_t v; };
     std::vector<Single> singles;
-    const size_t single_cap = (size_t)(cp.nnz / 256);
+    const size_t single_cap = (size_t)(cp.nnz / 256), element_cap = getenv("CSXB_NO_BLOCK_TABLES") ? single_cap : (size_t)(cp.nnz / 5 * 2);
     bool singles_ok = true;
     // CSX-Sym: images of this partition's stream units (dropped again if the units are folded into the table)
     std::vector<Pending> simg;
@@ -489,7 +492,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
       if (!to_table) {
         L.has_flat = true;
         L.flat_elems += size;
-        if (singles_ok && singles.size() + size <= single_cap) {
+        if (singles_ok && singles.size() + size <= element_cap) {
           // element coordinates of this unit (same geometry as the stream kernel)
           for (int k = 0; k < size; k++) {
             int64_t er = row, ec = start_col;
@@ -497,7 +500,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
             else if (kind == K_HORIZ) ec = start_col + (int64_t)k * delta;
             else if (kind == K_BROW) { er = row + k % (int)align; ec = start_col + k / (int)align; }
             else { er = row + k / (int)align; ec = start_col + k % (int)align; }
-            singles.push_back(Single{er, ec, v + k});
+            singles.push_back(Single{(int32_t)er, (int32_t)ec, (uint32_t)(v + k)});
           }
         } else {
           singles_ok = false;
@@ -526,24 +529,25 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
           const int64_t A = out.bc_align, R0 = out.bc_rows;
           for (int64_t k = 0; k * R0 < (int64_t)delta; k++) {
             const uint32_t vo = d.voff + (uint32_t)(k * R0 * A);
-            btents.push_back(BtEnt{(int64_t)pi, 0, (grow + k * R0) / R0, BlockImage{vo, (int32_t)start_col}});
+            btents.push_back(BtEnt{(int64_t)pi, 0, (grow + k * R0) / R0, BlockImage{vo, (uint32_t)start_col}});
             if (m.symmetric)
               for (int64_t g = cmin; g <= cmax;) {   // columns owned by one partition, or cut by a partition boundary
                 const int64_t q = owner_of(g);
                 if (q < 0) return "symmetric update targets a row that is not on this device";
-                btents.push_back(BtEnt{q, 1, g / A, BlockImage{vo, (int32_t)(grow + k * R0)}});
+                btents.push_back(BtEnt{q, 1, g / A, BlockImage{vo, (uint32_t)(grow + k * R0) | BT_IMAGE}});
                 g = std::min(cmax + 1, q_start((size_t)q) + q_rows((size_t)q));
               }
           }
         } else {
           const int64_t A = out.br_align, C0 = out.br_cols;
           for (int64_t k = 0; k * C0 < (int64_t)delta; k++)
-            btents.push_back(BtEnt{(int64_t)pi, 2, grow / A, BlockImage{d.voff + (uint32_t)(k * C0 * A), (int32_t)(start_col + k * C0)}});
-          if (m.symmetric) {   // image of a block-row unit: its columns are not aligned, a descriptor serves them
-            XDesc td = d;
-            td.meta |= XD_TRANSPOSED;
-            if (!list_rows(td, cmin, cmax, pend)) return "symmetric update targets a row that is not on this device";
-          }
+            btents.push_back(BtEnt{(int64_t)pi, 2, grow / A, BlockImage{d.voff + (uint32_t)(k * C0 * A), (uint32_t)(start_col + k * C0)}});
+          if (m.symmetric)   // image of a block-row unit: one entry per column (its columns are not aligned)
+            for (int64_t j = 0; j < (int64_t)delta; j++) {
+              const int64_t q = owner_of(start_col + j);
+              if (q < 0) return "symmetric update targets a row that is not on this device";
+              btents.push_back(BtEnt{q, 3, start_col + j, BlockImage{d.voff + (uint32_t)(j * A), (uint32_t)grow | BT_IMAGE}});
+            }
         }
       } else {
         for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) pend.push_back(Pending{(int64_t)pi, t, d});
@@ -557,7 +561,24 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     }
     if (v != cp.nnz) return "ctl stream covers " + std::to_string(v) + " values, expected " + std::to_string(cp.nnz);
     if (L.has_flat) sk.finish(); else sk.discard();
-    if (L.has_flat && singles_ok && (int64_t)singles.size() == L.flat_elems) {
+    if (L.has_flat && singles_ok && (int64_t)singles.size() == L.flat_elems && singles.size() > single_cap) {
+      // the stream units are a minority: their elements go to the table of single elements
+      for (const Single &sg : singles) {
+        const uint32_t vo = (uint32_t)(L.val_base + (uint64_t)sg.v);
+        const int64_t grow = cp.row_start + sg.row;
+        btents.push_back(BtEnt{(int64_t)pi, 4, grow, BlockImage{vo, (uint32_t)sg.col}});
+        if (m.symmetric) {
+          const int64_t q = owner_of(sg.col);
+          if (q < 0) return "symmetric update targets a row that is not on this device";
+          btents.push_back(BtEnt{q, 4, sg.col, BlockImage{vo, (uint32_t)grow | BT_IMAGE}});
+        }
+      }
+      sk.discard();
+      simg.clear();
+      blocks.resize(blocks_before);
+      L.has_flat = false;
+      L.flat_elems = 0;
+    } else if (L.has_flat && singles_ok && (int64_t)singles.size() == L.flat_elems) {
       // fold the few stream-kernel elements into the table as diagonal units of one element
       for (const Single &sg : singles) {
         XDesc d;
@@ -597,7 +618,9 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         BlockTable &T = L.bt[t];
         if (t == 0) { T.G = out.bc_rows; T.nloop = out.bc_align; T.sf = out.bc_align; T.sl = 1; }
         else if (t == 1) { T.G = out.bc_align; T.nloop = out.bc_rows; T.sf = 1; T.sl = out.bc_align; T.image = 1; }
-        else { T.G = out.br_align; T.nloop = out.br_cols; T.sf = 1; T.sl = out.br_align; }
+        else if (t == 2) { T.G = out.br_align; T.nloop = out.br_cols; T.sf = 1; T.sl = out.br_align; }
+        else if (t == 3) { T.G = out.br_align ? 1 : 0; T.nloop = out.br_align; T.sf = 0; T.sl = 1; T.image = 1; }
+        else { T.G = 1; T.nloop = 1; T.sf = 0; T.sl = 0; }
         if (T.G <= 0) { T.G = 1; continue; }
         T.j0 = L.row_start / T.G;
         T.ptr.assign((size_t)((L.row_start + L.nrows - 1) / T.G - T.j0 + 1) + 1, 0);

@@ -109,12 +109,18 @@ SPXB_HD inline uint32_t sk_unit_tasks(uint32_t kind, uint32_t size, uint32_t del
 // shape per table, and every sub-block gets an 8-byte entry in the list of the aligned group of G rows it adds to.
 // The thread that owns global row g (gather kernel) walks the entries of group g / G and adds
 //   sum over l < nloop of  values[voff + (g % G) * sf + l * sl] * x[other + l].
-//   block-column unit, own rows (rows x A, row-major):   G = sub-block rows, nloop = A, sf = A, sl = 1, other = first column
-//   block-column unit, CSX-Sym image (y[col] += v*x[row]): G = A, nloop = sub-block rows, sf = 1, sl = A, other = first row
-//   block-row unit, own rows (A x cols, column-major):   G = A, nloop = sub-block columns, sf = 1, sl = A, other = first column
+//   0 block-column unit, own rows (rows x A, row-major):     G = sub-block rows, nloop = A, sf = A, sl = 1, other = first column
+//   1 block-column unit, CSX-Sym image (y[col] += v*x[row]): G = A, nloop = sub-block rows, sf = 1, sl = A, other = first row
+//   2 block-row unit, own rows (A x cols, column-major):     G = A, nloop = sub-block columns, sf = 1, sl = A, other = first column
+//   3 block-row unit, CSX-Sym image, one entry per column:   G = 1, nloop = A, sf = 0, sl = 1, other = first row
+//   4 single elements (own row: other = column; CSX-Sym image: other = row): G = 1, nloop = 1
+// Table 4 takes the elements of the delta / horizontal / unaligned block units of a partition in which such units are
+// a minority (at most 40 % of the non-zeros): the partition then needs no stream kernel at all.
 // No ctl decoding, no write conflicts; under CSX-Sym both uses of a value happen in the same kernel, close in time, so
 // the second one is an L2 hit.
-struct BlockImage { uint32_t voff; int32_t other; };   // first value of the sub-block (device wide), first column / row
+struct BlockImage { uint32_t voff; uint32_t other; };   // first value of the sub-block (device wide); first column / row,
+                                                        // bit 31: the entry is a CSX-Sym image (table 4 holds both sorts)
+constexpr uint32_t BT_IMAGE = 0x80000000u;
 struct BlockTable {
   int G = 1, nloop = 0, sf = 0, sl = 0;
   int image = 0;                         // CSX-Sym images (y[col] += v*x[row]) rather than the units' own rows
@@ -122,7 +128,7 @@ struct BlockTable {
   std::vector<uint32_t> ptr;             // groups + 1
   std::vector<BlockImage> ent;
 };
-constexpr int BT_MAX = 3;                // tables per partition
+constexpr int BT_MAX = 5;                // tables per partition
 
 struct PartLayout {
   int64_t nrows = 0, row_start = 0, nnz = 0, ctl_size = 0;

@@ -100,7 +100,9 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
         const int64_t g = pl.row_start + lr, J = g / T.G;
         const int f = (int)(g - J * T.G) * T.sf;
         for (uint32_t e = T.ptr[J - T.j0]; e < T.ptr[J - T.j0 + 1]; e++)
-          for (int l = 0; l < T.nloop; l++) { dec_rows[T.ent[e].voff + f + l * T.sl] = (int32_t)g; dec_cols[T.ent[e].voff + f + l * T.sl] = T.ent[e].other + l; }
+          for (int l = 0; l < T.nloop && !(T.ent[e].other & BT_IMAGE); l++) {
+            dec_rows[T.ent[e].voff + f + l * T.sl] = (int32_t)g; dec_cols[T.ent[e].voff + f + l * T.sl] = (int32_t)T.ent[e].other + l;
+          }
       }
     }
     P.nbt = (int)pl.bt.size();

@@ -75,7 +75,7 @@ def test_emulated_chunk_kernel_config_shapes():
     """Scaled-down BASELINE configs: block stencil, symmetric block-banded, R-MAT."""
     rp, ci, va, n = stencil27(14)
     st = _check(rp, ci, va, n, n, {"spx.preproc.xform": "br,bc", "spx.preproc.sampling": "none"})
-    assert st[0] > 0
+    assert st[0] > 0 or st[12] > 0   # stream chunks, or everything in the block tables
     _check(rp, ci, va, n, n, {"spx.preproc.xform": "br,bc", "spx.preproc.sampling": "none", "spx.rt.nr_threads": 4})
     rp, ci, va, n = sym_block_banded(800, b=40)
     for o in ({}, {"spx.matrix.symmetric": "true"}, {"spx.matrix.symmetric": "true", "spx.rt.nr_threads": 3}):
