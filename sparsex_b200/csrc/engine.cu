@@ -539,7 +539,7 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
       if (dev_copy(m, T.ptr.data(), T.ptr.size(), &bp)) return -1;
       if (dev_copy(m, T.ent.data(), T.ent.size(), &bi)) return -1;
       static_assert(sizeof(BlockImage) == sizeof(uint2), "block table entry layout");
-      P.bt[t] = BtDev{bp, (const uint2 *)bi, (long long)T.j0, T.G, T.nloop, T.sf, T.sl, T.image};
+      P.bt[t] = BtDev{bp, (const uint2 *)bi, (long long)T.j0, T.G, T.nloop, T.sf, T.sl, T.image, (uint32_t)((0x100000000ull + T.G - 1) / T.G)};
       tables += (int64_t)T.ptr.size() * 4 + (int64_t)T.ent.size() * 8;
     }
     P.nbt = (int)pl.bt.size();
@@ -575,7 +575,8 @@ int csxb_upload(csxb_matrix_t *m, int device, int free_host) {
     P.full_colind = L.full_colind;
     P.rpt = pl.rpt;
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
-    nnz_stored += hp.nnz; ctl_bytes += (int64_t)hp.ctl.size(); rows_owned += pl.nrows;   // halo rows are written too
+    nnz_stored += hp.nnz; rows_owned += pl.nrows;   // halo rows are written too
+    if (!pl.sk_chunks.empty()) ctl_bytes += (int64_t)hp.ctl.size();   // only the stream kernel reads ctl
     tables += (int64_t)pl.tile_xoff.size() * 4 + (int64_t)pl.xdesc.size() * 16;
     if (pl.nrows) {
       if (!pl.sk_chunks.empty())
@@ -621,9 +622,10 @@ static void launch_gather_k(const PartDev &P, const PartLayout &pl, unsigned nt,
     else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, 4, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
     return;
   }
-  // descriptors can also come from other partitions (transposed images under CSX-Sym)
-  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET, 8, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
-  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, 8, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+  // descriptors can also come from other partitions (transposed images under CSX-Sym, whose many kinds need registers)
+  constexpr int MB = SYM ? 4 : 8;
+  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET, MB, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, MB, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
 }
 template <bool SYM, class XP>
 static void launch_gather(const PartDev &P0, const PartLayout &pl, int64_t t0, int64_t t1, const double *x, double *y,

@@ -96,6 +96,43 @@ struct SpmvGatherOp {
   __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * __ldg(x + xi); }
 };
 
+// Entries [e0, e1) of one group of a block table for the row whose values start at `vals` inside every sub-block:
+// sum over entries of sum over l < nloop of vals[voff + l * sl] * x[other + l].  NL = nloop at compile time (0: any);
+// two entries at a time, all their loads issued before the first FMA.
+template <int NL>
+__device__ __forceinline__ double bt_row(const BtDev &T, const double *__restrict__ vals, const double *__restrict__ x, uint32_t e0,
+                                         uint32_t e1) {
+  constexpr int N = NL > 0 ? NL : 1;
+  const int sl = T.sl;
+  double a0 = 0.0, a1 = 0.0;
+  uint32_t e = e0;
+  if (NL > 0) {
+    for (; e + 1 < e1; e += 2) {
+      const uint2 b0 = __ldg(T.ent + e), b1 = __ldg(T.ent + e + 1);
+      const double *v0 = vals + b0.x, *v1 = vals + b1.x, *x0 = x + (b0.y & ~BT_IMAGE), *x1 = x + (b1.y & ~BT_IMAGE);
+      double va[N], xa[N], vb[N], xb[N];
+#pragma unroll
+      for (int l = 0; l < N; l++) { va[l] = __ldg(v0 + l * sl); xa[l] = __ldg(x0 + l); vb[l] = __ldg(v1 + l * sl); xb[l] = __ldg(x1 + l); }
+#pragma unroll
+      for (int l = 0; l < N; l++) { a0 += va[l] * xa[l]; a1 += vb[l] * xb[l]; }
+    }
+  }
+  for (; e < e1; e++) {
+    const uint2 b = __ldg(T.ent + e);
+    const double *vp = vals + b.x, *xp = x + (b.y & ~BT_IMAGE);
+    if (NL > 0) {
+      double va[N], xa[N];
+#pragma unroll
+      for (int l = 0; l < N; l++) { va[l] = __ldg(vp + l * sl); xa[l] = __ldg(xp + l); }
+#pragma unroll
+      for (int l = 0; l < N; l++) a0 += va[l] * xa[l];
+    } else {
+      for (int l = 0; l < T.nloop; l++) a0 += __ldg(vp + l * sl) * __ldg(xp + l);
+    }
+  }
+  return a0 + a1;
+}
+
 // ---- multi-GPU exchange over peer memory ---------------------------------------------------------------
 // One process per GPU.  Every rank holds two full-length vectors (ping-pong) in one cudaMalloc'ed block that
 // the other ranks map through CUDA IPC.  Step k reads vec[k & 1] and writes vec[(k + 1) & 1]: the SpMV kernel
@@ -239,19 +276,22 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
   // BlockTable; block_row_tmpl.c, block_col_tmpl.c, block_*_sym_tmpl.c); entries in source order
   for (int c = 0; BT && c < P.nbt; c++) {
     const BtDev &T = P.bt[c];
-    const double *__restrict__ values = P.values;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < RPT; k++) {
       const long long lrow = lrow0 + k * 32 + lane;
       if (lrow < P.nrows) {
-        const long long g = P.row_start + lrow, J = g / T.G;
-        const int f = (int)(g - J * T.G) * T.sf;
-        const uint32_t e0 = __ldg(T.ptr + (J - T.j0)), e1 = __ldg(T.ptr + (J - T.j0) + 1);
-        for (uint32_t e = e0; e < e1; e++) {
-          const uint2 b = __ldg(T.ent + e);
-          const double *__restrict__ vp = values + b.x + f;
-          const double *__restrict__ xp = x + (b.y & ~BT_IMAGE);
-          for (int l = 0; l < T.nloop; l++) acc[k] += __ldg(vp + l * T.sl) * __ldg(xp + l);
+        const uint32_t g = (uint32_t)(P.row_start + lrow);
+        uint32_t J = g;
+        if (T.G != 1) { J = __umulhi(g, T.magic); if (J * (uint32_t)T.G > g) J--; }   // g / G
+        const int f = (int)(g - J * (uint32_t)T.G) * T.sf;
+        const uint32_t *pp = T.ptr + ((long long)J - T.j0);
+        const uint32_t e0 = __ldg(pp), e1 = __ldg(pp + 1);
+        switch (T.nloop) {
+          case 1: acc[k] += bt_row<1>(T, P.values + f, x, e0, e1); break;
+          case 2: acc[k] += bt_row<2>(T, P.values + f, x, e0, e1); break;
+          case 3: acc[k] += bt_row<3>(T, P.values + f, x, e0, e1); break;
+          case 4: acc[k] += bt_row<4>(T, P.values + f, x, e0, e1); break;
+          default: acc[k] += bt_row<0>(T, P.values + f, x, e0, e1);
         }
       }
     }

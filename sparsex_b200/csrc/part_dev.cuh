@@ -13,6 +13,7 @@ struct BtDev {                 // one block table (gpu_layout.hpp: BlockTable)
   const uint2 *ent;            // {first value of the sub-block (device wide), first column / row}
   long long j0;
   int G, nloop, sf, sl, image;
+  uint32_t magic;              // ceil(2^32 / G): g / G == umulhi(g, magic) or one more
 };
 struct PartDev {
   const uint8_t *ctl;          // this partition's ctl bytes (16-byte aligned, CTL_PAD readable bytes behind)

@@ -93,7 +93,7 @@ extern "C" int emul_spmv(const int32_t *rowptr, const int32_t *colind, const dou
     memcpy(P.idtab, pl.idtab, sizeof(P.idtab));
     for (size_t t = 0; t < pl.bt.size(); t++) {
       const BlockTable &T = pl.bt[t];
-      P.bt[t] = BtDev{T.ptr.data(), reinterpret_cast<const uint2 *>(T.ent.data()), (long long)T.j0, T.G, T.nloop, T.sf, T.sl, T.image};
+      P.bt[t] = BtDev{T.ptr.data(), reinterpret_cast<const uint2 *>(T.ent.data()), (long long)T.j0, T.G, T.nloop, T.sf, T.sl, T.image, (uint32_t)((0x100000000ull + T.G - 1) / T.G)};
       if (stats) stats[12] += (int64_t)T.ent.size();
       if (T.image) continue;   // decoded coordinates of the block-table units (csx_decode_bt_kernel)
       for (int64_t lr = 0; lr < pl.nrows; lr++) {

@@ -141,6 +141,7 @@ inline unsigned __match_any_sync(unsigned, unsigned v) {
   return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline void __syncwarp() { warp_emul::exchange(0); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
