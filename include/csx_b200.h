@@ -41,6 +41,15 @@ csxb_matrix_t *csxb_tune_csr(const int32_t *rowptr, const int32_t *colind, const
                              int part_lo, int part_hi, char *err, size_t errlen);
 csxb_matrix_t *csxb_tune_mmf(const char *path, const char *options, int part_lo, int part_hi,
                              char *err, size_t errlen);
+/* One process per GPU on matrices too large for one host: the CSR arrays hold exactly the rows
+ * [row_start, row_start + slab_rows) of partition `part` of the spx.rt.nr_threads-way split of a matrix
+ * with nrows_total rows (rowptr is relative to the slab; the caller applies the split rule of
+ * SparseInternal.hpp:119-152 to the row lengths).  The partition is encoded from its own rows alone, like
+ * the reference's per-thread preprocessing (CsxBuild.hpp:134-288), and equals what csxb_tune_csr yields
+ * for it on the whole matrix.  CSX-Sym: no reduction map (it needs every partition). */
+csxb_matrix_t *csxb_tune_csr_slab(const int32_t *rowptr, const int32_t *colind, const double *values,
+                                  int64_t slab_rows, int64_t nrows_total, int64_t ncols, int64_t row_start,
+                                  int part, const char *options, char *err, size_t errlen);
 void csxb_destroy(csxb_matrix_t *m);
 
 /* Matrix-level queries (spx_mat_get_nrows/ncols/nnz, src/api/matvec.c:447-476). */

@@ -20,7 +20,7 @@
 #include "csx_host.hpp"
 
 // defined in engine.cu (C++ linkage): tune from an in-memory COO input
-csxb_matrix_t *csxb_tune_coo_internal(const spxb::CooHost &coo, const char *options, char *err, size_t errlen);
+csxb_matrix_t *csxb_tune_coo_internal(const spxb::CooHost &coo, const char *options, int part_lo, int part_hi, char *err, size_t errlen);
 
 namespace {
 
@@ -33,6 +33,7 @@ int g_device = 0;
 bool g_async = false;
 bool g_gpu_ok = false;   // a managed vector was allocated successfully: a usable GPU is present
 int g_part_lo = 0, g_part_hi = -1;   // one process per GPU: encode and own only partitions [lo, hi)
+long long g_slab_row_start = -1, g_slab_total_rows = 0;   // the input holds only the rows of partition g_part_lo (csxb_tune_csr_slab)
 int g_log_level = 2;  // 0 none, 1 error, 2 warning, 3 info, 4 verbose, 5 debug
 FILE *g_log_file = nullptr;
 
@@ -165,6 +166,8 @@ void spx_option_set(const char *option, const char *value) {  // matvec.c:753-75
   if (k == "spx.b200.async") { g_async = (v == "true" || v == "1"); return; }
   if (k == "spx.b200.part_lo") { g_part_lo = atoi(value); return; }
   if (k == "spx.b200.part_hi") { g_part_hi = atoi(value); return; }
+  if (k == "spx.b200.slab_row_start") { g_slab_row_start = atoll(value); return; }
+  if (k == "spx.b200.slab_total_rows") { g_slab_total_rows = atoll(value); return; }
   spxb::TuneOptions probe;
   std::string e = probe.set(k, v);
   if (!e.empty()) {
@@ -237,11 +240,14 @@ spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
   char err[512] = "";
   std::string opts = options_string();
   csxb_matrix_t *m = nullptr;
-  if (in->type == 'C')
+  if (in->type == 'C' && g_slab_row_start >= 0)   // the arrays hold the rows of partition g_part_lo only
+    m = csxb_tune_csr_slab(in->rowptr, in->colind, in->values, in->nrows, g_slab_total_rows, in->ncols, g_slab_row_start, g_part_lo,
+                           opts.c_str(), err, sizeof(err));
+  else if (in->type == 'C')
     m = csxb_tune_csr(in->rowptr, in->colind, in->values, in->nrows, in->ncols, opts.c_str(), g_part_lo, g_part_hi, err,
                       sizeof(err));
   else if (in->type == 'M')
-    m = csxb_tune_coo_internal(*in->coo, opts.c_str(), err, sizeof(err));
+    m = csxb_tune_coo_internal(*in->coo, opts.c_str(), g_part_lo, g_part_hi, err, sizeof(err));
   if (!m) { spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
   if (csxb_upload(m, g_device, 0) != 0) {
     spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
@@ -249,7 +255,7 @@ spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
     return SPX_INVALID_MAT;
   }
   spx_matrix_t *A = spx_malloc(spx_matrix_t, sizeof(spx_matrix_t));
-  A->nrows = in->nrows; A->ncols = in->ncols; A->nnz = in->nnz;
+  A->nrows = (int)csxb_info(m, CSXB_NROWS); A->ncols = in->ncols; A->nnz = in->nnz;
   A->symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
   A->permutation = SPX_INVALID_PERM;
   A->csx = m;

@@ -100,5 +100,10 @@ std::string read_mmf(const char *path, CooHost &out);
 // only scanned to find their row boundaries.
 std::string tune_csr(const CsrView &in, const TuneOptions &opt, int part_lo, int part_hi, CsxMatrix &out);
 std::string tune_coo(const CooHost &in, const TuneOptions &opt, int part_lo, int part_hi, CsxMatrix &out);
+// One process per GPU on matrices too large for one host: `slab` holds exactly the rows [row_start, row_start +
+// slab.nrows) of partition `part` of the nr_threads-way split of a matrix with nrows_total rows (the caller applies the
+// split rule to the row lengths); the partition is encoded from its own rows alone, as the reference's per-thread
+// preprocessing does (CsxBuild.hpp:134-288).  CSX-Sym: no reduction map (it needs every partition).
+std::string tune_csr_slab(const CsrView &slab, int64_t nrows_total, int64_t row_start, int part, const TuneOptions &opt, CsxMatrix &out);
 
 }  // namespace spxb

@@ -1029,12 +1029,13 @@ struct Cursor {
   const CsrView *csr = nullptr;
   const CooHost *coo = nullptr;
   int64_t pos = 0, n = 0, row = 0;  // csr: row = current 0-based row
+  int64_t roff = 0;                 // csr slab input: global row of the slab's first row
   void init() {
     if (csr) { n = csr->nnz(); row = 0; while (row < csr->nrows && csr->rowptr[row + 1] <= 0) row++; }
     else n = (int64_t)coo->row.size();
   }
   bool end() const { return pos >= n; }
-  int32_t r() const { return csr ? (int32_t)row + 1 : coo->row[pos]; }
+  int32_t r() const { return csr ? (int32_t)(row + roff) + 1 : coo->row[pos]; }
   int32_t c() const { return csr ? csr->colind[pos] + 1 : coo->col[pos]; }   // Csr.hpp:352-367
   double v() const { return csr ? csr->values[pos] : coo->val[pos]; }
   void next() {
@@ -1073,7 +1074,7 @@ SplitResult take_partition(Cursor &cur, int64_t row_start, size_t limit, bool sy
         const int64_t pos = pos0 + (int64_t)k;
         while (A.rowptr[row + 1] <= pos) row++;
         const int32_t col = A.colind[pos] + 1;
-        p.e[k] = Rec{(int32_t)(row + 1 - row_start), col, 0, 0, 1, 0, (uint64_t)(pbase + k)};
+        p.e[k] = Rec{(int32_t)(row + cur.roff + 1 - row_start), col, 0, 0, 1, 0, (uint64_t)(pbase + k)};
         pool[pbase + k] = A.values[pos];
         lo = std::min(lo, col); hi = std::max(hi, col);
       }
@@ -1213,8 +1214,10 @@ void build_sym_map(const std::vector<Part> &lowers, int64_t ncols, std::vector<C
         if (seen[k][j]) { outs[np - 1]->map_cpus.push_back((uint32_t)k); outs[np - 1]->map_pos.push_back((uint32_t)(j - 1)); }
 }
 
+// slab_part >= 0: the input holds exactly the rows of partition `slab_part` of the nr_threads-way split (first row
+// cur.roff); the partition is encoded from them alone.
 std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptions &opt, int part_lo, int part_hi,
-                      CsxMatrix &out) {
+                      CsxMatrix &out, int slab_part = -1) {
   try {
     if (opt.nr_threads < 1) throw TuneError("invalid value for spx.rt.nr_threads");
     if (opt.heuristic != "ratio") throw TuneError("spx.preproc.heuristic=" + opt.heuristic + " is not supported (ratio only)");
@@ -1240,8 +1243,10 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
     std::vector<Part> parts(np);
     std::vector<ValVec> pools(np);
     std::vector<std::vector<double>> diags(np);
+    if (slab_part >= 0) { row_start = cur.roff; total = sym ? (uint64_t)(cur.n + cur.csr->nrows) / 2 : (uint64_t)cur.n; }
     for (int i = 0; i < np; i++) {
-      size_t limit = (size_t)((total - done) / (uint64_t)(np - i));
+      if (slab_part >= 0 && i != slab_part) continue;
+      size_t limit = slab_part >= 0 ? 0 : (size_t)((total - done) / (uint64_t)(np - i));   // 0: every element of the slab
       // the sym reduction map needs every partition's lower triangle
       bool keep = (i >= part_lo && i < part_hi) || (sym && np > 1);
       parts[i].nr_cols = ncols;
@@ -1254,8 +1259,8 @@ std::string tune_impl(Cursor &cur, int64_t nrows, int64_t ncols, const TuneOptio
       row_start += r.rows;
       done += (uint64_t)r.taken;
     }
-    if (done != total) throw TuneError("error in input matrix (matrix has less elements than claimed)");
-    if (sym) {
+    if (slab_part < 0 && done != total) throw TuneError("error in input matrix (matrix has less elements than claimed)");
+    if (sym && slab_part < 0) {   // (a slab does not see the other partitions: no reduction map, the GPU path needs none)
       std::vector<CsxPartition *> outs(np, nullptr);
       for (int i = part_lo; i < part_hi; i++) outs[i] = &out.parts[i - part_lo];
       build_sym_map(parts, ncols, outs);
@@ -1353,6 +1358,12 @@ std::string TuneOptions::set(const std::string &k, const std::string &v) {
 std::string tune_csr(const CsrView &in, const TuneOptions &opt, int part_lo, int part_hi, CsxMatrix &out) {
   Cursor c; c.csr = &in;
   return tune_impl(c, in.nrows, in.ncols, opt, part_lo, part_hi, out);
+}
+std::string tune_csr_slab(const CsrView &slab, int64_t nrows_total, int64_t row_start, int part, const TuneOptions &opt, CsxMatrix &out) {
+  if (part < 0 || part >= opt.nr_threads) return "invalid partition index";
+  if (row_start < 0 || row_start + slab.nrows > nrows_total) return "slab rows outside the matrix";
+  Cursor c; c.csr = &slab; c.roff = row_start;
+  return tune_impl(c, nrows_total, slab.ncols, opt, part, part + 1, out, part);
 }
 std::string tune_coo(const CooHost &in, const TuneOptions &opt, int part_lo, int part_hi, CsxMatrix &out) {
   Cursor c; c.coo = &in;

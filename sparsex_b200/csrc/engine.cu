@@ -318,12 +318,13 @@ static void put_err(char *err, size_t n, const std::string &m) {
 }
 
 // C++ entry used by api.cpp for inputs already parsed into memory (spx_input_load_mmf)
-csxb_matrix_t *csxb_tune_coo_internal(const CooHost &coo, const char *options, char *err, size_t errlen) {
+csxb_matrix_t *csxb_tune_coo_internal(const CooHost &coo, const char *options, int part_lo, int part_hi, char *err, size_t errlen) {
   TuneOptions o;
   std::string e = parse_options(options, o);
   if (!e.empty()) { put_err(err, errlen, e); return nullptr; }
+  if (part_hi < 0) { part_lo = 0; part_hi = o.nr_threads; }
   csxb_matrix *m = new csxb_matrix;
-  e = tune_coo(coo, o, 0, o.nr_threads, m->host);
+  e = tune_coo(coo, o, part_lo, part_hi, m->host);
   if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
   return m;
 }
@@ -341,6 +342,21 @@ csxb_matrix_t *csxb_tune_csr(const int32_t *rowptr, const int32_t *colind, const
   csxb_matrix *m = new csxb_matrix;
   CsrView v{rowptr, colind, values, nrows, ncols};
   e = tune_csr(v, o, part_lo, part_hi, m->host);
+  if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
+  return m;
+}
+
+csxb_matrix_t *csxb_tune_csr_slab(const int32_t *rowptr, const int32_t *colind, const double *values, int64_t slab_rows,
+                                  int64_t nrows_total, int64_t ncols, int64_t row_start, int part, const char *options, char *err,
+                                  size_t errlen) {
+  TuneOptions o;
+  std::string e = parse_options(options, o);
+  if (e.empty() && (!rowptr || !colind || !values || slab_rows < 0 || ncols < 0)) e = "invalid CSR arguments";
+  if (e.empty() && rowptr[0] != 0) e = "CSR arrays must be zero-based";
+  if (!e.empty()) { put_err(err, errlen, e); return nullptr; }
+  csxb_matrix *m = new csxb_matrix;
+  CsrView v{rowptr, colind, values, slab_rows, ncols};
+  e = tune_csr_slab(v, nrows_total, row_start, part, o, m->host);
   if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
   return m;
 }

@@ -38,6 +38,8 @@ def lib():
     vp, i32, i64, dbl, cp = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_char_p
     L.csxb_tune_csr.restype = vp
     L.csxb_tune_csr.argtypes = [vp, vp, vp, i64, i64, cp, i32, i32, cp, C.c_size_t]
+    L.csxb_tune_csr_slab.restype = vp
+    L.csxb_tune_csr_slab.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, cp, cp, C.c_size_t]
     L.csxb_tune_mmf.restype = vp
     L.csxb_tune_mmf.argtypes = [cp, cp, i32, i32, cp, C.c_size_t]
     L.csxb_destroy.argtypes = [vp]
@@ -126,6 +128,20 @@ class CsxMatrix(object):
         err = C.create_string_buffer(1024)
         h = lib().csxb_tune_csr(rowptr.ctypes.data, colind.ctypes.data, values.ctypes.data, nrows, ncols,
                                 _opts(opts), part_lo, part_hi, err, 1024)
+        if not h:
+            raise EngineError(err.value.decode())
+        return cls(h)
+
+    @classmethod
+    def tune_csr_slab(cls, rowptr, colind, values, nrows_total, ncols, row_start, part, opts=None):
+        """Partition `part` of the spx.rt.nr_threads-way split from its own rows only (csxb_tune_csr_slab):
+        rowptr (relative to the slab), colind, values of rows [row_start, row_start + len(rowptr) - 1)."""
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        colind = np.ascontiguousarray(colind, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        err = C.create_string_buffer(1024)
+        h = lib().csxb_tune_csr_slab(rowptr.ctypes.data, colind.ctypes.data, values.ctypes.data, rowptr.size - 1, nrows_total,
+                                     ncols, row_start, part, _opts(opts), err, 1024)
         if not h:
             raise EngineError(err.value.decode())
         return cls(h)
