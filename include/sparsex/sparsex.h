@@ -6,6 +6,7 @@
 #include <sparsex/common.h>
 #include <sparsex/error.h>
 #include <sparsex/matvec.h>
+#include <sparsex/timing.h>
 #include <sparsex/types.h>
 
 #endif /* SPARSEX_SPARSEX_H */

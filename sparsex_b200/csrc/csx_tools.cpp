@@ -156,15 +156,19 @@ struct Writer {
 };
 struct Reader {
   FILE *f; bool ok = true;
-  void raw(void *p, size_t n) { if (ok && n && fread(p, 1, n, f) != n) ok = false; }
+  int64_t left = 0;   // bytes of the file not read yet: no array can be longer than that
+  void raw(void *p, size_t n) {
+    if (ok && n && ((int64_t)n > left || fread(p, 1, n, f) != n)) ok = false;
+    if (ok) left -= (int64_t)n;
+  }
   int64_t i64() { int64_t v = 0; raw(&v, 8); return v; }
   template <class T> void vec(std::vector<T> &v) {
     int64_t n = i64();
-    if (!ok || n < 0 || n > (int64_t(1) << 40)) { ok = false; return; }
+    if (!ok || n < 0 || n > left / (int64_t)sizeof(T)) { ok = false; return; }
     v.resize((size_t)n);
     raw(v.data(), (size_t)n * sizeof(T));
   }
-  void str(std::string &s) { int64_t n = i64(); if (!ok || n < 0 || n > (1 << 24)) { ok = false; return; } s.resize((size_t)n); raw(&s[0], (size_t)n); }
+  void str(std::string &s) { int64_t n = i64(); if (!ok || n < 0 || n > left || n > (1 << 24)) { ok = false; return; } s.resize((size_t)n); raw(&s[0], (size_t)n); }
 };
 }  // namespace
 
@@ -194,6 +198,7 @@ std::string load_matrix(const char *path, CsxMatrix &m) {
   FILE *f = fopen(path, "rb");
   if (!f) return std::string("cannot open ") + path;
   Reader r{f};
+  if (fseek(f, 0, SEEK_END) == 0) { r.left = (int64_t)ftell(f); rewind(f); }
   char magic[8];
   r.raw(magic, 8);
   if (!r.ok || memcmp(magic, MAGIC, 8) != 0) { fclose(f); return std::string(path) + " is not a CSX container of this engine (or of another version)"; }
@@ -214,9 +219,17 @@ std::string load_matrix(const char *path, CsxMatrix &m) {
     r.vec(p.rows_info); r.vec(p.dvalues); r.vec(p.map_cpus); r.vec(p.map_pos);
     r.str(p.encoding_log);
     if (!r.ok || (int64_t)p.values.size() != p.nnz) { fclose(f); return "corrupt container (partition arrays)"; }
+    if (p.nrows < 0 || p.ncols != m.ncols || p.row_start < 0 || p.row_start + p.nrows > m.nrows || p.id_map.size() > 64 ||
+        (m.symmetric && (int64_t)p.dvalues.size() + p.row_start > m.nrows)) { fclose(f); return "corrupt container (partition header)"; }
   }
   fclose(f);
-  return r.ok ? "" : "truncated container";
+  if (!r.ok) return "truncated container";
+  // the same range checks the options go through at tune time (TuneOptions::set); the ctl stream itself is validated
+  // when the GPU tables are built (build_layout walks it with bounds checks)
+  if (m.nrows < 0 || m.ncols < 0 || (m.rows_per_thread != 0 && m.rows_per_thread != 1 && m.rows_per_thread != 4) || m.slab_rows < 1 ||
+      m.nparts_total < (int)np || m.part_lo < 0 || m.part_lo + (int)np > m.nparts_total)
+    return "corrupt container (options)";
+  return "";
 }
 
 }  // namespace spxb

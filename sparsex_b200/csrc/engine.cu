@@ -48,6 +48,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 // Edge CTA of the edge-tiles-first protocol (XchgDev.mode 1): waits for the neighbours' edge tiles of the previous
 // step, computes and pushes its tile, and the last edge CTA of the step publishes it.  Kept out of line so that
 // the interior path of the kernel keeps the register allocation of the plain kernel.
+// x is read with L1-bypassing loads here: the neighbours write the halo rows of this vector while the kernel runs.
 template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool BT>
 __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, double *y, double alpha, long long tile,
                                            long long row_block, const XchgDev &X, int ypar) {
@@ -64,7 +65,7 @@ __device__ __noinline__ void spmv_edge_cta(const PartDev &P, const double *x, do
   }
   __syncthreads();
   // spmv_tile pushes into push_vec[p][(k & 1) ^ 1]: hand it a step number with the parity of the target buffer
-  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev, BT>(P, x, y, alpha, 0.0, 1, tile, row_block, X, (unsigned long long)(ypar ^ 1));
+  spmv_tile<XD, SYM, RPT, KSET, VAR, true, XchgDev, BT, true>(P, x, y, alpha, 0.0, 1, tile, row_block, X, (unsigned long long)(ypar ^ 1));
   // Every edge CTA orders its stores before its count at device scope; the last one then issues the single
   // system-scope fence (cumulative over everything that happened before it) and the release stores of the flags.
   __threadfence();
@@ -739,8 +740,17 @@ static int run_partition(const PartDev &P, const PartLayout &pl, const SkIO &io,
 
 extern "C" {
 
+// kernels of a matrix run on the device it was uploaded to, whatever the caller's current device is
+static int on_matrix_device(const csxb_matrix *m) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return fail("cudaGetDevice failed");
+  if (cur != m->device && cudaSetDevice(m->device) != cudaSuccess) return fail("cudaSetDevice failed");
+  return 0;
+}
+
 int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, double *d_y, int overwrite, void *stream) {
   if (!m->uploaded) return fail("matrix not uploaded (csxb_upload)");
+  if (on_matrix_device(m)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   const bool sym = m->host.symmetric;
   SkIO io;
@@ -833,9 +843,11 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
     CUDA_TRY(cudaStreamSynchronize(m->s_run));
     CUDA_TRY(cudaStreamSynchronize(m->s_d2h));
     // rows after the last partition's last non-empty row belong to nobody: zero under spx_matvec_mult
-    // semantics (CsxKernels.cpp:93), beta*y under spx_matvec_kernel semantics
-    if (last_local && m->covered_rows_end < m->host.nrows)
-      for (int64_t r = m->covered_rows_end; r < m->host.nrows; r++) h_y[r] = overwrite ? 0.0 : beta * h_y[r];
+    // semantics (CsxKernels.cpp:93)
+    // (spx_matvec_kernel semantics leave them as they are: do_kernel_thread only scales the rows of its partition,
+    // CsxSpmv.cpp:52-64 — the same as csxb_spmv on device vectors)
+    if (overwrite && last_local && m->covered_rows_end < m->host.nrows)
+      for (int64_t r = m->covered_rows_end; r < m->host.nrows; r++) h_y[r] = 0.0;
   }
   if (cur != m->device && cur >= 0) CUDA_TRY(cudaSetDevice(cur));
   return 0;
@@ -986,6 +998,7 @@ double *csxb_xchg_vector(csxb_xchg_t *h, int which) { return h->dev.vec[which & 
 int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
   if (!h->connected) return fail("exchange not connected (csxb_xchg_connect)");
   csxb_matrix *m = h->m;
+  if (on_matrix_device(m)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   static const int dbg = getenv("CSXB_XCHG_DEBUG") ? atoi(getenv("CSXB_XCHG_DEBUG")) : 0;   // tuning aid
   XchgDev X = h->dev;
@@ -1066,12 +1079,17 @@ int csxb_vec_dot(const double *d_a, const double *d_b, int64_t n, double *result
   *result = 0.0;
   if (n <= 0) return 0;
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4);
-  static thread_local double *d_partial = nullptr;
-  static thread_local double *h_partial = nullptr;
-  if (!d_partial) {
-    CUDA_TRY(cudaMalloc((void **)&d_partial, 148 * 4 * sizeof(double)));
-    CUDA_TRY(cudaMallocHost((void **)&h_partial, 148 * 4 * sizeof(double)));
+  // scratch per device (the vectors decide where the kernel runs: the caller's current device)
+  static thread_local double *d_part[64] = {nullptr};
+  static thread_local double *h_part[64] = {nullptr};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail("device index out of range");
+  if (!d_part[dev]) {
+    CUDA_TRY(cudaMalloc((void **)&d_part[dev], 148 * 4 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost((void **)&h_part[dev], 148 * 4 * sizeof(double)));
   }
+  double *d_partial = d_part[dev], *h_partial = h_part[dev];
   cudaStream_t s = (cudaStream_t)stream;
   csx_vec_dot_kernel<<<grid, 256, 0, s>>>(d_a, d_b, (long long)n, d_partial);
   CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, grid * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1101,7 +1119,8 @@ int csxb_save(csxb_matrix_t *m, const char *path) {
 csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen) {
   if (!path) { put_err(err, errlen, "invalid file name"); return nullptr; }
   csxb_matrix *m = new csxb_matrix;
-  std::string e = load_matrix(path, m->host);
+  std::string e;
+  try { e = load_matrix(path, m->host); } catch (std::exception &ex) { e = std::string("cannot load the container: ") + ex.what(); }
   if (!e.empty()) { put_err(err, errlen, e); delete m; return nullptr; }
   return m;
 }

@@ -89,17 +89,28 @@ __device__ __forceinline__ bool linear_probe(const uint4 d, const KindEntry *__r
   return true;
 }
 
+// x loads.  COH: the vector is being written by other GPUs while this kernel runs (edge CTAs of the edge-tiles-first
+// exchange): ld.global.nc promises read-only data for the whole kernel and goes through L1, where a line fetched by an
+// interior CTA of the same SM before the neighbour's halo rows landed would be stale — such loads bypass L1 (ld.global.cg).
+template <bool COH>
+__device__ __forceinline__ double ldx(const double *p) {
+#ifndef CSXB_EMUL
+  if (COH) return __ldcg(p);
+#endif
+  return __ldg(p);
+}
+template <bool COH>
 struct SpmvGatherOp {
   const double *__restrict__ values;  // device-wide
-  const double *__restrict__ x;
+  const double *x;
   double acc;
-  __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * __ldg(x + xi); }
+  __device__ __forceinline__ void add(uint32_t vi, int xi) { acc += __ldg(values + vi) * ldx<COH>(x + xi); }
 };
 
 // Entries [e0, e1) of one group of a block table for the row whose values start at `vals` inside every sub-block:
 // sum over entries of sum over l < nloop of vals[voff + l * sl] * x[other + l].  NL = nloop at compile time (0: any);
 // two entries at a time, all their loads issued before the first FMA.
-template <int NL>
+template <int NL, bool COH>
 __device__ __forceinline__ double bt_row(const BtDev &T, const double *__restrict__ vals, const double *__restrict__ x, uint32_t e0,
                                          uint32_t e1) {
   constexpr int N = NL > 0 ? NL : 1;
@@ -112,7 +123,7 @@ __device__ __forceinline__ double bt_row(const BtDev &T, const double *__restric
       const double *v0 = vals + b0.x, *v1 = vals + b1.x, *x0 = x + (b0.y & ~BT_IMAGE), *x1 = x + (b1.y & ~BT_IMAGE);
       double va[N], xa[N], vb[N], xb[N];
 #pragma unroll
-      for (int l = 0; l < N; l++) { va[l] = __ldg(v0 + l * sl); xa[l] = __ldg(x0 + l); vb[l] = __ldg(v1 + l * sl); xb[l] = __ldg(x1 + l); }
+      for (int l = 0; l < N; l++) { va[l] = __ldg(v0 + l * sl); xa[l] = ldx<COH>(x0 + l); vb[l] = __ldg(v1 + l * sl); xb[l] = ldx<COH>(x1 + l); }
 #pragma unroll
       for (int l = 0; l < N; l++) { a0 += va[l] * xa[l]; a1 += vb[l] * xb[l]; }
     }
@@ -123,11 +134,11 @@ __device__ __forceinline__ double bt_row(const BtDev &T, const double *__restric
     if (NL > 0) {
       double va[N], xa[N];
 #pragma unroll
-      for (int l = 0; l < N; l++) { va[l] = __ldg(vp + l * sl); xa[l] = __ldg(xp + l); }
+      for (int l = 0; l < N; l++) { va[l] = __ldg(vp + l * sl); xa[l] = ldx<COH>(xp + l); }
 #pragma unroll
       for (int l = 0; l < N; l++) a0 += va[l] * xa[l];
     } else {
-      for (int l = 0; l < T.nloop; l++) a0 += __ldg(vp + l * sl) * __ldg(xp + l);
+      for (int l = 0; l < T.nloop; l++) a0 += __ldg(vp + l * sl) * ldx<COH>(xp + l);
     }
   }
   return a0 + a1;
@@ -181,7 +192,7 @@ enum { KSET_ANY = 0, KSET_DIAG1 = 1 };
 // The work of one warp of one CTA: rows [row_block * CTA_THREADS * RPT, +CTA_THREADS * RPT) with the descriptor list of
 // layout tile `tile` (the same number, unless an edge CTA of the exchange walks a quarter of a 4-rows-per-thread tile
 // with one row per thread).  PUSH: rows that other ranks read are also stored into their vectors (exchange).
-template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool PUSH, class XP, bool BT = false>
+template <bool XD, bool SYM, int RPT, int KSET, int VAR, bool PUSH, class XP, bool BT = false, bool COH = false>
 __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__restrict__ x, double *__restrict__ y, double alpha,
                                           double beta, int overwrite, const long long tile, const long long row_block, const XP &X,
                                           const unsigned long long xk) {
@@ -242,7 +253,7 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
 #pragma unroll
           for (int k = 0; k < RPT; k++) {
             v[k] = 0.0; xv[k] = 0.0;
-            if ((uint32_t)(t0 + k * 32) < size) { v[k] = __ldg(vp + k * 32); xv[k] = __ldg(xp + k * 32); }
+            if ((uint32_t)(t0 + k * 32) < size) { v[k] = __ldg(vp + k * 32); xv[k] = ldx<COH>(xp + k * 32); }
           }
 #pragma unroll
           for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
@@ -256,14 +267,14 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
           for (int k = 0; k < RPT; k++) {
             uint32_t vi; int xi;
             v[k] = 0.0; xv[k] = 0.0;
-            if (linear_probe<SYM>(d, P.ktab, grow0 + k * 32 + lane, vi, xi)) { v[k] = __ldg(values + vi); xv[k] = __ldg(x + xi); }
+            if (linear_probe<SYM>(d, P.ktab, grow0 + k * 32 + lane, vi, xi)) { v[k] = __ldg(values + vi); xv[k] = ldx<COH>(x + xi); }
           }
 #pragma unroll
           for (int k = 0; k < RPT; k++) acc[k] += v[k] * xv[k];
         } else {
 #pragma unroll
           for (int k = 0; k < RPT; k++) {
-            SpmvGatherOp op{values, x, 0.0};
+            SpmvGatherOp<COH> op{values, x, 0.0};
             gather_desc<SYM>(d, P.ktab, grow0 + k * 32 + lane, op);
             acc[k] += op.acc;
           }
@@ -287,11 +298,11 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
         const uint32_t *pp = T.ptr + ((long long)J - T.j0);
         const uint32_t e0 = __ldg(pp), e1 = __ldg(pp + 1);
         switch (T.nloop) {
-          case 1: acc[k] += bt_row<1>(T, P.values + f, x, e0, e1); break;
-          case 2: acc[k] += bt_row<2>(T, P.values + f, x, e0, e1); break;
-          case 3: acc[k] += bt_row<3>(T, P.values + f, x, e0, e1); break;
-          case 4: acc[k] += bt_row<4>(T, P.values + f, x, e0, e1); break;
-          default: acc[k] += bt_row<0>(T, P.values + f, x, e0, e1);
+          case 1: acc[k] += bt_row<1, COH>(T, P.values + f, x, e0, e1); break;
+          case 2: acc[k] += bt_row<2, COH>(T, P.values + f, x, e0, e1); break;
+          case 3: acc[k] += bt_row<3, COH>(T, P.values + f, x, e0, e1); break;
+          case 4: acc[k] += bt_row<4, COH>(T, P.values + f, x, e0, e1); break;
+          default: acc[k] += bt_row<0, COH>(T, P.values + f, x, e0, e1);
         }
       }
     }
@@ -303,7 +314,7 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
     if (lrow < P.nrows) {
       const long long g = P.row_start + lrow;
       double a = acc[k];
-      if (SYM && P.dvalues) a += __ldg(P.dvalues + lrow) * __ldg(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
+      if (SYM && P.dvalues) a += __ldg(P.dvalues + lrow) * ldx<COH>(x + g);   // diagonal (CsxJit.hpp:373-394 new-row hook)
       const double r = overwrite ? alpha * a : alpha * a + beta * y[g];
       y[g] = r;
       if constexpr (PUSH) {   // the exchange: rows another rank's partition reads go straight into its next x.

@@ -252,6 +252,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
   {
     std::map<uint32_t, int64_t> bc_elems, br_elems;          // align -> elements
     std::map<uint32_t, int64_t> bc_gcd, br_gcd;              // align -> gcd of the free dimension (and of the start rows)
+    std::map<uint32_t, int64_t> br_img_gcd;                  // align -> gcd of the column counts and the start columns
     std::map<uint32_t, bool> bc_colok, br_rowok;
     auto gcd64 = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
     for (size_t pi = 0; pi < np; pi++) {
@@ -286,6 +287,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         } else if (kind == K_BROW) {
           br_elems[align] += size;
           br_gcd[align] = gcd64(br_gcd[align], delta);
+          br_img_gcd[align] = gcd64(gcd64(br_img_gcd[align], delta), col);
           if (!br_rowok.count(align)) br_rowok[align] = true;
           if ((cp.row_start + row) % align) br_rowok[align] = false;
         }
@@ -307,8 +309,10 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     for (auto &kv : br_elems)
       if (kv.second > best && br_rowok[kv.first] && br_gcd[kv.first] * kv.first >= 4) {
         best = kv.second; out.br_align = (int)kv.first; out.br_cols = (int)br_gcd[kv.first];
+        out.br_img_cols = (int)std::min<int64_t>(br_img_gcd[kv.first], out.br_cols);
+        if (out.br_cols % std::max(out.br_img_cols, 1)) out.br_img_cols = 1;
       }
-    if (getenv("CSXB_NO_BLOCK_TABLES")) out.bc_align = out.bc_rows = out.br_align = out.br_cols = 0;   // tuning aid
+    if (getenv("CSXB_NO_BLOCK_TABLES")) out.bc_align = out.bc_rows = out.br_align = out.br_cols = out.br_img_cols = 0;   // tuning aid
   }
   // entries of the block tables (table numbers: gpu_layout.hpp)
   struct BtEnt { int64_t q; int tab; int64_t grp; BlockImage b; };
@@ -542,12 +546,16 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
           const int64_t A = out.br_align, C0 = out.br_cols;
           for (int64_t k = 0; k * C0 < (int64_t)delta; k++)
             btents.push_back(BtEnt{(int64_t)pi, 2, grow / A, BlockImage{d.voff + (uint32_t)(k * C0 * A), (uint32_t)(start_col + k * C0)}});
-          if (m.symmetric)   // image of a block-row unit: one entry per column (its columns are not aligned)
-            for (int64_t j = 0; j < (int64_t)delta; j++) {
-              const int64_t q = owner_of(start_col + j);
-              if (q < 0) return "symmetric update targets a row that is not on this device";
-              btents.push_back(BtEnt{q, 3, start_col + j, BlockImage{d.voff + (uint32_t)(j * A), (uint32_t)grow | BT_IMAGE}});
-            }
+          if (m.symmetric) {   // image of a block-row unit: one entry per aligned group of its columns (or per column)
+            const int64_t G = std::max(out.br_img_cols, 1);
+            for (int64_t j = 0; j < (int64_t)delta; j += G)
+              for (int64_t g = start_col + j; g < start_col + j + G;) {   // a group can be cut by a partition boundary
+                const int64_t q = owner_of(g);
+                if (q < 0) return "symmetric update targets a row that is not on this device";
+                btents.push_back(BtEnt{q, 3, g / G, BlockImage{d.voff + (uint32_t)(j * A), (uint32_t)grow | BT_IMAGE}});
+                g = std::min(start_col + j + G, q_start((size_t)q) + q_rows((size_t)q));
+              }
+          }
         }
       } else {
         for (int64_t t = row / TILE_ROWS; t <= (row + span) / TILE_ROWS; t++) pend.push_back(Pending{(int64_t)pi, t, d});
@@ -619,7 +627,7 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         if (t == 0) { T.G = out.bc_rows; T.nloop = out.bc_align; T.sf = out.bc_align; T.sl = 1; }
         else if (t == 1) { T.G = out.bc_align; T.nloop = out.bc_rows; T.sf = 1; T.sl = out.bc_align; T.image = 1; }
         else if (t == 2) { T.G = out.br_align; T.nloop = out.br_cols; T.sf = 1; T.sl = out.br_align; }
-        else if (t == 3) { T.G = out.br_align ? 1 : 0; T.nloop = out.br_align; T.sf = 0; T.sl = 1; T.image = 1; }
+        else if (t == 3) { T.G = out.br_align ? std::max(out.br_img_cols, 1) : 0; T.nloop = out.br_align; T.sf = out.br_align; T.sl = 1; T.image = 1; }
         else { T.G = 1; T.nloop = 1; T.sf = 0; T.sl = 0; }
         if (T.G <= 0) { T.G = 1; continue; }
         T.j0 = L.row_start / T.G;

@@ -112,7 +112,8 @@ SPXB_HD inline uint32_t sk_unit_tasks(uint32_t kind, uint32_t size, uint32_t del
 //   0 block-column unit, own rows (rows x A, row-major):     G = sub-block rows, nloop = A, sf = A, sl = 1, other = first column
 //   1 block-column unit, CSX-Sym image (y[col] += v*x[row]): G = A, nloop = sub-block rows, sf = 1, sl = A, other = first row
 //   2 block-row unit, own rows (A x cols, column-major):     G = A, nloop = sub-block columns, sf = 1, sl = A, other = first column
-//   3 block-row unit, CSX-Sym image, one entry per column:   G = 1, nloop = A, sf = 0, sl = 1, other = first row
+//   3 block-row unit, CSX-Sym image, one entry per aligned group of g columns (g = 1 if the columns are not aligned):
+//                                                           G = g, nloop = A, sf = A, sl = 1, other = first row
 //   4 single elements (own row: other = column; CSX-Sym image: other = row): G = 1, nloop = 1
 // Table 4 takes the elements of the delta / horizontal / unaligned block units of a partition in which such units are
 // a minority (at most 40 % of the non-zeros): the partition then needs no stream kernel at all.
@@ -173,6 +174,7 @@ struct DeviceLayout {
   // block units that live in the block tables: block-column units of width bc_align cut into sub-blocks of bc_rows rows
   // (0: none), block-row units of height br_align cut into sub-blocks of br_cols columns (0: none)
   int bc_align = 0, bc_rows = 0, br_align = 0, br_cols = 0;
+  int br_img_cols = 0;   // CSX-Sym images of block-row units: aligned groups of this many columns per entry (1: per column)
   // CSX-Sym with only some partitions on this device: rows [halo_lo, halo_hi) of lower ranks that local units
   // update; parts.back() is their pseudo-partition (is_halo)
   int64_t halo_lo = 0, halo_hi = 0;

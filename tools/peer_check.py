@@ -15,7 +15,13 @@ from sparsex_b200.dist import connect_peer_exchange  # noqa: E402
 from tests.matrices import poisson2d, rmat, stencil27  # noqa: E402
 
 CASES = {"poisson": (lambda: poisson2d(300), {}), "rmat": (lambda: rmat(14), {"spx.preproc.xform": "none"}),
-         "stencil": (lambda: stencil27(40), {})}
+         "stencil": (lambda: stencil27(40), {}),
+         # tiles of 4 rows per thread (what partitions of 2^20 rows and more run): edge tiles split over four CTAs
+         "poisson4": (lambda: poisson2d(300), {"spx.b200.rows_per_thread": 4}),
+         "stencil4": (lambda: stencil27(40), {"spx.b200.rows_per_thread": 4}),
+         # block units in the block tables of the gather kernel; delta units in the stream kernel
+         "blocks": (lambda: stencil27(40), {"spx.preproc.xform": "br,bc"}),
+         "blocks4": (lambda: stencil27(40), {"spx.preproc.xform": "br,bc", "spx.b200.rows_per_thread": 4})}
 
 
 def main():
