@@ -641,8 +641,9 @@ static void launch_gather_k(const PartDev &P, const PartLayout &pl, unsigned nt,
   }
   // descriptors can also come from other partitions (transposed images under CSX-Sym, whose many kinds need registers)
   constexpr int MB = SYM ? 4 : 8;
-  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET, MB, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
-  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, MB, 0, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+  const size_t dyn = 0;
+  if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET, MB, 0, XP><<<grid, block, dyn, s>>>(P, x, y, alpha, beta, overwrite, X);
+  else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, MB, 0, XP><<<grid, block, dyn, s>>>(P, x, y, alpha, beta, overwrite, X);
 }
 template <bool SYM, class XP>
 static void launch_gather(const PartDev &P0, const PartLayout &pl, int64_t t0, int64_t t1, const double *x, double *y,
@@ -682,14 +683,15 @@ static void launch_gather_xe(const PartDev &P0, const PartLayout &pl, const doub
     }
     return;
   }
+  const size_t dyn = 0;
   if (pl.rpt == 4) {
-    if (diag1) csx_spmv_xe_kernel<true, 4, KSET_DIAG1, 8, 1><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
-    else if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
-    else csx_spmv_xe_kernel<false, 4, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    if (diag1) csx_spmv_xe_kernel<true, 4, KSET_DIAG1, 8, 1><<<grid, block, dyn, s>>>(P, x, y, alpha, ypar, X);
+    else if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY><<<grid, block, dyn, s>>>(P, x, y, alpha, ypar, X);
+    else csx_spmv_xe_kernel<false, 4, KSET_ANY><<<grid, block, dyn, s>>>(P, x, y, alpha, ypar, X);
   } else {
-    if (diag1) csx_spmv_xe_kernel<true, 1, KSET_DIAG1><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
-    else if (xd) csx_spmv_xe_kernel<true, 1, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
-    else csx_spmv_xe_kernel<false, 1, KSET_ANY><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+    if (diag1) csx_spmv_xe_kernel<true, 1, KSET_DIAG1><<<grid, block, dyn, s>>>(P, x, y, alpha, ypar, X);
+    else if (xd) csx_spmv_xe_kernel<true, 1, KSET_ANY><<<grid, block, dyn, s>>>(P, x, y, alpha, ypar, X);
+    else csx_spmv_xe_kernel<false, 1, KSET_ANY><<<grid, block, dyn, s>>>(P, x, y, alpha, ypar, X);
   }
 }
 // Launches the stream kernel over chunks [c0, c1) of one partition: the instantiation is chosen by the partition's

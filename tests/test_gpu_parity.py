@@ -288,9 +288,18 @@ def test_pipelined_host_buffer_path(slab_rows):
             y = y0.copy()
             A.spmv_host(0.5, x, y)
             assert np.max(np.abs(y - 0.5 * ref) / (0.5 * bound)) <= TOL
+            # spx_matvec_kernel semantics: rows behind the last non-empty row belong to no partition and stay as they are
+            # (do_kernel_thread scales the rows of its partition only, CsxSpmv.cpp:52-64) — on every path
+            owned = int(np.nonzero(np.diff(rp))[0].max()) + 1
+            want = 0.75 * ref - 0.3 * y0
+            want[owned:] = y0[owned:]
             y = y0.copy()
             A.spmv_host(0.75, x, y, beta=-0.3, overwrite=False)
-            assert np.max(np.abs(y - (0.75 * ref - 0.3 * y0)) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300)) <= TOL
+            assert np.max(np.abs(y - want) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300)) <= TOL
+            import torch
+            dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y0.copy()).cuda()
+            A.spmv(0.75, dx, dy, beta=-0.3, overwrite=False)
+            assert np.max(np.abs(dy.cpu().numpy() - want) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300)) <= TOL
             A.close()
 
 
