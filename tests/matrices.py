@@ -319,10 +319,11 @@ def rmat_block_row_counts(scale, edge_factor=16, abcd=(0.57, 0.19, 0.19, 0.05), 
     import torch
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")
     n = 1 << scale
+    bsz = n >> _rmat_k(scale)
     counts = torch.zeros(n, dtype=torch.int64, device=device)
     for blk in range(1 << _rmat_k(scale)):
         key = _rmat_block(scale, blk, edge_factor, abcd, seed, device)
-        counts += torch.bincount(key // n, minlength=n)
+        counts[blk * bsz:(blk + 1) * bsz] = torch.bincount(key // n - blk * bsz, minlength=bsz)
     return counts.cpu().numpy()
 
 
