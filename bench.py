@@ -490,15 +490,17 @@ def main():
     sampler.start()
     region_ms = [timed_region() for _ in range(max(args.outer, 1))]
     # the timed region can be a few milliseconds: keep the same load running, untimed, until the clock sampler has
-    # seen it for at least 100 ms
-    t_probe = time.perf_counter()
-    while time.perf_counter() - t_probe < 0.1:
-        if graph is not None:
+    # seen it for at least 100 ms.  The number of extra steps is the same on every rank (a rank that issued more steps than
+    # its neighbours would wait for them forever).
+    ms_med = float(np.median(region_ms))
+    extra = int(np.ceil(100.0 / max(ms_med / args.steps, 1e-3)))
+    if graph is not None:
+        for _ in range((extra + G - 1) // G):
             graph.replay()
-        else:
-            for _ in range(4):
-                step()
-        torch.cuda.synchronize()
+    else:
+        for _ in range(extra):
+            step()
+    torch.cuda.synchronize()
     barrier()
     clocks = sampler.finish()
     ms = float(np.median(region_ms))

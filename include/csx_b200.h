@@ -85,6 +85,10 @@ const char *csxb_part_log(const csxb_matrix_t *m, int part);
  * Returns 0 or a negative error (message via csxb_last_error). */
 int csxb_upload(csxb_matrix_t *m, int device, int free_host);
 const char *csxb_last_error(void);
+/* Builds the GPU tables on the host only (no device needed) and reports their sizes, 12 numbers per row owner
+ * (local partitions, then the CSX-Sym halo pseudo-partition): rows, tiles, table descriptors, stream chunks, stream
+ * units, fix-up entries, gaps, entries of block tables 0..4.  Returns the number of row owners, -1 on error. */
+int csxb_layout_stats(csxb_matrix_t *m, int64_t *out, int max_owners);
 
 /* Device footprint and algorithmic traffic of one SpMV over the local
  * partitions, in bytes: */

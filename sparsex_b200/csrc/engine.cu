@@ -115,15 +115,33 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_xe_kernel(const __
   }
 }
 
-// Exchange for partitions whose rows are only final after the chunk kernel: copies the rows the peers read.
+// Exchange for partitions whose rows are only final after the last kernel of the step (stream units): copies the rows
+// the peers read into their vectors.  Every element is loaded once (16 bytes per thread where aligned) and stored to
+// every peer that reads it.
 __global__ void __launch_bounds__(256) csx_xchg_push_kernel(const __grid_constant__ XchgDev X) {
   const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(X.step);
-  const double *src = X.vec[(k & 1) ^ 1];
-  for (int p = 0; p < X.npush; p++) {
-    double *dst = X.push_vec[p][(k & 1) ^ 1];
-    for (long long g = X.push_lo[p] + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < X.push_hi[p];
-         g += (long long)gridDim.x * blockDim.x)
-      dst[g] = src[g];
+  const int par = (int)((k & 1) ^ 1);
+  const double *src = X.vec[par];
+  long long lo = LLONG_MAX, hi = 0;
+  for (int p = 0; p < X.npush; p++) { lo = min(lo, X.push_lo[p]); hi = max(hi, X.push_hi[p]); }
+  lo &= ~1ll;   // pairs of rows: the vectors are 16-byte aligned
+  const long long stride = 2ll * gridDim.x * blockDim.x;
+  for (long long g = lo + 2ll * ((long long)blockIdx.x * blockDim.x + threadIdx.x); g < hi; g += stride) {
+    if (g + 1 < hi && g >= lo) {
+      const double2 v = *reinterpret_cast<const double2 *>(src + g);
+      for (int p = 0; p < X.npush; p++) {
+        double *dst = X.push_vec[p][par];
+        if (g >= X.push_lo[p] && g + 1 < X.push_hi[p]) *reinterpret_cast<double2 *>(dst + g) = v;
+        else {
+          if (g >= X.push_lo[p] && g < X.push_hi[p]) dst[g] = v.x;
+          if (g + 1 >= X.push_lo[p] && g + 1 < X.push_hi[p]) dst[g + 1] = v.y;
+        }
+      }
+    } else {
+      for (long long q = g; q < g + 2 && q < hi; q++)
+        for (int p = 0; p < X.npush; p++)
+          if (q >= X.push_lo[p] && q < X.push_hi[p]) X.push_vec[p][par][q] = src[q];
+    }
   }
 }
 // Rows past the last partition's rows belong to nobody: zero in every step's result (VecInit(y, 0), CsxKernels.cpp:93).
@@ -442,6 +460,31 @@ const char *csxb_part_log(const csxb_matrix_t *m, int part) {
 }
 
 const char *csxb_last_error(void) { return g_last_error.c_str(); }
+
+// Builds the GPU tables on the host only (no device needed) and reports their sizes: per row owner (local partitions,
+// then the CSX-Sym halo pseudo-partition) 12 numbers — rows, tiles, table descriptors, stream chunks, stream units,
+// fix-up entries, gaps, entries of block tables 0..4.  Returns the number of row owners, -1 on error (tuning aid, tests).
+int csxb_layout_stats(csxb_matrix_t *m, int64_t *out, int max_owners) {
+  CsxMatrix &H = m->host;
+  std::vector<int64_t> saved;
+  for (auto &p : H.parts) { saved.push_back(p.nrows); if (H.symmetric) p.nrows = (int64_t)p.dvalues.size(); }
+  DeviceLayout L;
+  std::string e = build_layout(H, L);
+  for (size_t i = 0; i < H.parts.size(); i++) H.parts[i].nrows = saved[i];
+  if (!e.empty()) return fail("layout: " + e);
+  for (size_t q = 0; q < L.parts.size() && (int)q < max_owners; q++) {
+    const PartLayout &pl = L.parts[q];
+    int64_t *o = out + 12 * q;
+    o[0] = pl.nrows; o[1] = pl.ntiles; o[2] = (int64_t)pl.xdesc.size(); o[3] = (int64_t)pl.sk_chunks.size();
+    o[4] = (int64_t)pl.sk_uoffs.size(); o[5] = (int64_t)pl.sk_fix_idx.size(); o[6] = (int64_t)pl.sk_gaps.size();
+    for (int t = 0; t < 5; t++) o[7 + t] = 0;
+    for (const BlockTable &T : pl.bt) {
+      int t = T.G == 1 && T.nloop == 1 ? 4 : (T.image ? (T.sl == 1 ? 3 : 1) : (T.sl == 1 ? 0 : 2));
+      o[7 + t] += (int64_t)T.ent.size();
+    }
+  }
+  return (int)L.parts.size();
+}
 
 }  // extern "C"
 
@@ -1012,7 +1055,7 @@ int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
     if (X.mode == 1) launch_gather_xe(m->pdev[i], pl, X.vec[h->parity], X.vec[h->parity ^ 1], alpha, h->parity ^ 1, s, X);
     else if (run_partition<false>(m->pdev[i], pl, io, alpha, 0.0, 1, s, X)) return fail("no stream kernel for the partition's pattern set");
   }
-  if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 4, 256, 0, s>>>(h->dev);
+  if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 8, 256, 0, s>>>(h->dev);
   if (h->tail_hi > h->tail_lo)
     csx_xchg_zero_tail_kernel<<<(unsigned)std::min<int64_t>(148, (h->tail_hi - h->tail_lo + 255) / 256), 256, 0, s>>>(h->dev, h->tail_lo, h->tail_hi, h->dev.mode == 1 ? (h->parity ^ 1) : -1);
   if (!(dbg & 1) && h->dev.mode == 0) csx_xchg_sync_kernel<<<1, 32, 0, s>>>(h->dev, dbg);

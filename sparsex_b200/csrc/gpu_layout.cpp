@@ -247,14 +247,18 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
     return true;
   };
   // ---- which block units go to the block tables (gpu_layout.hpp: BlockTable) -------------------------------------
-  // One pass over the unit heads: per block kind the dominant width / height, and the largest sub-block size that
-  // divides every unit of that kind and (block-column units) every start row.
+  // One pass over the unit heads: per block kind and width / height, the sub-block size (2..16 lines) that covers the
+  // most elements — a unit is covered when the sub-block divides its free dimension and (block-column units) its start
+  // row.  Units of the chosen kind that are not covered (a block cut by a partition boundary) go to the table of single
+  // elements.
   {
-    std::map<uint32_t, int64_t> bc_elems, br_elems;          // align -> elements
-    std::map<uint32_t, int64_t> bc_gcd, br_gcd;              // align -> gcd of the free dimension (and of the start rows)
-    std::map<uint32_t, int64_t> br_img_gcd;                  // align -> gcd of the column counts and the start columns
-    std::map<uint32_t, bool> bc_colok, br_rowok;
-    auto gcd64 = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
+    constexpr int CAND = 17;
+    std::map<uint32_t, std::vector<int64_t>> bc_cov, br_cov, bri_cov;   // align -> elements covered by sub-block size r
+    auto cov = [&](std::map<uint32_t, std::vector<int64_t>> &mp, uint32_t a) -> std::vector<int64_t> & {
+      std::vector<int64_t> &v = mp[a];
+      if (v.empty()) v.assign(CAND, 0);
+      return v;
+    };
     for (size_t pi = 0; pi < np; pi++) {
       const CsxPartition &cp = m.parts[pi];
       KindEntry tab[64];
@@ -276,42 +280,39 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         const uint32_t id = flags & 0x3f;
         if (id >= nid || size == 0) return "ctl stream uses an unmapped unit id";
         const uint32_t kind = tab[id].kind_align & 0xff, align = (tab[id].kind_align >> 8) & 0xff, delta = tab[id].delta;
+        const int64_t grow = cp.row_start + row;
         if (kind <= K_DELTA64) {
           for (int k = 1; k < size; k++) { uint64_t d = 0; memcpy(&d, ctl + p, delta); p += delta; col += (int64_t)d; }
         } else if (kind == K_HORIZ) col += (int64_t)(size - 1) * delta;
         else if (kind == K_BCOL) {
-          bc_elems[align] += size;
-          bc_gcd[align] = gcd64(gcd64(bc_gcd[align], delta), cp.row_start + row);
-          if (!bc_colok.count(align)) bc_colok[align] = true;
-          if (col % align) bc_colok[align] = false;
+          std::vector<int64_t> &v = cov(bc_cov, align);
+          if (!m.symmetric || col % align == 0)
+            for (int r = 2; r < CAND; r++) if (delta % r == 0 && grow % r == 0) v[r] += size;
         } else if (kind == K_BROW) {
-          br_elems[align] += size;
-          br_gcd[align] = gcd64(br_gcd[align], delta);
-          br_img_gcd[align] = gcd64(gcd64(br_img_gcd[align], delta), col);
-          if (!br_rowok.count(align)) br_rowok[align] = true;
-          if ((cp.row_start + row) % align) br_rowok[align] = false;
+          if (grow % align == 0) {
+            std::vector<int64_t> &v = cov(br_cov, align), &vi = cov(bri_cov, align);
+            for (int r = 1; r < CAND; r++) {
+              if (delta % r == 0) v[r] += size;
+              if (delta % r == 0 && col % r == 0) vi[r] += size;
+            }
+          }
         }
       }
     }
-    int64_t best = 0;
-    for (auto &kv : bc_elems)
-      if (kv.second > best && bc_gcd[kv.first] >= 2 && bc_gcd[kv.first] * kv.first >= 4 && (!m.symmetric || bc_colok[kv.first])) {
-        best = kv.second; out.bc_align = (int)kv.first; out.bc_rows = (int)std::min<int64_t>(bc_gcd[kv.first], 127);
-      }
-    if (out.bc_align && bc_gcd[out.bc_align] > 127) {   // keep the sub-block a divisor
-      int64_t g = bc_gcd[out.bc_align];
-      int r = 127;
-      while (g % r) r--;
-      out.bc_rows = r;
-      if (r < 2) out.bc_align = out.bc_rows = 0;
+    auto pick = [&](std::map<uint32_t, std::vector<int64_t>> &mp, int rmin, int &A, int &R0) {
+      int64_t best = 0;
+      for (auto &kv : mp)
+        for (int r = CAND - 1; r >= rmin; r--)   // the largest sub-block among (nearly) equal coverages
+          if ((int64_t)r * kv.first >= 4 && kv.second[r] > best + best / 64) { best = kv.second[r]; A = (int)kv.first; R0 = r; }
+    };
+    pick(bc_cov, 2, out.bc_align, out.bc_rows);
+    pick(br_cov, 1, out.br_align, out.br_cols);
+    if (out.br_align) {   // CSX-Sym images of the block-row units: aligned groups of columns that divide the sub-block
+      const std::vector<int64_t> &vi = bri_cov[(uint32_t)out.br_align];
+      out.br_img_cols = 1;
+      for (int r = CAND - 1; r >= 2; r--)
+        if (out.br_cols % r == 0 && vi[r] >= br_cov[(uint32_t)out.br_align][out.br_cols] - br_cov[(uint32_t)out.br_align][out.br_cols] / 64) { out.br_img_cols = r; break; }
     }
-    best = 0;
-    for (auto &kv : br_elems)
-      if (kv.second > best && br_rowok[kv.first] && br_gcd[kv.first] * kv.first >= 4) {
-        best = kv.second; out.br_align = (int)kv.first; out.br_cols = (int)br_gcd[kv.first];
-        out.br_img_cols = (int)std::min<int64_t>(br_img_gcd[kv.first], out.br_cols);
-        if (out.br_cols % std::max(out.br_img_cols, 1)) out.br_img_cols = 1;
-      }
     if (getenv("CSXB_NO_BLOCK_TABLES")) out.bc_align = out.bc_rows = out.br_align = out.br_cols = out.br_img_cols = 0;   // tuning aid
   }
   // entries of the block tables (table numbers: gpu_layout.hpp)
@@ -529,7 +530,20 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
         // block tables: one entry per sub-block under the group of rows it adds to (own rows here, images at the owners
         // of its columns)
         const int64_t grow = cp.row_start + row;
-        if (kind == K_BCOL) {
+        const bool fits = kind == K_BCOL ? ((int64_t)delta % out.bc_rows == 0 && grow % out.bc_rows == 0 && (!m.symmetric || start_col % out.bc_align == 0))
+                                         : ((int64_t)delta % out.br_cols == 0 && grow % out.br_align == 0);
+        if (!fits) {   // (a block cut by a partition boundary ...): its elements one by one
+          for (int k = 0; k < size; k++) {
+            const int64_t er = grow + (kind == K_BROW ? k % (int)align : k / (int)align);
+            const int64_t ec = start_col + (kind == K_BROW ? k / (int)align : k % (int)align);
+            btents.push_back(BtEnt{(int64_t)pi, 4, er, BlockImage{d.voff + (uint32_t)k, (uint32_t)ec}});
+            if (m.symmetric) {
+              const int64_t q = owner_of(ec);
+              if (q < 0) return "symmetric update targets a row that is not on this device";
+              btents.push_back(BtEnt{q, 4, ec, BlockImage{d.voff + (uint32_t)k, (uint32_t)er | BT_IMAGE}});
+            }
+          }
+        } else if (kind == K_BCOL) {
           const int64_t A = out.bc_align, R0 = out.bc_rows;
           for (int64_t k = 0; k * R0 < (int64_t)delta; k++) {
             const uint32_t vo = d.voff + (uint32_t)(k * R0 * A);
@@ -546,7 +560,11 @@ std::string build_layout(const CsxMatrix &m, DeviceLayout &out) {
           const int64_t A = out.br_align, C0 = out.br_cols;
           for (int64_t k = 0; k * C0 < (int64_t)delta; k++)
             btents.push_back(BtEnt{(int64_t)pi, 2, grow / A, BlockImage{d.voff + (uint32_t)(k * C0 * A), (uint32_t)(start_col + k * C0)}});
-          if (m.symmetric) {   // image of a block-row unit: one entry per aligned group of its columns (or per column)
+          if (m.symmetric && out.br_img_cols > 1 && start_col % out.br_img_cols) {   // columns off the grid: a descriptor
+            XDesc td = d;
+            td.meta |= XD_TRANSPOSED;
+            if (!list_rows(td, cmin, cmax, pend)) return "symmetric update targets a row that is not on this device";
+          } else if (m.symmetric) {   // image of a block-row unit: one entry per aligned group of its columns (or per column)
             const int64_t G = std::max(out.br_img_cols, 1);
             for (int64_t j = 0; j < (int64_t)delta; j += G)
               for (int64_t g = start_col + j; g < start_col + j + G;) {   // a group can be cut by a partition boundary
