@@ -105,6 +105,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) csx_spmv_xe_kernel(const __
   if (b < X.nb) {
     // Edge CTAs walk their tile with one row per thread (a 4-rows-per-thread tile is split over four CTAs): the sooner
     // the edge rows are out, the more slack the neighbours have before their next step needs them.
+    // With many edge tiles (a 3-D stencil: 65 tiles per side) the split costs more than it gains: whole tiles then.
+    if (RPT == 4 && X.split == 1) {
+      const long long tile = b < X.edge_lo_end ? b : X.edge_hi_begin + (b - X.edge_lo_end);
+      spmv_edge_cta<XD, false, RPT, KSET, 0, BT>(P, x, y, alpha, tile, tile, X, ypar);
+      return;
+    }
     constexpr int SPLIT = RPT == 4 ? 4 : 1;
     const int bt = b / SPLIT, sub = b % SPLIT;
     const long long tile = bt < X.edge_lo_end ? bt : X.edge_hi_begin + (bt - X.edge_lo_end);
@@ -973,8 +979,10 @@ static void xchg_choose_mode(csxb_xchg *h, int64_t own_lo, int64_t own_hi) {
   while (a < pl.ntiles && is_edge(a)) a++;
   while (b > a && is_edge(b - 1)) b--;
   for (int64_t t = a; t < b; t++) if (is_edge(t)) return;   // an interior tile touches another rank: keep the sync kernel
-  const int split = pl.rpt == 4 ? 4 : 1;   // edge CTAs per edge tile (csx_spmv_xe_kernel)
-  D.mode = 1; D.edge_lo_end = (int)a; D.edge_hi_begin = (int)b; D.nb = (int)(a + (pl.ntiles - b)) * split;
+  // edge CTAs per edge tile (csx_spmv_xe_kernel): a few edge tiles are split so that their rows are out early
+  const char *smax = getenv("CSXB_XCHG_SPLIT_MAX");   // tests: 0 forces whole edge tiles
+  const int split = (pl.rpt == 4 && a + (pl.ntiles - b) <= (smax ? atoi(smax) : 16)) ? 4 : 1;
+  D.mode = 1; D.edge_lo_end = (int)a; D.edge_hi_begin = (int)b; D.nb = (int)(a + (pl.ntiles - b)) * split; D.split = split;
 }
 
 // bases[q] = rank q's block as seen from this device (IPC mapping, or the pointer itself inside one process)

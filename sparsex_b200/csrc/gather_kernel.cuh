@@ -170,7 +170,8 @@ struct XchgDev {
   // neighbours' edge tiles of the previous step, and the last of them to finish publishes this step to the
   // neighbours — a whole step before anybody needs it.  The other tiles touch no remote data and never wait.
   int mode;                                // 0: sync kernel at the end of every step, 1: edge tiles first
-  int nb;                                  // number of edge tiles
+  int nb;                                  // number of edge CTAs
+  int split;                               // edge CTAs per edge tile: 4 (one row per thread) when there are few edge tiles, else 1
   int edge_lo_end, edge_hi_begin;          // edge tiles are [0, edge_lo_end) and [edge_hi_begin, ntiles)
   unsigned long long *started, *bdone;     // local counters: CTAs that have read the step number / edge CTAs finished
 };

@@ -303,14 +303,16 @@ def test_pipelined_host_buffer_path(slab_rows):
             A.close()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_peer_exchange_logical_ranks(world):
+@pytest.mark.parametrize("world,split_max", [(2, None), (4, None), (3, "0")])
+def test_peer_exchange_logical_ranks(world, split_max, monkeypatch):
     """csxb_xchg_*: repeated SpMV with the exchange fused into the kernel.  All logical ranks live on cuda:0 in
     this process (csxb_xchg_connect_ptr), every rank issues its steps on its own stream (a step ends with the
     flag exchange with its neighbours); after every step each rank's next x must hold alpha*A*x on every column
     its partition reads."""
     torch = _torch()
     from sparsex_b200 import CsxMatrix, PeerExchange, lib
+    if split_max is not None:   # whole edge tiles instead of four one-row-per-thread CTAs (what many edge tiles get)
+        monkeypatch.setenv("CSXB_XCHG_SPLIT_MAX", split_max)
     rng = np.random.default_rng(world)
     cases = [poisson2d(70)[:3] + (4900, {}), stencil27(12)[:3] + (1728, {"spx.preproc.xform": "br,bc", "spx.preproc.sampling": "none"}),
              rmat(11)[:3] + (2048, {"spx.preproc.xform": "none"}),
