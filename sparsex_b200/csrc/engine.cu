@@ -215,12 +215,14 @@ __global__ void __launch_bounds__(CTA_THREADS) csx_decode_gather_kernel(const __
 }
 
 // ---- kernel 2 of non-symmetric partitions: stream kernel (stream_kernel.cuh), one warp per chunk ----------------
-__device__ __forceinline__ void sk_vectors(const SkIO &io, const double *&x, double *&y) {
+__device__ __forceinline__ int sk_vectors(const SkIO &io, const double *&x, double *&y) {
   x = io.x; y = io.y;
   if (io.step) {   // multi-GPU exchange: vectors by step parity
     const unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(io.step);
     x = io.vec[k & 1]; y = io.vec[(k & 1) ^ 1];
+    return (int)((k & 1) ^ 1);
   }
+  return 0;
 }
 template <int R, uint32_t KM, int BC, int BRC>
 __global__ void __launch_bounds__(SK_WARPS * 32, 4) csx_stream_kernel(const __grid_constant__ PartDev P, const __grid_constant__ SkIO io,
@@ -236,8 +238,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32, 4) csx_stream_kernel(const __gr
   const uint32_t ch = P.sk_c0 + blockIdx.x * SK_WARPS + warp;
   if (ch >= P.sk_c1) return;
   const double *x; double *y;
-  sk_vectors(io, x, y);
-  sk_chunk<R, KM, BC, BRC, false>(P, ch, sacc[warp], sid, lane, x, y, alpha, beta, overwrite, nullptr, nullptr);
+  const int ypar = sk_vectors(io, x, y);
+  sk_chunk<R, KM, BC, BRC, false>(P, ch, sacc[warp], sid, lane, x, y, alpha, beta, overwrite, nullptr, nullptr, &io, ypar);
 }
 __global__ void __launch_bounds__(SK_WARPS * 32) csx_stream_decode_kernel(const __grid_constant__ PartDev P, int *rows, int *cols) {
   __shared__ double sacc[SK_WARPS][SK_WIN];
@@ -259,18 +261,23 @@ __global__ void __launch_bounds__(256) csx_stream_fixup_kernel(const __grid_cons
                                                                 double alpha, double beta, int overwrite, long long clip_lo,
                                                                 long long clip_hi) {
   const double *x; double *y;
-  sk_vectors(io, x, y);
+  const int ypar = sk_vectors(io, x, y);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   for (long long i = P.sk_f0 + tid; i < P.sk_f1; i += nth) {
     double s = 0.0;
     for (uint32_t j = P.sk_fix_ptr[i]; j < P.sk_fix_ptr[i + 1]; j++) s += P.sk_scratch[P.sk_fix_idx[j]];
-    y[P.row_start + P.sk_fix_rows[i]] += alpha * s;
+    const long long g = P.row_start + P.sk_fix_rows[i];
+    const double v = y[g] + alpha * s;
+    y[g] = v;
+    sk_push(io, ypar, g, v);   // (the stream kernel pushed the row without these sums: the final value follows)
   }
   for (uint32_t g = P.sk_g0 + blockIdx.x; g < P.sk_g1; g += gridDim.x) {   // one CTA per gap (most gaps are short)
     const long long lo = max(P.sk_gaps[2 * g], clip_lo), hi = min(P.sk_gaps[2 * g + 1], clip_hi);
     for (long long r = lo + threadIdx.x; r < hi; r += blockDim.x) {
       double *yp = y + P.row_start + r;
-      *yp = overwrite ? 0.0 : beta * *yp;
+      const double v = overwrite ? 0.0 : beta * *yp;
+      *yp = v;
+      sk_push(io, ypar, P.row_start + r, v);
     }
   }
 }
@@ -805,7 +812,7 @@ int csxb_spmv(csxb_matrix_t *m, double alpha, const double *d_x, double beta, do
   cudaStream_t s = (cudaStream_t)stream;
   const bool sym = m->host.symmetric;
   SkIO io;
-  io.x = d_x; io.y = d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
+  io.x = d_x; io.y = d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr; io.npush = 0;
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
     int rc;
@@ -879,7 +886,7 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
         launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, beta, overwrite, m->s_run, NoXchg());
       } else {   // stream kernel writes y, fix-up, then the gather over the table adds
         SkIO io;
-        io.x = m->d_x; io.y = m->d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr;
+        io.x = m->d_x; io.y = m->d_y; io.step = nullptr; io.vec[0] = io.vec[1] = nullptr; io.npush = 0;
         if (launch_stream(m->pdev[sl.part], pl, sl.chunk0, sl.chunk1, io, alpha, beta, overwrite, m->s_run)) return fail("no stream kernel for the partition's pattern set");
         launch_fixup(m->pdev[sl.part], sl.f0, sl.f1, sl.g0, sl.g1, sl.row_lo - pl.row_start, sl.row_hi - pl.row_start, io, alpha, beta, overwrite, m->s_run);
         if (!pl.xdesc.empty() || !pl.bt.empty()) launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, 1.0, 0, m->s_run, NoXchg());
@@ -912,7 +919,7 @@ struct csxb_xchg {
   size_t n = 0;
   std::vector<void *> peer_base;     // other ranks' blocks (CUDA IPC mappings; own slot = base)
   XchgDev dev;
-  bool connected = false, fused_push = true;
+  bool connected = false;
   int64_t tail_lo = 0, tail_hi = 0;   // rows no rank owns (after the last partition's rows)
   int parity = 0;                     // protocol 1: index of the vector the next step reads (host side)
   int64_t issued = 0;                 // steps issued so far
@@ -940,7 +947,6 @@ csxb_xchg_t *csxb_xchg_create(csxb_matrix_t *m, int rank, int world) {
   unsigned long long *ctrl = (unsigned long long *)((char *)h->base + 2 * vb);
   h->dev.step = ctrl; h->dev.error = ctrl + 1; h->dev.started = ctrl + 2; h->dev.bdone = ctrl + 3; h->dev.flags = ctrl + 16;
   h->dev.rank = rank;
-  for (auto &pl : m->layout.parts) if (!pl.sk_chunks.empty()) h->fused_push = false;
   if (world == 1) {
     xchg_choose_mode(h, 0, (int64_t)h->n);
     h->connected = true;
@@ -965,7 +971,7 @@ static void xchg_choose_mode(csxb_xchg *h, int64_t own_lo, int64_t own_hi) {
   XchgDev &D = h->dev;
   D.mode = 0; D.nb = 0; D.edge_lo_end = 0; D.edge_hi_begin = 0;
   static const int dbg = getenv("CSXB_XCHG_DEBUG") ? atoi(getenv("CSXB_XCHG_DEBUG")) : 0;
-  if (!h->fused_push || h->m->layout.parts.size() != 1 || (dbg & 8)) return;
+  if (h->m->layout.parts.size() != 1 || !h->m->layout.parts[0].sk_chunks.empty() || (dbg & 8)) return;   // stream units: protocol 0
   const PartLayout &pl = h->m->layout.parts[0];
   if (!pl.ntiles || pl.ntiles > (int64_t(1) << 30)) return;
   const int64_t tr = pl.tile_rows();
@@ -1055,15 +1061,29 @@ int csxb_xchg_spmv(csxb_xchg_t *h, double alpha, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   static const int dbg = getenv("CSXB_XCHG_DEBUG") ? atoi(getenv("CSXB_XCHG_DEBUG")) : 0;   // tuning aid
   XchgDev X = h->dev;
-  if (!h->fused_push || (dbg & 4)) X.npush = 0;   // rows are final only after the chunk kernel: pushed by a copy kernel below
+  const bool copy_push = (dbg & 4) != 0;   // tuning aid: rows pushed by a copy kernel after the step's kernels
   SkIO io;
   io.x = nullptr; io.y = nullptr; io.step = h->dev.step; io.vec[0] = h->dev.vec[0]; io.vec[1] = h->dev.vec[1];
   for (size_t i = 0; i < m->pdev.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
-    if (X.mode == 1) launch_gather_xe(m->pdev[i], pl, X.vec[h->parity], X.vec[h->parity ^ 1], alpha, h->parity ^ 1, s, X);
-    else if (run_partition<false>(m->pdev[i], pl, io, alpha, 0.0, 1, s, X)) return fail("no stream kernel for the partition's pattern set");
+    if (X.mode == 1) { launch_gather_xe(m->pdev[i], pl, X.vec[h->parity], X.vec[h->parity ^ 1], alpha, h->parity ^ 1, s, X); continue; }
+    // The exchange is part of whichever kernel writes the final value of a row: the gather kernel when the partition
+    // has a gather pass (it runs last), else the stream kernel and its fix-up.
+    const bool gather_last = pl.sk_chunks.empty() || !pl.xdesc.empty() || !pl.bt.empty();
+    XchgDev Xp = X;
+    io.npush = 0;
+    if (copy_push) Xp.npush = 0;
+    else if (!gather_last) {
+      Xp.npush = 0;
+      io.npush = X.npush;
+      for (int p = 0; p < X.npush; p++) {
+        io.push_lo[p] = X.push_lo[p]; io.push_hi[p] = X.push_hi[p];
+        io.push_vec[p][0] = X.push_vec[p][0]; io.push_vec[p][1] = X.push_vec[p][1];
+      }
+    }
+    if (run_partition<false>(m->pdev[i], pl, io, alpha, 0.0, 1, s, Xp)) return fail("no stream kernel for the partition's pattern set");
   }
-  if (!h->fused_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 8, 256, 0, s>>>(h->dev);
+  if (copy_push && h->dev.npush) csx_xchg_push_kernel<<<148 * 8, 256, 0, s>>>(h->dev);
   if (h->tail_hi > h->tail_lo)
     csx_xchg_zero_tail_kernel<<<(unsigned)std::min<int64_t>(148, (h->tail_hi - h->tail_lo + 255) / 256), 256, 0, s>>>(h->dev, h->tail_lo, h->tail_hi, h->dev.mode == 1 ? (h->parity ^ 1) : -1);
   if (!(dbg & 1) && h->dev.mode == 0) csx_xchg_sync_kernel<<<1, 32, 0, s>>>(h->dev, dbg);

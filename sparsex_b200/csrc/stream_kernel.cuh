@@ -31,12 +31,23 @@ constexpr int SK_WIN = SK_WROWS + 8;                // window doubles per warp (
 
 // Source / target vectors of one launch.  `step` != nullptr: vectors by step parity of the multi-GPU exchange
 // (gather_kernel.cuh: XchgDev), read from the device-resident step counter so that a captured graph can be replayed.
+constexpr int SK_MAX_PEERS = 15;
 struct SkIO {
   const double *x;
   double *y;
   const unsigned long long *step;
   double *vec[2];
+  // multi-GPU exchange fused into the kernels that write the final rows of a partition without a gather pass: a row
+  // that rank p reads (global rows [push_lo[p], push_hi[p])) is also stored into p's vector over NVLink as it is written
+  int npush;
+  long long push_lo[SK_MAX_PEERS], push_hi[SK_MAX_PEERS];
+  double *push_vec[SK_MAX_PEERS][2];
 };
+// stores v to row g of the target vector of every peer that reads the row
+__device__ __forceinline__ void sk_push(const SkIO &io, int par, long long g, double v) {
+  for (int p = 0; p < io.npush; p++)
+    if (g >= io.push_lo[p] && g < io.push_hi[p]) io.push_vec[p][par][g] = v;
+}
 
 // Bulk prefetch of [p, p + bytes) into L2 (cp.async.bulk.prefetch: one instruction, no registers, no LSU wavefronts),
 // clipped to `end`.  The stream kernel's loads form a dependent chain (chunk entry -> unit offsets -> heads -> deltas ->
@@ -341,7 +352,7 @@ __device__ __forceinline__ void sk_window(const SkCtx &c, const uint32_t A, cons
 template <int R, uint32_t KM, int BC, int BRC, bool DECODE>
 __device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, double *sacc, const uint4 *sid, const int lane,
                                          const double *__restrict__ x, double *__restrict__ y, const double alpha, const double beta,
-                                         const int overwrite, int *drows, int *dcols) {
+                                         const int overwrite, int *drows, int *dcols, const SkIO *io = nullptr, const int ypar = 0) {
   const uint4 *q = P.sk_chunks + 2 * (size_t)ch;
   const uint4 qa = __ldg(q), qb = __ldg(q + 1);
   const uint32_t cursor0 = qa.z;
@@ -472,16 +483,13 @@ __device__ __forceinline__ void sk_chunk(const PartDev &P, const uint32_t ch, do
 
   // ---- 3. the chunk's rows leave the window ---------------------------------------------------------------------
   {
-    uint32_t i = f_lo + lane;
-    if (i < f_hi) {
+    const bool push = io != nullptr && io->npush > 0;
+    for (uint32_t i = f_lo + lane; i < f_hi; i += 32) {
       double *yp = y + (c.grow0 + i);
-      const double v = alpha * sacc[i];
-      *yp = overwrite ? v : v + beta * *yp;
-    }
-    for (i += 32; i < f_hi; i += 32) {
-      double *yp = y + (c.grow0 + i);
-      const double v = alpha * sacc[i];
-      *yp = overwrite ? v : v + beta * *yp;
+      double v = alpha * sacc[i];
+      if (!overwrite) v += beta * *yp;
+      *yp = v;
+      if (push) sk_push(*io, ypar, c.grow0 + i, v);
     }
   }
   if (headf | (t_hi > f_hi)) {   // rows of other chunks: to the scratch array
