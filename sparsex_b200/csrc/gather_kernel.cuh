@@ -204,6 +204,13 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
 #pragma unroll
   for (int k = 0; k < RPT; k++) acc[k] = 0.0;
 
+  unsigned long long pol_stream = 0, pol_keep = 0;   // L2 cache policies of VAR 3
+#ifndef CSXB_EMUL
+  if (VAR == 3) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  }
+#endif
   if (XD) {
     const uint32_t b = __ldg(P.tile_xoff + tile), e = __ldg(P.tile_xoff + tile + 1);
     const int grow0 = (int)(P.row_start + lrow0);       // global rows of this warp: [grow0, grow0 + 32*RPT)
@@ -229,6 +236,27 @@ __device__ __forceinline__ void spmv_tile(const PartDev &P, const double *__rest
           const double *__restrict__ vp = values + ((long long)d.x + t0);
           const double *__restrict__ xp = x + ((long long)(int)d.z + t0);
 #ifndef CSXB_EMUL
+          if (VAR == 3 && RPT == 4) {
+            // as VAR 1, with cache policies: the values are read once (no L1 allocation, first to leave L2), x is re-read
+            // by the other diagonals and by neighbouring tiles (last to leave L2)
+            double v0, v1, v2, v3, x0, x1, x2, x3;
+            asm volatile(
+                "{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                "setp.lt.u32 p0, %8, %12;\n\tsetp.lt.u32 p1, %9, %12;\n\tsetp.lt.u32 p2, %10, %12;\n\tsetp.lt.u32 p3, %11, %12;\n\t"
+                "mov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+                "mov.f64 %2, 0d0000000000000000;\n\tmov.f64 %3, 0d0000000000000000;\n\t"
+                "mov.f64 %4, 0d0000000000000000;\n\tmov.f64 %5, 0d0000000000000000;\n\t"
+                "mov.f64 %6, 0d0000000000000000;\n\tmov.f64 %7, 0d0000000000000000;\n\t"
+                "@p0 ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%13], %15;\n\t@p0 ld.global.nc.L2::cache_hint.f64 %4, [%14], %16;\n\t"
+                "@p1 ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %1, [%13+256], %15;\n\t@p1 ld.global.nc.L2::cache_hint.f64 %5, [%14+256], %16;\n\t"
+                "@p2 ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %2, [%13+512], %15;\n\t@p2 ld.global.nc.L2::cache_hint.f64 %6, [%14+512], %16;\n\t"
+                "@p3 ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %3, [%13+768], %15;\n\t@p3 ld.global.nc.L2::cache_hint.f64 %7, [%14+768], %16;\n\t}"
+                : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3), "=d"(x0), "=d"(x1), "=d"(x2), "=d"(x3)
+                : "r"((uint32_t)t0), "r"((uint32_t)(t0 + 32)), "r"((uint32_t)(t0 + 64)), "r"((uint32_t)(t0 + 96)), "r"(size),
+                  "l"(vp), "l"(xp), "l"(pol_stream), "l"(pol_keep));
+            acc[0] += v0 * x0; acc[1 % RPT] += v1 * x1; acc[2 % RPT] += v2 * x2; acc[3 % RPT] += v3 * x3;
+            continue;
+          }
           if (VAR == 1 && RPT == 4) {
             // the eight loads of a unit as one block, so that all of them are in flight before the first FMA
             double v0, v1, v2, v3, x0, x1, x2, x3;
