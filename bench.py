@@ -102,6 +102,7 @@ def workload(key):
         # scaled-down versions (development, tests)
         "c5s": ("c5_rmat_22_scaled_down", "rmat", {"spx.preproc.xform": "none"}, dict(scale=22)),
         "c4s": ("c4_sym_block_banded_3M_scaled_down", "symbb", {"spx.matrix.symmetric": "true"}, dict(nb=1_000_000, b=1024)),
+        "c4ns": ("c4_block_banded_3M_not_symmetric_mode_scaled_down", "symbb", {}, dict(nb=1_000_000, b=1024)),
         "c3s": ("c3_stencil27_128_scaled_down", "s27", {}, dict(g=128)),
         "c3bs": ("c3_stencil27_128_blocks_scaled_down", "s27", {"spx.preproc.xform": "br,bc"}, dict(g=128)),
         "c2q": ("c2_poisson2d_2048_quarter_size", "p2", {}, dict(g=2048)),
