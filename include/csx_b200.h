@@ -130,6 +130,22 @@ csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen);
 int csxb_get_entry(csxb_matrix_t *m, int64_t row, int64_t col, double *value);
 int csxb_set_entry(csxb_matrix_t *m, int64_t row, int64_t col, double value);
 
+/* ---- reverse Cuthill-McKee reordering ------------------------------------------------
+ * Replaces ReorderCSR (src/internals/Facade.cpp:56-69 -> Rcm.hpp:318-340 DoReorder_RCM, FindPerm :116-153 on
+ * boost::cuthill_mckee_ordering).  Host code.  csxb_rcm_csr: zero-based square CSR; perm[old] = new (what
+ * spx_mat_get_perm returns); bandwidth[0/1] (may be NULL) = bandwidth before / after.  Returns 0, 1 when the matrix
+ * has no off-diagonal element ("no reordering available for this matrix", the input stays as it is), < 0 on bad
+ * arguments.  csxb_permute_csr: B = P A P^T into caller-allocated arrays of the same sizes (row i of B = row
+ * inv_perm[i] of A, columns through perm, sorted; Rcm.hpp:289-316, Csr.hpp:270-360). */
+int csxb_rcm_csr(const int32_t *rowptr, const int32_t *colind, int64_t nrows, int64_t ncols, int32_t *perm,
+                 int64_t *bandwidth);
+/* The permutation is kept with the tuned matrix and stored by csxb_save (matvec.c:298, 422, 445).  get returns the
+ * length (0 = none) and copies when perm is not NULL. */
+int csxb_set_perm(csxb_matrix_t *m, const int32_t *perm, int64_t n);
+int64_t csxb_get_perm(const csxb_matrix_t *m, int32_t *perm);
+int csxb_permute_csr(const int32_t *rowptr, const int32_t *colind, const double *values, int64_t nrows,
+                     const int32_t *perm, int32_t *out_rowptr, int32_t *out_colind, double *out_values);
+
 /* ---- BLAS-1 on device-resident vectors -------------------------------------------
  * What a solver iteration needs next to the SpMV, so that it stays on the GPU
  * (VecScale / VecScaleAdd / VecAdd / VecSub / VecMult, src/internals/Vector.cpp:259-377).

@@ -17,7 +17,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libcsx_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("csx_oracle.cpp", "oracle_capi.cpp", "csx_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("csx_oracle.cpp", "oracle_capi.cpp", "rcm_oracle.cpp", "csx_oracle.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libcsx_oracle.so"], stdout=subprocess.DEVNULL)
     return so

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <vector>
 #include <unistd.h>
 
 #include <csx_b200.h>
@@ -68,6 +69,8 @@ struct input {    // src/api/matvec.c:43-48
   const spx_index_t *rowptr, *colind;
   const spx_value_t *values;
   spxb::CooHost *coo;
+  spx_index_t *own_rowptr, *own_colind;   // SPX_MAT_REORDER: the reordered copy the input now stands for (Rcm.hpp:289-316)
+  spx_value_t *own_values;
 };
 struct partition {  // src/api/matvec.c:53-60
   size_t nr_partitions;
@@ -203,6 +206,7 @@ spx_input_t *spx_input_load_csr(const spx_index_t *rowptr, const spx_index_t *co
   A->nrows = nrows; A->ncols = ncols; A->nnz = rowptr[nrows];
   A->rowptr = rowptr; A->colind = colind; A->values = values;
   A->coo = nullptr;
+  A->own_rowptr = A->own_colind = nullptr; A->own_values = nullptr;
   return A;
 }
 
@@ -221,22 +225,70 @@ spx_input_t *spx_input_load_mmf(const char *filename) {
   A->nrows = (spx_index_t)coo->nrows; A->ncols = (spx_index_t)coo->ncols; A->nnz = (spx_index_t)coo->row.size();
   A->rowptr = A->colind = nullptr; A->values = nullptr;
   A->coo = coo;
+  A->own_rowptr = A->own_colind = nullptr; A->own_values = nullptr;
   return A;
 }
 
 spx_error_t spx_input_destroy(spx_input_t *A) {
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid input handle"); return SPX_FAILURE; }
   delete A->coo;
+  free(A->own_rowptr); free(A->own_colind); free(A->own_values);
   spx_free(A);
   return SPX_SUCCESS;
 }
 
 // ---------------------------------------------------------------- tuning --
+static void log_line(int level, const char *msg) {   // the reference's LOG_INFO / LOG_WARNING lines of Rcm.hpp
+  if (g_log_level >= level) fprintf(g_log_file ? g_log_file : stderr, "%s\n", msg);
+}
+
+// ReorderCSR / ReorderMMF (src/internals/Facade.cpp:56-84 -> Rcm.hpp DoReorder_RCM): on success the input stands for
+// P A P^T from here on and *permutation holds perm[old] = new; on failure ("no reordering available", "reordering
+// failed") the input is left as it is and no permutation exists — the tune goes on either way, as in the reference.
+static void reorder_input(spx_input_t *in, spx_perm_t **permutation) {
+  log_line(3, "Reordering input matrix...");
+  if (in->nrows != in->ncols || in->nrows <= 0 || g_slab_row_start >= 0) { log_line(2, "reordering failed"); return; }
+  std::vector<int32_t> eu, ev, perm, inv;
+  int64_t bw[2] = {0, 0};
+  if (in->type == 'C') spxb::rcm_edges_csr(in->rowptr, in->colind, in->nrows, false, eu, ev);
+  else if (in->coo->buffered) spxb::rcm_edges_coo(*in->coo, eu, ev);
+  if (!spxb::rcm_find_perm(in->nrows, eu, ev, perm, inv, bw)) {
+    log_line(2, "no reordering available for this matrix");
+    log_line(2, "reordering failed");
+    return;
+  }
+  char line[96];
+  snprintf(line, sizeof(line), "Original Bandwidth: %lld", (long long)bw[0]); log_line(3, line);
+  snprintf(line, sizeof(line), "Final Bandwidth: %lld", (long long)bw[1]); log_line(3, line);
+  if (in->type == 'C') {
+    spx_index_t *rp = (spx_index_t *)malloc(sizeof(spx_index_t) * ((size_t)in->nrows + 1));
+    spx_index_t *ci = (spx_index_t *)malloc(sizeof(spx_index_t) * (size_t)(in->nnz ? in->nnz : 1));
+    spx_value_t *va = (spx_value_t *)malloc(sizeof(spx_value_t) * (size_t)(in->nnz ? in->nnz : 1));
+    if (!rp || !ci || !va || csxb_permute_csr(in->rowptr, in->colind, in->values, in->nrows, perm.data(), rp, ci, va) != 0) {
+      free(rp); free(ci); free(va);
+      log_line(2, "reordering failed");
+      return;
+    }
+    free(in->own_rowptr); free(in->own_colind); free(in->own_values);
+    in->rowptr = in->own_rowptr = rp; in->colind = in->own_colind = ci; in->values = in->own_values = va;
+  } else {
+    spxb::rcm_apply_coo(*in->coo, perm);
+  }
+  *permutation = (spx_perm_t *)malloc(sizeof(spx_perm_t) * (size_t)in->nrows);   // Facade.cpp:63-66
+  for (spx_index_t i = 0; i < in->nrows; i++) (*permutation)[i] = perm[i];
+  log_line(3, "Reordering complete");
+}
+
 spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
   if (!in) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid input matrix"); return SPX_INVALID_MAT; }
-  // Optional SPX_MAT_REORDER (RCM, Rcm.hpp) is outside this engine's scope; the
-  // variadic slot cannot be read portably when the caller passed nothing, so it
-  // is left untouched and the matrix is tuned in its given ordering.
+  // matvec.c:268-272 reads the optional argument unconditionally; so does this (a caller that passes nothing leaves
+  // whatever the register holds, in the reference as here)
+  va_list ap;
+  va_start(ap, in);
+  spx_option_t option = va_arg(ap, spx_option_t);
+  va_end(ap);
+  spx_perm_t *permutation = SPX_INVALID_PERM;
+  if (option == SPX_MAT_REORDER) reorder_input(in, &permutation);
   char err[512] = "";
   std::string opts = options_string();
   csxb_matrix_t *m = nullptr;
@@ -248,16 +300,18 @@ spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
                       sizeof(err));
   else if (in->type == 'M')
     m = csxb_tune_coo_internal(*in->coo, opts.c_str(), g_part_lo, g_part_hi, err, sizeof(err));
-  if (!m) { spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
+  if (!m) { free(permutation); spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
   if (csxb_upload(m, g_device, 0) != 0) {
     spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
     csxb_destroy(m);
+    free(permutation);
     return SPX_INVALID_MAT;
   }
+  if (permutation) csxb_set_perm(m, permutation, in->nrows);   // stored with the matrix by spx_mat_save (matvec.c:422)
   spx_matrix_t *A = spx_malloc(spx_matrix_t, sizeof(spx_matrix_t));
   A->nrows = (int)csxb_info(m, CSXB_NROWS); A->ncols = in->ncols; A->nnz = in->nnz;
   A->symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
-  A->permutation = SPX_INVALID_PERM;
+  A->permutation = permutation;
   A->csx = m;
   A->stage_x = A->stage_y = nullptr;
   return A;
@@ -269,6 +323,7 @@ spx_error_t spx_mat_destroy(spx_matrix_t *A) {
   if (A->stage_x) cudaFree(A->stage_x);
   if (A->stage_y) cudaFree(A->stage_y);
   csxb_destroy(A->csx);
+  free(A->permutation);
   spx_free(A);
   return SPX_SUCCESS;
 }
@@ -304,6 +359,10 @@ spx_error_t spx_mat_get_entry(const spx_matrix_t *A, spx_index_t row, spx_index_
     SETERROR_0(SPX_OUT_OF_BOUNDS);
     return SPX_FAILURE;
   }
+  if (A->permutation != SPX_INVALID_PERM) {   // matvec.c:351-354 (and only meaningful for the square matrices RCM accepts)
+    row = A->permutation[row - indexing] + indexing;
+    column = A->permutation[column - indexing] + indexing;
+  }
   if (!value || csxb_get_entry(A->csx, row - indexing, column - indexing, value) != 0) {
     SETERROR_0(SPX_ERR_ENTRY_NOT_FOUND);
     return SPX_FAILURE;
@@ -319,6 +378,10 @@ spx_error_t spx_mat_set_entry(spx_matrix_t *A, spx_index_t row, spx_index_t colu
   if (row - indexing < 0 || row - indexing >= A->nrows || column - indexing < 0 || column - indexing >= A->ncols) {
     SETERROR_0(SPX_OUT_OF_BOUNDS);
     return SPX_FAILURE;
+  }
+  if (A->permutation != SPX_INVALID_PERM) {   // matvec.c:394-397
+    row = A->permutation[row - indexing] + indexing;
+    column = A->permutation[column - indexing] + indexing;
   }
   if (csxb_set_entry(A->csx, row - indexing, column - indexing, value) != 0) {
     SETERROR_0(SPX_ERR_ENTRY_NOT_FOUND);
@@ -351,14 +414,19 @@ spx_matrix_t *spx_mat_restore(const char *filename) {
   A->nnz = (spx_index_t)csxb_info(m, CSXB_NNZ);
   A->symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
   A->permutation = SPX_INVALID_PERM;
+  const int64_t np = csxb_get_perm(m, nullptr);   // LoadTuned hands the stored permutation back (matvec.c:444-445)
+  if (np > 0) {
+    A->permutation = (spx_perm_t *)malloc(sizeof(spx_perm_t) * (size_t)np);
+    csxb_get_perm(m, A->permutation);
+  }
   A->csx = m;
   A->stage_x = A->stage_y = nullptr;
   return A;
 }
-spx_perm_t *spx_mat_get_perm(const spx_matrix_t *A) {
+spx_perm_t *spx_mat_get_perm(const spx_matrix_t *A) {   // matvec.c:536-549
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_INVALID_PERM; }
-  SETERROR_1(SPX_ERR_ARG_INVALID, "a permutation is not available");
-  return SPX_INVALID_PERM;
+  if (!A->permutation) { SETERROR_1(SPX_ERR_ARG_INVALID, "a permutation is not available"); return SPX_INVALID_PERM; }
+  return A->permutation;
 }
 
 // ------------------------------------------------------------- partitions --

@@ -78,6 +78,7 @@ struct CsxMatrix {
   int nparts_total = 0;                    // partitions the matrix was split into
   int part_lo = 0;                         // parts[k] is global partition part_lo + k
   std::vector<CsxPartition> parts;
+  std::vector<int32_t> permutation;        // RCM (SPX_MAT_REORDER): old index -> new index; empty = given ordering
 };
 
 // Input views -----------------------------------------------------------
@@ -90,10 +91,19 @@ struct CooHost {   // MMF reader output, 1-based, row-major sorted
   int64_t nrows = 0, ncols = 0;
   std::vector<int> row, col;
   std::vector<double> val;
+  bool buffered = false;   // symmetric or column-wise file: the reference holds it in memory (Mmf.hpp:218), RCM sees its elements
 };
 
 // mmf.cpp — reference: include/sparsex/internals/Mmf.hpp:331-478
 std::string read_mmf(const char *path, CooHost &out);
+
+// rcm.cpp — reference: include/sparsex/internals/Rcm.hpp:116-340 (Boost Graph Library's cuthill_mckee_ordering restated)
+bool rcm_find_perm(int64_t n, const std::vector<int32_t> &eu, const std::vector<int32_t> &ev, std::vector<int32_t> &perm,
+                   std::vector<int32_t> &inv_perm, int64_t *bandwidth);
+void rcm_edges_csr(const int32_t *rowptr, const int32_t *colind, int64_t nrows, bool symmetric, std::vector<int32_t> &eu,
+                   std::vector<int32_t> &ev);
+void rcm_edges_coo(const CooHost &coo, std::vector<int32_t> &eu, std::vector<int32_t> &ev);
+void rcm_apply_coo(CooHost &coo, const std::vector<int32_t> &perm);
 
 // encoder.cpp — reference call stack SURVEY.md §3.2.  Encodes partitions
 // [part_lo, part_hi) of the nr_threads-way split; the other partitions are

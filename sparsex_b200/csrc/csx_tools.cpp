@@ -190,6 +190,7 @@ std::string save_matrix(const CsxMatrix &m, const char *path) {
     w.vec(p.rows_info); w.vec(p.dvalues); w.vec(p.map_cpus); w.vec(p.map_pos);
     w.str(p.encoding_log);
   }
+  w.vec(m.permutation);   // SaveTuned stores the permutation with the matrix (matvec.c:422, CsxSaveRestore.hpp)
   const bool ok = w.ok && fclose(f) == 0;
   return ok ? "" : std::string("write error on ") + path;
 }
@@ -221,6 +222,19 @@ std::string load_matrix(const char *path, CsxMatrix &m) {
     if (!r.ok || (int64_t)p.values.size() != p.nnz) { fclose(f); return "corrupt container (partition arrays)"; }
     if (p.nrows < 0 || p.ncols != m.ncols || p.row_start < 0 || p.row_start + p.nrows > m.nrows || p.id_map.size() > 64 ||
         (m.symmetric && (int64_t)p.dvalues.size() + p.row_start > m.nrows)) { fclose(f); return "corrupt container (partition header)"; }
+  }
+  if (r.ok && r.left > 0) {   // containers written before the permutation was stored end here
+    r.vec(m.permutation);
+    if (r.ok && !m.permutation.empty()) {
+      bool good = (int64_t)m.permutation.size() == m.nrows;
+      std::vector<bool> seen(good ? (size_t)m.nrows : 0, false);
+      for (size_t i = 0; good && i < m.permutation.size(); i++) {
+        const int32_t v = m.permutation[i];
+        good = v >= 0 && v < m.nrows && !seen[(size_t)v];
+        if (good) seen[(size_t)v] = true;
+      }
+      if (!good) { fclose(f); return "corrupt container (permutation)"; }
+    }
   }
   fclose(f);
   if (!r.ok) return "truncated container";

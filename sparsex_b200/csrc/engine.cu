@@ -1208,6 +1208,18 @@ csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen) {
   return m;
 }
 
+// The RCM permutation travels with the matrix (matvec.c:298, 422, 445): perm[old] = new, n = 0 clears it.
+int csxb_set_perm(csxb_matrix_t *m, const int32_t *perm, int64_t n) {
+  if (!m || n < 0 || (n && (!perm || n != m->host.nrows))) return fail("invalid permutation");
+  m->host.permutation.assign(perm, perm + n);
+  return 0;
+}
+int64_t csxb_get_perm(const csxb_matrix_t *m, int32_t *perm) {
+  if (!m) return -1;
+  if (perm) std::copy(m->host.permutation.begin(), m->host.permutation.end(), perm);
+  return (int64_t)m->host.permutation.size();
+}
+
 // Locates A(row, col) (zero-based): partition, index into its values (or into dvalues when diag is set).
 static int locate_entry(csxb_matrix *m, int64_t row, int64_t col, size_t &part, int64_t &idx, bool &diag) {
   CsxMatrix &H = m->host;

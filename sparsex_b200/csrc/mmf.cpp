@@ -84,6 +84,7 @@ std::string read_mmf(const char *path, CooHost &out) {
     std::sort(es.begin(), es.end(), [](const Entry &a, const Entry &b) { return a.r < b.r || (a.r == b.r && a.c < b.c); });
   out = CooHost();
   out.nrows = nr; out.ncols = nc;
+  out.buffered = buffered;
   out.row.reserve(es.size()); out.col.reserve(es.size()); out.val.reserve(es.size());
   for (const Entry &e : es) {
     if (e.r < 1 || e.r > nr || e.c < 1 || e.c > nc) return "index out of bounds in MMF file";

@@ -70,6 +70,14 @@ def lib():
     L.csxb_get_entry.argtypes = [vp, i64, i64, C.POINTER(dbl)]
     L.csxb_set_entry.restype = i32
     L.csxb_set_entry.argtypes = [vp, i64, i64, dbl]
+    L.csxb_rcm_csr.restype = i32
+    L.csxb_rcm_csr.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.csxb_permute_csr.restype = i32
+    L.csxb_permute_csr.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    L.csxb_set_perm.restype = i32
+    L.csxb_set_perm.argtypes = [vp, vp, i64]
+    L.csxb_get_perm.restype = i64
+    L.csxb_get_perm.argtypes = [vp, vp]
     L.csxb_xchg_create.restype = vp
     L.csxb_xchg_create.argtypes = [vp, i32, i32]
     L.csxb_xchg_handle.restype = i32
@@ -89,6 +97,35 @@ def lib():
     L.csxb_xchg_destroy.argtypes = [vp]
     _LIB = L
     return L
+
+
+def rcm_csr(rowptr, colind, n):
+    """csxb_rcm_csr: (perm, (bandwidth before, after)) with perm[old] = new, or (None, None) when the matrix has
+    no off-diagonal element (Rcm.hpp:275-279)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    perm = np.empty(n, dtype=np.int32)
+    bw = np.zeros(2, dtype=np.int64)
+    rc = lib().csxb_rcm_csr(rowptr.ctypes.data, colind.ctypes.data, n, n, perm.ctypes.data, bw.ctypes.data)
+    if rc == 1:
+        return None, None
+    if rc != 0:
+        raise EngineError("csxb_rcm_csr: invalid arguments")
+    return perm, (int(bw[0]), int(bw[1]))
+
+
+def permute_csr(rowptr, colind, values, perm):
+    """csxb_permute_csr: P A P^T as (rowptr, colind, values)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    perm = np.ascontiguousarray(perm, dtype=np.int32)
+    n = len(rowptr) - 1
+    orp, oci, ova = np.empty_like(rowptr), np.empty_like(colind), np.empty_like(values)
+    if lib().csxb_permute_csr(rowptr.ctypes.data, colind.ctypes.data, values.ctypes.data, n, perm.ctypes.data,
+                              orp.ctypes.data, oci.ctypes.data, ova.ctypes.data) != 0:
+        raise EngineError("csxb_permute_csr: invalid arguments")
+    return orp, oci, ova
 
 
 def _opts(opts):
@@ -349,6 +386,10 @@ class SpxApi(object):
             "spx_mat_get_partition": (vp, [vp]),
             "spx_mat_get_entry": (i32, [vp, i32, i32, C.POINTER(dbl)]),
             "spx_mat_get_engine": (vp, [vp]),
+            "spx_mat_set_entry": (i32, [vp, i32, i32, dbl]),
+            "spx_mat_get_perm": (C.POINTER(i32), [vp]),
+            "spx_mat_save": (i32, [vp, cp]), "spx_mat_restore": (vp, [cp]),
+            "spx_vec_reorder": (i32, [VP, C.POINTER(i32)]), "spx_vec_inv_reorder": (i32, [VP, C.POINTER(i32)]),
             "spx_partition_csr": (vp, [vp, i32, C.c_size_t]),
             "spx_partition_get_rs": (C.POINTER(i32), [vp]), "spx_partition_get_re": (C.POINTER(i32), [vp]),
             "spx_partition_destroy": (i32, [vp]),
@@ -376,6 +417,12 @@ class SpxApi(object):
             f.restype = res
             f.argtypes = args
             setattr(self, name, f)
+        tune = self.spx_mat_tune
+
+        def spx_mat_tune(inp, option=0):
+            # the optional argument is always passed: the callee reads the variadic slot unconditionally (matvec.c:268-272)
+            return tune(inp, C.c_int(option))
+        self.spx_mat_tune = spx_mat_tune
 
     @staticmethod
     def as_numpy(vec):

@@ -442,6 +442,97 @@ def test_set_entry_and_restore_on_device(tmp_path):
     api.spx_input_destroy(inp)
 
 
+def test_spx_mat_tune_reorder(tmp_path):
+    """spx_mat_tune(input, SPX_MAT_REORDER) (matvec.c:262-300, Rcm.hpp): the tuned matrix is P A P^T, the permutation is
+    the one csxb_rcm_csr computes, vectors go through spx_vec_reorder / spx_vec_inv_reorder, single entries are
+    addressed in the original numbering, the container keeps the permutation; symmetric MatrixMarket input."""
+    torch = _torch()
+    import ctypes as C
+    import scipy.sparse as sp
+    from sparsex_b200 import load_spx_api, SpxApi, engine
+    from tests.test_cpu_rcm import scrambled_banded, csr
+    SPX_MAT_REORDER = 42
+    api = load_spx_api()
+    api.spx_init()
+    api.spx_log_disable_all()
+    for sym in (b"false", b"true"):
+        n = 6000
+        a = scrambled_banded(n, 6, 31)
+        a = sp.csr_matrix(a + a.T)          # values symmetric too, so that CSX-Sym applies
+        rp, ci, va = csr(a)
+        api.spx_option_set(b"spx.rt.nr_threads", b"2")
+        api.spx_option_set(b"spx.matrix.symmetric", sym)
+        inp = api.spx_input_load_csr(rp.ctypes.data, ci.ctypes.data, va.ctypes.data, n, n)
+        M = api.spx_mat_tune(inp, SPX_MAT_REORDER)
+        assert M
+        pp = api.spx_mat_get_perm(M)
+        assert pp
+        perm = np.ctypeslib.as_array(pp, shape=(n,)).copy()
+        want, bw = engine.rcm_csr(rp, ci, n)
+        assert np.array_equal(perm, want) and bw[1] < bw[0]
+        x = api.spx_vec_create(n, None)
+        y = api.spx_vec_create(n, None)
+        rng = np.random.default_rng(5)
+        xs = rng.uniform(-1, 1, n)
+        SpxApi.as_numpy(x)[:] = xs
+        assert api.spx_vec_reorder(x, pp) == 0
+        assert np.array_equal(SpxApi.as_numpy(x)[perm], xs)
+        assert api.spx_matvec_mult(0.75, M, x, y) == 0
+        api.spx_device_synchronize()
+        assert api.spx_vec_inv_reorder(y, pp) == 0
+        ref = 0.75 * _csr_spmv(rp, ci, va, xs, n)
+        bound = 0.75 * _abs_bound(rp, ci, va, xs, n) + 1e-300
+        assert np.max(np.abs(SpxApi.as_numpy(y) - ref) / bound) <= TOL
+        # entries in the caller's numbering
+        v = C.c_double()
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        for k in rng.integers(0, len(va), 25):
+            assert api.spx_mat_get_entry(M, int(rows[k]), int(ci[k]), C.byref(v)) == 0 and v.value == va[k]
+        path = os.path.join(str(tmp_path), "r.csxb").encode()
+        assert api.spx_mat_save(M, path) == 0
+        R = api.spx_mat_restore(path)
+        assert R
+        rp2 = api.spx_mat_get_perm(R)
+        assert rp2 and np.array_equal(np.ctypeslib.as_array(rp2, shape=(n,)), perm)
+        api.spx_mat_destroy(R)
+        api.spx_mat_destroy(M)
+        api.spx_input_destroy(inp)
+        api.spx_vec_destroy(x)
+        api.spx_vec_destroy(y)
+    # MatrixMarket: a symmetric file is held in memory and reordered (Rcm.hpp:155-204)
+    api.spx_option_set(b"spx.matrix.symmetric", b"false")
+    api.spx_option_set(b"spx.rt.nr_threads", b"1")
+    path = os.path.join(GOLDEN, "matrices", "symmetric.mtx.sorted").encode()
+    inp = api.spx_input_load_mmf(path)
+    M = api.spx_mat_tune(inp, SPX_MAT_REORDER)
+    assert M
+    pp = api.spx_mat_get_perm(M)
+    n = api.spx_mat_get_nrows(M)
+    assert pp and sorted(np.ctypeslib.as_array(pp, shape=(n,)).tolist()) == list(range(n))
+    from tests.test_cpu_rcm import oracle_rcm
+    ent = [l.split() for l in open(path.decode()) if not l.startswith("%")][1:]
+    r = np.array([int(e[0]) - 1 for e in ent]); c = np.array([int(e[1]) - 1 for e in ent]); v = np.array([float(e[2]) for e in ent])
+    off = r != c
+    full = sp.csr_matrix((np.concatenate([v, v[off]]), (np.concatenate([r, c[off]]), np.concatenate([c, r[off]]))), shape=(n, n))
+    frp, fci, fva = csr(full)
+    mperm = np.ctypeslib.as_array(pp, shape=(n,)).copy()
+    assert np.array_equal(mperm, oracle_rcm(frp, fci, n, symmetric=1))   # edges = the upper triangle, row-major
+    x = api.spx_vec_create(n, None)
+    y = api.spx_vec_create(n, None)
+    xs = np.random.default_rng(6).uniform(-1, 1, n)
+    SpxApi.as_numpy(x)[:] = xs
+    api.spx_vec_reorder(x, pp)
+    assert api.spx_matvec_mult(1.0, M, x, y) == 0
+    api.spx_device_synchronize()
+    api.spx_vec_inv_reorder(y, pp)
+    assert np.max(np.abs(SpxApi.as_numpy(y) - _csr_spmv(frp, fci, fva, xs, n)) / (_abs_bound(frp, fci, fva, xs, n) + 1e-300)) <= TOL
+    api.spx_vec_destroy(x)
+    api.spx_vec_destroy(y)
+    api.spx_mat_destroy(M)
+    api.spx_input_destroy(inp)
+    api.spx_option_set(b"spx.rt.nr_threads", b"1")
+
+
 def test_blas1_helpers_on_device_vectors():
     """spx_vec_* on library (managed, HBM-resident) vectors run on the GPU; a conjugate-gradient iteration written
     against the SparseX API (src/examples/ style) converges on an SPD matrix."""

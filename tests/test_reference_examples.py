@@ -33,7 +33,8 @@ def test_reference_examples_compile_unchanged():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("prog,args", [("csr_example", []), ("mmf_example", ["tests/golden/matrices/demopatt.mtx.sorted"]),
-                                       ("advanced_example", ["tests/golden/matrices/demopatt.mtx.sorted"])])
+                                       ("advanced_example", ["tests/golden/matrices/demopatt.mtx.sorted"]),
+                                       ("reordering_example", ["tests/golden/matrices/symmetric.mtx.sorted"])])
 def test_reference_examples_run(prog, args):
     import torch
     if not torch.cuda.is_available():
