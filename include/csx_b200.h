@@ -130,6 +130,26 @@ csxb_matrix_t *csxb_load(const char *path, char *err, size_t errlen);
 int csxb_get_entry(csxb_matrix_t *m, int64_t row, int64_t col, double *value);
 int csxb_set_entry(csxb_matrix_t *m, int64_t row, int64_t col, double value);
 
+/* ---- several GPUs behind one handle, one process ------------------------------------
+ * Replaces the reference's worker-thread pool over the nr_threads partitions of one matrix (CsxKernels.cpp:35-129
+ * MatVecMult / MatVecMult_sym, the CSX-Sym local buffers and their reduction, CsxSpmv.cpp:37-50): the partitions of a
+ * tuned (or loaded) matrix that has not been uploaded are dealt out, in contiguous ranges, to the listed devices
+ * (a device may be listed more than once: logical members on one GPU).  csxb_group_create consumes `whole` on success.
+ * csxb_group_spmv: y = alpha*A*x (+ beta*y unless overwrite); x and y may be host, pinned, managed or device memory;
+ * synchronous.  CSX-Sym: the sums for rows of lower members are added by their owners in member order (no atomics).
+ * (Repeated SpMV with the exchange inside the kernels is csxb_xchg_*; this is the one-call form behind spx_matvec_*.) */
+typedef struct csxb_group csxb_group_t;
+csxb_group_t *csxb_group_create(csxb_matrix_t *whole, const int *devices, int ndev, int free_host, char *err, size_t errlen);
+void csxb_group_destroy(csxb_group_t *g);
+int csxb_group_size(const csxb_group_t *g);
+csxb_matrix_t *csxb_group_member(csxb_group_t *g, int i);
+int csxb_group_device(const csxb_group_t *g, int i);
+int csxb_group_spmv(csxb_group_t *g, double alpha, const double *x, double beta, double *y, int overwrite);
+int csxb_group_save(csxb_group_t *g, const char *path);
+int csxb_group_get_entry(csxb_group_t *g, int64_t row, int64_t col, double *value);
+int csxb_group_set_entry(csxb_group_t *g, int64_t row, int64_t col, double value);
+int csxb_group_set_perm(csxb_group_t *g, const int32_t *perm, int64_t n);
+
 /* ---- reverse Cuthill-McKee reordering ------------------------------------------------
  * Replaces ReorderCSR (src/internals/Facade.cpp:56-69 -> Rcm.hpp:318-340 DoReorder_RCM, FindPerm :116-153 on
  * boost::cuthill_mckee_ordering).  Host code.  csxb_rcm_csr: zero-based square CSR; perm[old] = new (what

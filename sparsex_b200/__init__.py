@@ -6,7 +6,7 @@ host encoder, C-ABI in ``include/csx_b200.h`` and the ``spx_*`` drop-in API in
 tests and by ``bench.py``: thin ctypes bindings, no compute of its own and no
 CPU fallback — if the shared library is missing, importing the bindings fails.
 """
-from .engine import (CsxMatrix, EngineError, PeerExchange, lib, lib_path,  # noqa: F401
+from .engine import (CsxMatrix, DeviceGroup, EngineError, PeerExchange, lib, lib_path,  # noqa: F401
                      load_spx_api, SpxApi)
 
-__all__ = ["CsxMatrix", "EngineError", "PeerExchange", "lib", "lib_path", "load_spx_api", "SpxApi"]
+__all__ = ["CsxMatrix", "DeviceGroup", "EngineError", "PeerExchange", "lib", "lib_path", "load_spx_api", "SpxApi"]

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <sstream>
 #include <string>
 #include <vector>
 #include <unistd.h>
@@ -31,6 +32,7 @@ std::map<std::string, std::string> &props() {
   return p;
 }
 int g_device = 0;
+std::vector<int> g_devices;   // spx.rt.nr_gpus / spx.b200.devices: the GPUs one matrix is spread over (one process)
 bool g_async = false;
 bool g_gpu_ok = false;   // a managed vector was allocated successfully: a usable GPU is present
 int g_part_lo = 0, g_part_hi = -1;   // one process per GPU: encode and own only partitions [lo, hi)
@@ -60,7 +62,8 @@ struct matrix {   // src/api/matvec.c:30-38
   spx_index_t nrows, ncols, nnz;
   int symmetric;
   spx_perm_t *permutation;
-  csxb_matrix_t *csx;
+  csxb_matrix_t *csx;          // one GPU: the tuned matrix; several GPUs: member 0 of `group`
+  csxb_group_t *group;         // several GPUs in this process (spx.rt.nr_gpus > 1), else NULL
   double *stage_x, *stage_y;   // device staging for vectors that live in plain host memory
 };
 struct input {    // src/api/matvec.c:43-48
@@ -166,6 +169,18 @@ void spx_option_set(const char *option, const char *value) {  // matvec.c:753-75
   if (!option || !value) { SETWARNING(SPX_WARN_TUNING_OPT); return; }
   std::string k(option), v(value);
   if (k == "spx.b200.device") { g_device = atoi(value); return; }
+  if (k == "spx.rt.nr_gpus" || k == "spx.b200.nr_gpus") {   // GPUs 0 .. n-1
+    g_devices.clear();
+    for (int i = 0; i < atoi(value); i++) g_devices.push_back(i);
+    return;
+  }
+  if (k == "spx.b200.devices") {   // explicit list, e.g. "2,3" (an index may repeat: logical members on one GPU)
+    g_devices.clear();
+    std::stringstream ss(v);
+    std::string t;
+    while (std::getline(ss, t, ',')) if (!t.empty()) g_devices.push_back(atoi(t.c_str()));
+    return;
+  }
   if (k == "spx.b200.async") { g_async = (v == "true" || v == "1"); return; }
   if (k == "spx.b200.part_lo") { g_part_lo = atoi(value); return; }
   if (k == "spx.b200.part_hi") { g_part_hi = atoi(value); return; }
@@ -279,6 +294,27 @@ static void reorder_input(spx_input_t *in, spx_perm_t **permutation) {
   log_line(3, "Reordering complete");
 }
 
+// One GPU: upload.  Several (spx.rt.nr_gpus / spx.b200.devices, all partitions local): the partitions are dealt out
+// to the GPUs (csxb_group_create consumes m).  On failure m is destroyed and the error handler has been called.
+static bool place_on_devices(csxb_matrix_t *m, csxb_group_t **group) {
+  *group = nullptr;
+  const bool whole = csxb_info(m, CSXB_PART_LO) == 0 && csxb_info(m, CSXB_NPARTS) == csxb_info(m, CSXB_NPARTS_TOTAL);
+  if (g_devices.size() > 1 && whole && csxb_info(m, CSXB_NPARTS) > 1) {
+    char err[512] = "";
+    *group = csxb_group_create(m, g_devices.data(), (int)g_devices.size(), 0, err, sizeof(err));
+    if (*group) return true;
+    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err);
+    csxb_destroy(m);
+    return false;
+  }
+  if (csxb_upload(m, g_devices.size() == 1 ? g_devices[0] : g_device, 0) != 0) {
+    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+    csxb_destroy(m);
+    return false;
+  }
+  return true;
+}
+
 spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
   if (!in) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid input matrix"); return SPX_INVALID_MAT; }
   // matvec.c:268-272 reads the optional argument unconditionally; so does this (a caller that passes nothing leaves
@@ -291,6 +327,14 @@ spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
   if (option == SPX_MAT_REORDER) reorder_input(in, &permutation);
   char err[512] = "";
   std::string opts = options_string();
+  if (g_devices.size() > 1 && g_part_hi < 0 && g_slab_row_start < 0) {
+    // at least one partition per GPU: the partition count is the reference's spx.rt.nr_threads
+    auto it = props().find("spx.rt.nr_threads");
+    if (it == props().end() || atoi(it->second.c_str()) < (int)g_devices.size()) {
+      opts += "spx.rt.nr_threads=" + std::to_string(g_devices.size()) + ";";
+      log_line(3, "spx.rt.nr_threads raised to the number of GPUs");
+    }
+  }
   csxb_matrix_t *m = nullptr;
   if (in->type == 'C' && g_slab_row_start >= 0)   // the arrays hold the rows of partition g_part_lo only
     m = csxb_tune_csr_slab(in->rowptr, in->colind, in->values, in->nrows, g_slab_total_rows, in->ncols, g_slab_row_start, g_part_lo,
@@ -301,18 +345,16 @@ spx_matrix_t *spx_mat_tune(spx_input_t *in, ...) {
   else if (in->type == 'M')
     m = csxb_tune_coo_internal(*in->coo, opts.c_str(), g_part_lo, g_part_hi, err, sizeof(err));
   if (!m) { free(permutation); spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
-  if (csxb_upload(m, g_device, 0) != 0) {
-    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
-    csxb_destroy(m);
-    free(permutation);
-    return SPX_INVALID_MAT;
-  }
   if (permutation) csxb_set_perm(m, permutation, in->nrows);   // stored with the matrix by spx_mat_save (matvec.c:422)
+  const int nrows_tuned = (int)csxb_info(m, CSXB_NROWS), symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
+  csxb_group_t *group = nullptr;
+  if (!place_on_devices(m, &group)) { free(permutation); return SPX_INVALID_MAT; }
   spx_matrix_t *A = spx_malloc(spx_matrix_t, sizeof(spx_matrix_t));
-  A->nrows = (int)csxb_info(m, CSXB_NROWS); A->ncols = in->ncols; A->nnz = in->nnz;
-  A->symmetric = (int)csxb_info(m, CSXB_SYMMETRIC);
+  A->nrows = nrows_tuned; A->ncols = in->ncols; A->nnz = in->nnz;
+  A->symmetric = symmetric;
   A->permutation = permutation;
-  A->csx = m;
+  A->group = group;
+  A->csx = group ? csxb_group_member(group, 0) : m;
   A->stage_x = A->stage_y = nullptr;
   return A;
 }
@@ -322,7 +364,8 @@ spx_error_t spx_mat_destroy(spx_matrix_t *A) {
   cudaDeviceSynchronize();
   if (A->stage_x) cudaFree(A->stage_x);
   if (A->stage_y) cudaFree(A->stage_y);
-  csxb_destroy(A->csx);
+  if (A->group) csxb_group_destroy(A->group);
+  else csxb_destroy(A->csx);
   free(A->permutation);
   spx_free(A);
   return SPX_SUCCESS;
@@ -363,7 +406,8 @@ spx_error_t spx_mat_get_entry(const spx_matrix_t *A, spx_index_t row, spx_index_
     row = A->permutation[row - indexing] + indexing;
     column = A->permutation[column - indexing] + indexing;
   }
-  if (!value || csxb_get_entry(A->csx, row - indexing, column - indexing, value) != 0) {
+  if (!value || (A->group ? csxb_group_get_entry(A->group, row - indexing, column - indexing, value)
+                          : csxb_get_entry(A->csx, row - indexing, column - indexing, value)) != 0) {
     SETERROR_0(SPX_ERR_ENTRY_NOT_FOUND);
     return SPX_FAILURE;
   }
@@ -383,7 +427,8 @@ spx_error_t spx_mat_set_entry(spx_matrix_t *A, spx_index_t row, spx_index_t colu
     row = A->permutation[row - indexing] + indexing;
     column = A->permutation[column - indexing] + indexing;
   }
-  if (csxb_set_entry(A->csx, row - indexing, column - indexing, value) != 0) {
+  if ((A->group ? csxb_group_set_entry(A->group, row - indexing, column - indexing, value)
+                : csxb_set_entry(A->csx, row - indexing, column - indexing, value)) != 0) {
     SETERROR_0(SPX_ERR_ENTRY_NOT_FOUND);
     return SPX_FAILURE;
   }
@@ -393,7 +438,7 @@ spx_error_t spx_mat_set_entry(spx_matrix_t *A, spx_index_t row, spx_index_t colu
 spx_error_t spx_mat_save(const spx_matrix_t *A, const char *filename) {
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_FAILURE; }
   if (!filename) { SETWARNING(SPX_WARN_CSXFILE); filename = "csx_file"; }
-  if (csxb_save(A->csx, filename) != 0) {
+  if ((A->group ? csxb_group_save(A->group, filename) : csxb_save(A->csx, filename)) != 0) {
     spx_err_get_handler()(SPX_ERR_FILE, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
     return SPX_FAILURE;
   }
@@ -404,11 +449,6 @@ spx_matrix_t *spx_mat_restore(const char *filename) {
   char err[512] = "";
   csxb_matrix_t *m = csxb_load(filename, err, sizeof(err));
   if (!m) { spx_err_get_handler()(SPX_ERR_FILE, __FILE__, __LINE__, __func__, "%s", err); return SPX_INVALID_MAT; }
-  if (csxb_upload(m, g_device, 0) != 0) {
-    spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
-    csxb_destroy(m);
-    return SPX_INVALID_MAT;
-  }
   spx_matrix_t *A = spx_malloc(spx_matrix_t, sizeof(spx_matrix_t));
   A->nrows = (spx_index_t)csxb_info(m, CSXB_NROWS); A->ncols = (spx_index_t)csxb_info(m, CSXB_NCOLS);
   A->nnz = (spx_index_t)csxb_info(m, CSXB_NNZ);
@@ -419,7 +459,10 @@ spx_matrix_t *spx_mat_restore(const char *filename) {
     A->permutation = (spx_perm_t *)malloc(sizeof(spx_perm_t) * (size_t)np);
     csxb_get_perm(m, A->permutation);
   }
-  A->csx = m;
+  csxb_group_t *group = nullptr;
+  if (!place_on_devices(m, &group)) { free(A->permutation); spx_free(A); return SPX_INVALID_MAT; }
+  A->group = group;
+  A->csx = group ? csxb_group_member(group, 0) : m;
   A->stage_x = A->stage_y = nullptr;
   return A;
 }
@@ -440,11 +483,16 @@ static spx_partition_t *part_alloc(size_t n) {
 }
 spx_partition_t *spx_mat_get_partition(const spx_matrix_t *A) {  // matvec.c:485-514: a new object, caller destroys
   if (!A) { SETERROR_1(SPX_ERR_ARG_INVALID, "invalid matrix handle"); return SPX_INVALID_PART; }
-  int np = (int)csxb_info(A->csx, CSXB_NPARTS);
+  const int nh = A->group ? csxb_group_size(A->group) : 1;
+  int np = 0;
+  for (int h = 0; h < nh; h++) np += (int)csxb_info(A->group ? csxb_group_member(A->group, h) : A->csx, CSXB_NPARTS);
   spx_partition_t *p = part_alloc(np);
-  for (int i = 0; i < np; i++) {
-    p->row_start[i] = (spx_index_t)csxb_part_info(A->csx, i, CSXB_P_ROW_START);
-    p->row_end[i] = p->row_start[i] + (spx_index_t)csxb_part_info(A->csx, i, CSXB_P_NROWS);
+  for (int h = 0, k = 0; h < nh; h++) {
+    const csxb_matrix_t *m = A->group ? csxb_group_member(A->group, h) : A->csx;
+    for (int i = 0; i < (int)csxb_info(m, CSXB_NPARTS); i++, k++) {
+      p->row_start[k] = (spx_index_t)csxb_part_info(m, i, CSXB_P_ROW_START);
+      p->row_end[k] = p->row_start[k] + (spx_index_t)csxb_part_info(m, i, CSXB_P_NROWS);
+    }
   }
   return p;
 }
@@ -488,6 +536,13 @@ spx_error_t spx_partition_destroy(spx_partition_t *p) {
 static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx_vector_t *x, spx_value_t beta,
                             spx_vector_t *y, int overwrite) {
   spx_matrix_t *A = const_cast<spx_matrix_t *>(Ac);
+  if (A->group) {   // several GPUs: columns out, kernels, (CSX-Sym: reduction,) rows back; synchronous
+    if (csxb_group_spmv(A->group, alpha, x->elements, beta, y->elements, overwrite) != 0) {
+      spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());
+      return SPX_FAILURE;
+    }
+    return SPX_SUCCESS;
+  }
   cudaSetDevice(g_device);
   const double *dx = x->elements;
   double *dy = y->elements;

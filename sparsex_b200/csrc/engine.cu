@@ -1299,3 +1299,5 @@ int csxb_decode_coords(const csxb_matrix_t *mc, int part, int32_t *rows, int32_t
 }
 
 }  // extern "C"
+
+#include "device_group.inl"

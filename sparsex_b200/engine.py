@@ -78,6 +78,23 @@ def lib():
     L.csxb_set_perm.argtypes = [vp, vp, i64]
     L.csxb_get_perm.restype = i64
     L.csxb_get_perm.argtypes = [vp, vp]
+    L.csxb_group_create.restype = vp
+    L.csxb_group_create.argtypes = [vp, vp, i32, i32, cp, C.c_size_t]
+    L.csxb_group_destroy.argtypes = [vp]
+    L.csxb_group_size.restype = i32
+    L.csxb_group_size.argtypes = [vp]
+    L.csxb_group_member.restype = vp
+    L.csxb_group_member.argtypes = [vp, i32]
+    L.csxb_group_device.restype = i32
+    L.csxb_group_device.argtypes = [vp, i32]
+    L.csxb_group_spmv.restype = i32
+    L.csxb_group_spmv.argtypes = [vp, dbl, vp, dbl, vp, i32]
+    L.csxb_group_save.restype = i32
+    L.csxb_group_save.argtypes = [vp, cp]
+    L.csxb_group_get_entry.restype = i32
+    L.csxb_group_get_entry.argtypes = [vp, i64, i64, C.POINTER(dbl)]
+    L.csxb_group_set_entry.restype = i32
+    L.csxb_group_set_entry.argtypes = [vp, i64, i64, dbl]
     L.csxb_xchg_create.restype = vp
     L.csxb_xchg_create.argtypes = [vp, i32, i32]
     L.csxb_xchg_handle.restype = i32
@@ -281,6 +298,64 @@ class CsxMatrix(object):
     def close(self):
         if self._h:
             lib().csxb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceGroup(object):
+    """csxb_group_* (include/csx_b200.h): the partitions of one tuned matrix spread over several GPUs of this process.
+    Consumes `matrix` (which must hold all partitions and must not be uploaded)."""
+
+    def __init__(self, matrix, devices, free_host=False):
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        err = C.create_string_buffer(1024)
+        self.nrows, self.ncols = matrix.nrows, matrix.ncols
+        self._h = lib().csxb_group_create(matrix._h, dev.ctypes.data, len(dev), int(free_host), err, 1024)
+        if not self._h:
+            raise EngineError(err.value.decode())
+        matrix._h = None   # consumed
+        self.size = lib().csxb_group_size(self._h)
+
+    def member_info(self, i, what):
+        return lib().csxb_info(lib().csxb_group_member(self._h, i), what)
+
+    def spmv(self, alpha, x, y, beta=0.0, overwrite=True):
+        """x, y: numpy float64 arrays (host buffers) or torch float64 tensors (device or pinned memory)."""
+        def ptr(v, n):
+            if isinstance(v, np.ndarray):
+                assert v.dtype == np.float64 and v.flags.c_contiguous and v.size == n
+                return v.ctypes.data
+            assert v.is_contiguous() and v.numel() == n
+            return v.data_ptr()
+        if lib().csxb_group_spmv(self._h, alpha, ptr(x, self.ncols), beta, ptr(y, self.nrows), int(overwrite)) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return y
+
+    def save(self, path):
+        if lib().csxb_group_save(self._h, path.encode()) != 0:
+            raise EngineError(lib().csxb_last_error().decode())
+
+    def get_entry(self, row, col):
+        v = C.c_double()
+        rc = lib().csxb_group_get_entry(self._h, row, col, C.byref(v))
+        if rc < 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return v.value if rc == 0 else None
+
+    def set_entry(self, row, col, value):
+        rc = lib().csxb_group_set_entry(self._h, row, col, value)
+        if rc < 0:
+            raise EngineError(lib().csxb_last_error().decode())
+        return rc == 0
+
+    def close(self):
+        if self._h:
+            lib().csxb_group_destroy(self._h)
             self._h = None
 
     def __del__(self):

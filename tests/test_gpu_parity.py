@@ -470,8 +470,9 @@ def test_spx_mat_tune_reorder(tmp_path):
         perm = np.ctypeslib.as_array(pp, shape=(n,)).copy()
         want, bw = engine.rcm_csr(rp, ci, n)
         assert np.array_equal(perm, want) and bw[1] < bw[0]
-        x = api.spx_vec_create(n, None)
-        y = api.spx_vec_create(n, None)
+        parts = api.spx_mat_get_partition(M)
+        x = api.spx_vec_create(n, parts)
+        y = api.spx_vec_create(n, parts)
         rng = np.random.default_rng(5)
         xs = rng.uniform(-1, 1, n)
         SpxApi.as_numpy(x)[:] = xs
@@ -495,6 +496,7 @@ def test_spx_mat_tune_reorder(tmp_path):
         rp2 = api.spx_mat_get_perm(R)
         assert rp2 and np.array_equal(np.ctypeslib.as_array(rp2, shape=(n,)), perm)
         api.spx_mat_destroy(R)
+        api.spx_partition_destroy(parts)
         api.spx_mat_destroy(M)
         api.spx_input_destroy(inp)
         api.spx_vec_destroy(x)
@@ -517,8 +519,9 @@ def test_spx_mat_tune_reorder(tmp_path):
     frp, fci, fva = csr(full)
     mperm = np.ctypeslib.as_array(pp, shape=(n,)).copy()
     assert np.array_equal(mperm, oracle_rcm(frp, fci, n, symmetric=1))   # edges = the upper triangle, row-major
-    x = api.spx_vec_create(n, None)
-    y = api.spx_vec_create(n, None)
+    parts = api.spx_mat_get_partition(M)
+    x = api.spx_vec_create(n, parts)
+    y = api.spx_vec_create(n, parts)
     xs = np.random.default_rng(6).uniform(-1, 1, n)
     SpxApi.as_numpy(x)[:] = xs
     api.spx_vec_reorder(x, pp)
@@ -528,9 +531,144 @@ def test_spx_mat_tune_reorder(tmp_path):
     assert np.max(np.abs(SpxApi.as_numpy(y) - _csr_spmv(frp, fci, fva, xs, n)) / (_abs_bound(frp, fci, fva, xs, n) + 1e-300)) <= TOL
     api.spx_vec_destroy(x)
     api.spx_vec_destroy(y)
+    api.spx_partition_destroy(parts)
     api.spx_mat_destroy(M)
     api.spx_input_destroy(inp)
     api.spx_option_set(b"spx.rt.nr_threads", b"1")
+
+
+def _group_cases():
+    rng = np.random.default_rng(77)
+    rp, ci, va, n = sym_block_banded(2500, b=30)[:3] + (7500,)
+    yield "symbb", rp, ci, va, n, True
+    rp, ci, va = random_structured(rng, 3000, 3000, symmetric=True)
+    yield "random_sym", rp, ci, va, 3000, True
+    rp, ci, va, n = poisson2d(90)
+    yield "poisson", rp, ci, va, n, False
+    rp, ci, va = random_structured(rng, 2500, 2500)
+    # trailing empty rows: they belong to no partition
+    rp = np.concatenate([rp, np.full(40, rp[-1], dtype=rp.dtype)])
+    yield "random_trailing", rp, ci, va, 2540, False
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0, 0, 0]], ids=["2members", "5members"])
+def test_device_group_logical_members(devices, tmp_path):
+    """csxb_group_* (several GPUs behind one handle, one process) with every member on cuda:0: host buffers (the
+    members' slab pipelines on concurrent host threads), device vectors, CSX-Sym with the owner-side reduction, both y
+    semantics, trailing rows, entries, container round trip."""
+    torch = _torch()
+    from sparsex_b200 import CsxMatrix, DeviceGroup
+    rng = np.random.default_rng(len(devices))
+    for name, rp, ci, va, n, symmetric in _group_cases():
+        nc = n   # (the case with trailing empty rows is square too: its last 40 columns are never read)
+        for sym in ([False, True] if symmetric else [False]):
+            opts = {"spx.rt.nr_threads": 6, "spx.b200.slab_rows": 512}
+            if sym:
+                opts["spx.matrix.symmetric"] = "true"
+            A = CsxMatrix.tune_csr(rp, ci, va, n, nc, opts)
+            G = DeviceGroup(A, devices)
+            assert G.size == min(len(devices), 6)
+            x = rng.uniform(-1, 1, nc)
+            y0 = rng.uniform(-1, 1, n)
+            ref = _csr_spmv(rp, ci, va, x, n)
+            bound = _abs_bound(rp, ci, va, x, n) + 1e-300
+            last = int(np.max(np.nonzero(np.diff(rp))[0])) + 1   # rows behind it belong to nobody
+            # host buffers, spx_matvec_mult semantics: stale content of y must not survive
+            y = np.full(n, 7.0)
+            G.spmv(0.5, x, y)
+            assert np.max(np.abs(y - 0.5 * ref) / (0.5 * bound)) <= TOL, (name, sym, "host mult")
+            assert np.all(y[last:] == 0.0)
+            # host buffers, spx_matvec_kernel semantics: rows behind the last partition stay as they are
+            y = y0.copy()
+            G.spmv(0.75, x, y, beta=-0.3, overwrite=False)
+            want = 0.75 * ref - 0.3 * y0
+            want[last:] = y0[last:]
+            assert np.max(np.abs(y - want) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300)) <= TOL, (name, sym, "host kernel")
+            # device vectors
+            dx = torch.from_numpy(x).cuda()
+            dy = torch.full((n,), 7.0, dtype=torch.float64, device="cuda")
+            G.spmv(0.5, dx, dy)
+            y = dy.cpu().numpy()
+            assert np.max(np.abs(y - 0.5 * ref) / (0.5 * bound)) <= TOL, (name, sym, "device mult")
+            assert np.all(y[last:] == 0.0)
+            dy = torch.from_numpy(y0.copy()).cuda()
+            G.spmv(0.75, dx, dy, beta=-0.3, overwrite=False)
+            assert np.max(np.abs(dy.cpu().numpy() - want) / (0.75 * bound + 0.3 * np.abs(y0) + 1e-300)) <= TOL, (name, sym, "device kernel")
+            # repeated calls give the same bits (no atomics anywhere, fixed reduction order)
+            dy2 = torch.empty_like(dy)
+            G.spmv(0.5, dx, dy2)
+            dy3 = torch.empty_like(dy)
+            G.spmv(0.5, dx, dy3)
+            assert torch.equal(dy2, dy3)
+            # entries live in the member that owns the row
+            rows = np.repeat(np.arange(n), np.diff(rp))
+            for k in rng.integers(0, len(va), 12):
+                assert G.get_entry(int(rows[k]), int(ci[k])) == va[k]
+            # container round trip: all partitions back in one file
+            path = os.path.join(str(tmp_path), "g.csxb")
+            G.save(path)
+            B = CsxMatrix.load(path).upload(0)
+            yb = np.zeros(n)
+            B.spmv_host(0.5, x, yb)
+            assert np.max(np.abs(yb - 0.5 * ref) / (0.5 * bound)) <= TOL
+            B.close()
+            G.close()
+
+
+def test_spx_api_on_several_gpus():
+    """The drop-in API with spx.b200.devices / spx.rt.nr_gpus: library (managed) vectors and user buffers; real
+    GPUs when the box has more than one, logical members on cuda:0 otherwise."""
+    torch = _torch()
+    from sparsex_b200 import load_spx_api, SpxApi
+    api = load_spx_api()
+    api.spx_init()
+    ndev = torch.cuda.device_count()
+    devs = ",".join(str(i % ndev) for i in range(max(2, min(ndev, 4)))).encode()
+    rp, ci, va, n = sym_block_banded(3000, b=40)[:3] + (9000,)
+    rng = np.random.default_rng(3)
+    xs = rng.uniform(-1, 1, n)
+    ref = _csr_spmv(rp, ci, va, xs, n)
+    bound = _abs_bound(rp, ci, va, xs, n) + 1e-300
+    try:
+        for sym in (b"false", b"true"):
+            api.spx_option_set(b"spx.b200.devices", devs)
+            api.spx_option_set(b"spx.matrix.symmetric", sym)
+            api.spx_option_set(b"spx.rt.nr_threads", b"1")    # raised to the number of GPUs
+            inp = api.spx_input_load_csr(rp.ctypes.data, ci.ctypes.data, va.ctypes.data, n, n)
+            M = api.spx_mat_tune(inp)
+            assert M
+            parts = api.spx_mat_get_partition(M)
+            nparts = devs.count(b",") + 1
+            rs = api.spx_partition_get_rs(parts)
+            re_ = api.spx_partition_get_re(parts)
+            assert rs[0] == 0 and all(rs[i + 1] == re_[i] for i in range(nparts - 1)) and re_[nparts - 1] == n
+            x = api.spx_vec_create(n, parts)
+            y = api.spx_vec_create(n, parts)
+            SpxApi.as_numpy(x)[:] = xs
+            assert api.spx_matvec_mult(0.5, M, x, y) == 0
+            assert np.max(np.abs(SpxApi.as_numpy(y) - 0.5 * ref) / (0.5 * bound)) <= TOL
+            y0 = SpxApi.as_numpy(y).copy()
+            assert api.spx_matvec_kernel(2.0, M, x, 0.5, y) == 0
+            assert np.max(np.abs(SpxApi.as_numpy(y) - (2.0 * ref + 0.5 * y0)) / (2.0 * bound + 0.5 * np.abs(y0) + 1e-300)) <= TOL
+            # user buffers
+            import ctypes as C
+            xb, yb = xs.copy(), np.zeros(n)
+            tuned = C.c_void_p()
+            xv = api.spx_vec_create_from_buff(xb.ctypes.data, C.byref(tuned), n, parts, 43)
+            yv = api.spx_vec_create_from_buff(yb.ctypes.data, C.byref(tuned), n, parts, 43)
+            assert api.spx_matvec_mult(0.5, M, xv, yv) == 0
+            assert np.max(np.abs(yb - 0.5 * ref) / (0.5 * bound)) <= TOL
+            v = C.c_double()
+            assert api.spx_mat_get_entry(M, n - 1, int(ci[rp[n - 1]]), C.byref(v)) == 0 and v.value == va[rp[n - 1]]
+            for h in (xv, yv, x, y):
+                api.spx_vec_destroy(h)
+            api.spx_partition_destroy(parts)
+            api.spx_mat_destroy(M)
+            api.spx_input_destroy(inp)
+    finally:
+        api.spx_option_set(b"spx.b200.devices", b"")
+        api.spx_option_set(b"spx.matrix.symmetric", b"false")
+        api.spx_option_set(b"spx.rt.nr_threads", b"1")
 
 
 def test_blas1_helpers_on_device_vectors():
