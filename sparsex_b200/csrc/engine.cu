@@ -693,14 +693,18 @@ static bool gather_cache_policies(const PartLayout &pl) {
   return forced >= 0 ? forced != 0 : pl.nnz >= 12 * pl.nrows;
 }
 
+// Resident CTAs per SM the block-table instantiations are compiled for.  The table walk is a chain of dependent loads
+// (group pointer -> entry -> values, x), so it lives on occupancy: one row per thread fits 40 registers without spills
+// (6 CTAs), four rows per thread 48 (5 CTAs); measured on the block configs in profiles/r02_bt_variants.txt.
+template <int RPT> struct BtMinB { static constexpr int value = RPT == 1 ? 6 : 5; };
 // Launches kernel 1 over tiles [t0, t1) of one partition.  XP = XchgDev fuses the multi-GPU exchange into it.
 template <bool SYM, int RPT, int KSET, class XP>
 static void launch_gather_k(const PartDev &P, const PartLayout &pl, unsigned nt, const double *x, double *y, double alpha,
                             double beta, int overwrite, cudaStream_t s, const XP &X) {
   dim3 grid(nt), block(CTA_THREADS);
   if (!pl.bt.empty()) {   // block tables: the generic instantiation with the table loop (64 registers)
-    if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET_ANY, 4, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
-    else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, 4, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+    if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET_ANY, BtMinB<RPT>::value, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+    else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, BtMinB<RPT>::value, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
     return;
   }
   // descriptors can also come from other partitions (transposed images under CSX-Sym, whose many kinds need registers)
@@ -740,11 +744,11 @@ static void launch_gather_xe(const PartDev &P0, const PartLayout &pl, const doub
   const bool xd = !pl.xdesc.empty(), diag1 = pl.xd_diag1_only && xd && pl.bt.empty();
   if (!pl.bt.empty()) {
     if (pl.rpt == 4) {
-      if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
-      else csx_spmv_xe_kernel<false, 4, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+      if (xd) csx_spmv_xe_kernel<true, 4, KSET_ANY, BtMinB<4>::value, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+      else csx_spmv_xe_kernel<false, 4, KSET_ANY, BtMinB<4>::value, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
     } else {
-      if (xd) csx_spmv_xe_kernel<true, 1, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
-      else csx_spmv_xe_kernel<false, 1, KSET_ANY, 4, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+      if (xd) csx_spmv_xe_kernel<true, 1, KSET_ANY, BtMinB<1>::value, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
+      else csx_spmv_xe_kernel<false, 1, KSET_ANY, BtMinB<1>::value, 0, true><<<grid, block, 0, s>>>(P, x, y, alpha, ypar, X);
     }
     return;
   }

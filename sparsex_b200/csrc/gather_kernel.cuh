@@ -118,8 +118,13 @@ __device__ __forceinline__ double bt_row(const BtDev &T, const double *__restric
   double a0 = 0.0, a1 = 0.0;
   uint32_t e = e0;
   if (NL > 0) {
+    // the entries of the next pair are requested before the values of this pair are used: the chain entry -> values
+    // of one iteration overlaps the next one's entry loads
+    uint2 n0{0u, 0u}, n1{0u, 0u};
+    if (e + 1 < e1) { n0 = __ldg(T.ent + e); n1 = __ldg(T.ent + e + 1); }
     for (; e + 1 < e1; e += 2) {
-      const uint2 b0 = __ldg(T.ent + e), b1 = __ldg(T.ent + e + 1);
+      const uint2 b0 = n0, b1 = n1;
+      if (e + 3 < e1) { n0 = __ldg(T.ent + e + 2); n1 = __ldg(T.ent + e + 3); }
       const double *v0 = vals + b0.x, *v1 = vals + b1.x, *x0 = x + (b0.y & ~BT_IMAGE), *x1 = x + (b1.y & ~BT_IMAGE);
       double va[N], xa[N], vb[N], xb[N];
 #pragma unroll

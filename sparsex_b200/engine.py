@@ -22,7 +22,8 @@ class EngineError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsparsex_b200.so")
+    # SPARSEX_B200_LIB: another build of the same library (kernel experiments, tools/variants.sh)
+    return os.environ.get("SPARSEX_B200_LIB") or os.path.join(_HERE, "libsparsex_b200.so")
 
 
 def lib():
