@@ -46,7 +46,7 @@ struct TuneOptions {
   int host_threads = 0;            // spx.b200.host_threads : 0 = hardware concurrency
   int rows_per_thread = 0;         // spx.b200.rows_per_thread : GPU tile shape, 0 = by partition size, else 1 or 4
   int slice_elems = 0;             // spx.b200.slice : elements one lane of the chunk kernel handles, 0 = from the unit mix
-  long long slab_rows = 1 << 19;   // spx.b200.slab_rows : rows per slab of the pipelined host-buffer SpMV
+  long long slab_rows = 0;         // spx.b200.slab_rows : rows per slab of the pipelined host-buffer SpMV, 0 = sizes chosen by the engine
   // Returns "" or an error message.  Unknown mnemonics are an error
   // (Runtime.hpp:108-134 logs and ignores; the C API layer downgrades this to a warning).
   std::string set(const std::string &mnemonic, const std::string &value);
@@ -74,7 +74,7 @@ struct CsxMatrix {
   bool symmetric = false, full_colind = false;
   int rows_per_thread = 0;                 // requested GPU tile shape (0 = automatic)
   int slice_elems = 0;                     // requested chunk-kernel slice length (0 = automatic)
-  long long slab_rows = 1 << 19;           // rows per slab of the pipelined host-buffer SpMV
+  long long slab_rows = 0;                 // rows per slab of the pipelined host-buffer SpMV (0 = chosen by the engine)
   int nparts_total = 0;                    // partitions the matrix was split into
   int part_lo = 0;                         // parts[k] is global partition part_lo + k
   std::vector<CsxPartition> parts;

@@ -240,7 +240,7 @@ std::string load_matrix(const char *path, CsxMatrix &m) {
   if (!r.ok) return "truncated container";
   // the same range checks the options go through at tune time (TuneOptions::set); the ctl stream itself is validated
   // when the GPU tables are built (build_layout walks it with bounds checks)
-  if (m.nrows < 0 || m.ncols < 0 || (m.rows_per_thread != 0 && m.rows_per_thread != 1 && m.rows_per_thread != 4) || m.slab_rows < 1 ||
+  if (m.nrows < 0 || m.ncols < 0 || (m.rows_per_thread != 0 && m.rows_per_thread != 1 && m.rows_per_thread != 4) || m.slab_rows < 0 ||
       m.nparts_total < (int)np || m.part_lo < 0 || m.part_lo + (int)np > m.nparts_total)
     return "corrupt container (options)";
   return "";

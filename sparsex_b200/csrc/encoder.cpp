@@ -1342,7 +1342,7 @@ std::string TuneOptions::set(const std::string &k, const std::string &v) {
     }
     else if (k == "spx.b200.slab_rows") {
       slab_rows = std::stoll(v);
-      if (slab_rows < 1) return "spx.b200.slab_rows must be positive";
+      if (slab_rows < 0) return "spx.b200.slab_rows must not be negative";
     }
     else if (k == "spx.b200.slice") {
       slice_elems = std::stoi(v);

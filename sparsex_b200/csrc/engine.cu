@@ -518,11 +518,22 @@ static int dev_copy(csxb_matrix *m, const T *src, size_t n, T **dst, size_t extr
 // fix-ups and its tiles of the gather kernel have run, and travel back then.
 static void build_slabs(csxb_matrix *m) {
   m->slabs.clear();
-  const int64_t SLAB_ROWS = m->host.slab_rows;
+  // spx.b200.slab_rows = 0 (default): an eighth of the device's rows, between 2^19 and 2^21 rows.  Uploads and downloads
+  // share the host link (measured on the B200 box: 55 GB/s one way, 43 GB/s per direction when both run back to back);
+  // with one upload and one download in flight the link gives 33 GB/s per direction in 4 MiB slabs and 38 GB/s in 8 or
+  // 16 MiB slabs (config 2: 4.02 -> 3.50 ms per call); slabs that grow and shrink towards the ends did not help (4.03 ms).
+  int64_t SLAB_ROWS = m->host.slab_rows;
+  if (SLAB_ROWS <= 0) {
+    int64_t total_rows = 0;
+    for (const PartLayout &pl : m->layout.parts) if (pl.ntiles) total_rows += pl.nrows;
+    SLAB_ROWS = int64_t(1) << 19;
+    while (SLAB_ROWS < (int64_t(1) << 21) && SLAB_ROWS * 16 <= total_rows) SLAB_ROWS *= 2;
+  }
   for (size_t i = 0; i < m->layout.parts.size(); i++) {
     const PartLayout &pl = m->layout.parts[i];
     if (!pl.ntiles) continue;
-    const int64_t tr = pl.tile_rows(), tiles_per = std::max<int64_t>(1, SLAB_ROWS / tr);
+    const int64_t tr = pl.tile_rows();
+    const int64_t tiles_per = std::max<int64_t>(1, SLAB_ROWS / tr);
     uint32_t c = 0, f = 0;
     const uint32_t nc = (uint32_t)pl.sk_chunks.size(), nf = (uint32_t)pl.sk_fix_rows.size(), ng = (uint32_t)pl.sk_gaps.size();
     int64_t xmax = -1, yup = 0;
@@ -878,6 +889,25 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
       m->slab_ev.resize(2 * m->slabs.size());
       for (size_t i = old; i < m->slab_ev.size(); i++) CUDA_TRY(cudaEventCreateWithFlags(&m->slab_ev[i], cudaEventDisableTiming));
     }
+    // CSXB_HOST_TRACE=1 (tuning aid): device time stamps of every slab's upload, kernels and download
+    static const bool trace = getenv("CSXB_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+      tev.resize(3 * m->slabs.size() + 1);
+      for (auto &e : tev) CUDA_TRY(cudaEventCreate(&e));
+      CUDA_TRY(cudaEventRecord(tev.back(), m->s_h2d));
+    }
+    // (downloads that trail the uploads by one or two slabs, CSXB_D2H_LAG in an earlier build, were no faster: config 2
+    // 3.47 ms per call with none, 3.65 - 3.96 ms with a lag of one slab, at slabs of 2^20 - 2^21 rows)
+    auto issue_download = [&](size_t k) -> int {
+      const csxb_matrix::Slab &sl = m->slabs[k];
+      if (sl.y_hi > sl.y_lo) {
+        CUDA_TRY(cudaStreamWaitEvent(m->s_d2h, m->slab_ev[2 * k + 1], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_y + sl.y_lo, m->d_y + sl.y_lo, (size_t)(sl.y_hi - sl.y_lo) * 8, cudaMemcpyDeviceToHost, m->s_d2h));
+      }
+      if (trace) CUDA_TRY(cudaEventRecord(tev[3 * k + 2], m->s_d2h));
+      return 0;
+    };
     int64_t x_done = m->slabs.front().x_lo;   // columns [x_lo of the first slab, x_done) are on the device
     int64_t y_up = 0;                         // y rows below this one are on the device (spx_matvec_kernel semantics)
     for (size_t k = 0; k < m->slabs.size(); k++) {
@@ -895,6 +925,7 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
         }
       }
       CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k], m->s_h2d));
+      if (trace) CUDA_TRY(cudaEventRecord(tev[3 * k], m->s_h2d));
       CUDA_TRY(cudaStreamWaitEvent(m->s_run, m->slab_ev[2 * k], 0));
       if (pl.sk_chunks.empty()) {
         launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, beta, overwrite, m->s_run, NoXchg());
@@ -906,10 +937,22 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
         if (!pl.xdesc.empty() || !pl.bt.empty()) launch_gather<false>(m->pdev[sl.part], pl, sl.tile0, sl.tile1, m->d_x, m->d_y, alpha, 1.0, 0, m->s_run, NoXchg());
       }
       CUDA_TRY(cudaEventRecord(m->slab_ev[2 * k + 1], m->s_run));
-      if (sl.y_hi > sl.y_lo) {
-        CUDA_TRY(cudaStreamWaitEvent(m->s_d2h, m->slab_ev[2 * k + 1], 0));
-        CUDA_TRY(cudaMemcpyAsync(h_y + sl.y_lo, m->d_y + sl.y_lo, (size_t)(sl.y_hi - sl.y_lo) * 8, cudaMemcpyDeviceToHost, m->s_d2h));
+      if (trace) CUDA_TRY(cudaEventRecord(tev[3 * k + 1], m->s_run));
+      if (issue_download(k)) return -1;
+    }
+    if (trace) {
+      CUDA_TRY(cudaStreamSynchronize(m->s_run));
+      CUDA_TRY(cudaStreamSynchronize(m->s_d2h));
+      for (size_t k = 0; k < m->slabs.size(); k++) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, tev.back(), tev[3 * k]);
+        cudaEventElapsedTime(&b, tev.back(), tev[3 * k + 1]);
+        cudaEventElapsedTime(&c, tev.back(), tev[3 * k + 2]);
+        const csxb_matrix::Slab &sl = m->slabs[k];
+        fprintf(stderr, "[host-trace] slab %3zu rows [%lld, %lld) x to %lld: up %.3f ms, run %.3f ms, down %.3f ms\n", k,
+                (long long)sl.row_lo, (long long)sl.row_hi, (long long)sl.x_hi, a, b, c);
       }
+      for (auto &e : tev) cudaEventDestroy(e);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(m->s_run));
