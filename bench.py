@@ -597,7 +597,7 @@ def main():
     yh = torch.zeros(n, dtype=torch.float64).pin_memory()
     vx = api.spx_vec_create_from_buff(xh.data_ptr(), None, n, None, 43)
     vy = api.spx_vec_create_from_buff(yh.data_ptr(), None, n, None, 43)
-    for _ in range(2):
+    for _ in range(6):   # warm-up; the library's host-buffer path settles its slab-kernel setting in the first five calls
         api.spx_matvec_mult(alpha, A, vx, vy)
     barrier()
     t0 = time.perf_counter()
@@ -625,6 +625,7 @@ def main():
     e2e = {"value": 2.0 * nnz * args.e2e_steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(hb[0]),
            "d2h_bytes_per_step": int(hb[1]), "steps": args.e2e_steps,
            "host_affinity": numa_note,
+           "slab_kernel_cap_bytes": int(L.csxb_info(eng._h, 10)),
            "api": "spx_matvec_mult on spx_vec_create_from_buff vectors (pinned host memory); every rank uploads the "
                   "columns its partition reads and downloads its rows, slab-pipelined (H2D, kernels, D2H overlap)"}
     peer_sync_kernel = peer is not None and peer.protocol()[0] == 0   # protocol 0 ends every step with a sync kernel

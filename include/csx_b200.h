@@ -58,7 +58,10 @@ enum { CSXB_NROWS = 0, CSXB_NCOLS = 1, CSXB_NNZ = 2, CSXB_SYMMETRIC = 3, CSXB_NP
        /* CSX-Sym with only some partitions local (valid after csxb_upload): rows [LO, HI) of y belong to
         * other devices; csxb_spmv zeroes them and adds this device's transposed contributions there, the
         * caller sends them to their owners and adds (sparsex_b200/dist.py: SymHaloReduce). */
-       CSXB_SYM_HALO_LO = 8, CSXB_SYM_HALO_HI = 9 };
+       CSXB_SYM_HALO_LO = 8, CSXB_SYM_HALO_HI = 9,
+       /* csxb_spmv_host: bytes of dynamic shared memory that cap the resident CTAs of the slab kernels (chosen by timing
+        * the first calls), and the number of calls so far */
+       CSXB_HOST_CAP = 10, CSXB_HOST_CALLS = 11 };
 int64_t csxb_info(const csxb_matrix_t *m, int what);
 
 /* Per-partition CSX arrays == csx_matrix_t / csx_sym_matrix_t / map_t

@@ -20,6 +20,8 @@
 // y handling of CsxKernels.cpp:35-129 / CsxSpmv.cpp:28-86.
 #include <cuda_runtime.h>
 
+#include <chrono>
+
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -313,6 +315,9 @@ struct csxb_matrix {
   std::vector<Slab> slabs;
   std::vector<cudaEvent_t> slab_ev;
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
+  int host_calls = 0;                  // csxb_spmv_host: calls so far (the first five choose host_cap)
+  double host_tune_s[2] = {0.0, 0.0};  // best time with the cap [0] and without [1]
+  size_t host_cap = 0;                 // dynamic shared memory per CTA of the slab kernels (caps the resident CTAs)
   int64_t bytes[7] = {0, 0, 0, 0, 0, 0, 0};
   std::vector<std::string> logs;
   std::vector<RowIndex> row_index;   // per partition, built on the first csxb_get/set_entry
@@ -420,6 +425,8 @@ int64_t csxb_info(const csxb_matrix_t *m, int what) {
     case CSXB_FULL_COLIND: return m->host.full_colind;
     case CSXB_SYM_HALO_LO: return m->sym_halo_lo;
     case CSXB_SYM_HALO_HI: return m->sym_halo_hi;
+    case CSXB_HOST_CAP: return (int64_t)m->host_cap;
+    case CSXB_HOST_CALLS: return m->host_calls;
   }
   return -1;
 }
@@ -708,14 +715,28 @@ static bool gather_cache_policies(const PartLayout &pl) {
 // (group pointer -> entry -> values, x), so it lives on occupancy: one row per thread fits 40 registers without spills
 // (6 CTAs), four rows per thread 48 (5 CTAs); measured on the block configs in profiles/r02_bt_variants.txt.
 template <int RPT> struct BtMinB { static constexpr int value = RPT == 1 ? 6 : 5; };
+// csxb_spmv_host only: dynamic shared memory per CTA of the gather kernels it launches.  The kernels do not use it; it caps
+// the CTAs resident per SM, i.e. how hard a slab's kernel pulls on HBM while the copy engines move x and y over PCIe.
+static thread_local size_t t_gather_dyn = 0;
+constexpr size_t HOST_CAP_SMEM = 40000;   // 5 CTAs per SM
+template <class K>
+static size_t gather_dyn(K kernel) {
+  if (t_gather_dyn > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t_gather_dyn);
+  return t_gather_dyn;
+}
 // Launches kernel 1 over tiles [t0, t1) of one partition.  XP = XchgDev fuses the multi-GPU exchange into it.
 template <bool SYM, int RPT, int KSET, class XP>
 static void launch_gather_k(const PartDev &P, const PartLayout &pl, unsigned nt, const double *x, double *y, double alpha,
                             double beta, int overwrite, cudaStream_t s, const XP &X) {
   dim3 grid(nt), block(CTA_THREADS);
   if (!pl.bt.empty()) {   // block tables: the generic instantiation with the table loop (64 registers)
-    if (!pl.xdesc.empty()) csx_spmv_kernel<true, SYM, RPT, KSET_ANY, BtMinB<RPT>::value, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
-    else csx_spmv_kernel<false, SYM, RPT, KSET_ANY, BtMinB<RPT>::value, 0, XP, true><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+    if (!pl.xdesc.empty()) {
+      auto k = csx_spmv_kernel<true, SYM, RPT, KSET_ANY, BtMinB<RPT>::value, 0, XP, true>;
+      k<<<grid, block, gather_dyn(k), s>>>(P, x, y, alpha, beta, overwrite, X);
+    } else {
+      auto k = csx_spmv_kernel<false, SYM, RPT, KSET_ANY, BtMinB<RPT>::value, 0, XP, true>;
+      k<<<grid, block, gather_dyn(k), s>>>(P, x, y, alpha, beta, overwrite, X);
+    }
     return;
   }
   // descriptors can also come from other partitions (transposed images under CSX-Sym, whose many kinds need registers)
@@ -736,8 +757,13 @@ static void launch_gather(const PartDev &P0, const PartLayout &pl, int64_t t0, i
   if (pl.rpt == 4) {
     if (diag1) {  // the instantiation the stencil configs run: loads of a unit issued as one PTX block
       dim3 grid(nt), block(CTA_THREADS);
-      if (gather_cache_policies(pl)) csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 3, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
-      else csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 1, XP><<<grid, block, 0, s>>>(P, x, y, alpha, beta, overwrite, X);
+      if (gather_cache_policies(pl)) {
+        auto k = csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 3, XP>;
+        k<<<grid, block, gather_dyn(k), s>>>(P, x, y, alpha, beta, overwrite, X);
+      } else {
+        auto k = csx_spmv_kernel<true, false, 4, KSET_DIAG1, 8, 1, XP>;
+        k<<<grid, block, gather_dyn(k), s>>>(P, x, y, alpha, beta, overwrite, X);
+      }
     }
     else launch_gather_k<SYM, 4, KSET_ANY>(P, pl, nt, x, y, alpha, beta, overwrite, s, X);
   } else {
@@ -908,6 +934,19 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
       if (trace) CUDA_TRY(cudaEventRecord(tev[3 * k + 2], m->s_d2h));
       return 0;
     };
+    // A slab's kernel at full tilt takes HBM bandwidth from the copy engines that move the other slabs' x and y
+    // (27-point stencil, 8 M rows: 1.92 - 1.97 ms per call as is, 1.75 ms with the kernels capped at 5 CTAs per SM, 1.87 - 1.90
+    // ms at 3 or 2); whether a cap pays depends on how long the kernels are next to the copies, so the first calls time
+    // both settings (calls 1, 3: no cap; 2, 4: cap) and the faster one stays.  CSXB_HOST_SMEM = bytes forces a setting.
+    const auto call_t0 = std::chrono::steady_clock::now();
+    const int tune_call = m->host_calls < 5 ? m->host_calls : -1;
+    {
+      const char *v = getenv("CSXB_HOST_SMEM");
+      if (v) t_gather_dyn = (size_t)atol(v);
+      else if (tune_call > 0) t_gather_dyn = (tune_call % 2 == 0) ? HOST_CAP_SMEM : 0;
+      else t_gather_dyn = m->host_cap;
+    }
+    struct DynReset { ~DynReset() { t_gather_dyn = 0; } } dyn_reset;
     int64_t x_done = m->slabs.front().x_lo;   // columns [x_lo of the first slab, x_done) are on the device
     int64_t y_up = 0;                         // y rows below this one are on the device (spx_matvec_kernel semantics)
     for (size_t k = 0; k < m->slabs.size(); k++) {
@@ -963,6 +1002,12 @@ int csxb_spmv_host(csxb_matrix_t *m, double alpha, const double *h_x, double bet
     // CsxSpmv.cpp:52-64 — the same as csxb_spmv on device vectors)
     if (overwrite && last_local && m->covered_rows_end < m->host.nrows)
       for (int64_t r = m->covered_rows_end; r < m->host.nrows; r++) h_y[r] = 0.0;
+    if (tune_call >= 0) {
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - call_t0).count();
+      if (tune_call > 0) { double &best = m->host_tune_s[tune_call % 2]; best = best == 0.0 ? dt : std::min(best, dt); }
+      if (tune_call == 4) m->host_cap = m->host_tune_s[0] < m->host_tune_s[1] ? HOST_CAP_SMEM : 0;
+      m->host_calls++;
+    }
   }
   if (cur != m->device && cur >= 0) CUDA_TRY(cudaSetDevice(cur));
   return 0;
