@@ -61,7 +61,8 @@ enum { CSXB_NROWS = 0, CSXB_NCOLS = 1, CSXB_NNZ = 2, CSXB_SYMMETRIC = 3, CSXB_NP
        CSXB_SYM_HALO_LO = 8, CSXB_SYM_HALO_HI = 9,
        /* csxb_spmv_host: bytes of dynamic shared memory that cap the resident CTAs of the slab kernels (chosen by timing
         * the first calls), and the number of calls so far */
-       CSXB_HOST_CAP = 10, CSXB_HOST_CALLS = 11 };
+       CSXB_HOST_CAP = 10, CSXB_HOST_CALLS = 11,
+       CSXB_DEVICE = 12 /* the device the matrix was uploaded to, -1 before csxb_upload */ };
 int64_t csxb_info(const csxb_matrix_t *m, int what);
 
 /* Per-partition CSX arrays == csx_matrix_t / csx_sym_matrix_t / map_t

@@ -543,7 +543,9 @@ static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx
     }
     return SPX_SUCCESS;
   }
-  cudaSetDevice(g_device);
+  // the device the matrix lives on, not the current value of spx.b200.device (it may have changed since spx_mat_tune)
+  const int device = (int)csxb_info(A->csx, CSXB_DEVICE);
+  cudaSetDevice(device);
   const double *dx = x->elements;
   double *dy = y->elements;
   bool x_host = !is_managed(x), y_host = !is_managed(y);
@@ -565,7 +567,7 @@ static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx
     }
     dx = A->stage_x;
   } else {
-    cudaMemPrefetchAsync(x->elements, x->size * 8, g_device, 0);
+    cudaMemPrefetchAsync(x->elements, x->size * 8, device, 0);
   }
   if (y_host) {
     if (!A->stage_y && cudaMalloc((void **)&A->stage_y, (size_t)(A->nrows ? A->nrows : 1) * 8) != cudaSuccess) {
@@ -575,7 +577,7 @@ static spx_error_t run_spmv(const spx_matrix_t *Ac, spx_value_t alpha, const spx
     if (!overwrite) cudaMemcpyAsync(A->stage_y, y->elements, (size_t)A->nrows * 8, cudaMemcpyHostToDevice, 0);
     dy = A->stage_y;
   } else {
-    cudaMemPrefetchAsync(y->elements, y->size * 8, g_device, 0);
+    cudaMemPrefetchAsync(y->elements, y->size * 8, device, 0);
   }
   if (csxb_spmv(A->csx, alpha, dx, beta, dy, overwrite, nullptr) != 0) {
     spx_err_get_handler()(SPX_ERR_TUNED_MAT, __FILE__, __LINE__, __func__, "%s", csxb_last_error());

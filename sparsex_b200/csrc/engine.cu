@@ -427,6 +427,7 @@ int64_t csxb_info(const csxb_matrix_t *m, int what) {
     case CSXB_SYM_HALO_HI: return m->sym_halo_hi;
     case CSXB_HOST_CAP: return (int64_t)m->host_cap;
     case CSXB_HOST_CALLS: return m->host_calls;
+    case CSXB_DEVICE: return m->uploaded ? m->device : -1;
   }
   return -1;
 }
