@@ -159,10 +159,14 @@ int csxb_group_set_perm(csxb_group_t *g, const int32_t *perm, int64_t n);
  * boost::cuthill_mckee_ordering).  Host code.  csxb_rcm_csr: zero-based square CSR; perm[old] = new (what
  * spx_mat_get_perm returns); bandwidth[0/1] (may be NULL) = bandwidth before / after.  Returns 0, 1 when the matrix
  * has no off-diagonal element ("no reordering available for this matrix", the input stays as it is), < 0 on bad
- * arguments.  csxb_permute_csr: B = P A P^T into caller-allocated arrays of the same sizes (row i of B = row
+ * arguments.  csxb_rcm_edges: the same ordering for an explicit list of undirected edges (added in the given order); start >= 0
+ * names the starting vertex of a connected graph (boost's cuthill_mckee_ordering(G, s, ...)), -1 lets the algorithm pick.
+ * csxb_permute_csr: B = P A P^T into caller-allocated arrays of the same sizes (row i of B = row
  * inv_perm[i] of A, columns through perm, sorted; Rcm.hpp:289-316, Csr.hpp:270-360). */
 int csxb_rcm_csr(const int32_t *rowptr, const int32_t *colind, int64_t nrows, int64_t ncols, int32_t *perm,
                  int64_t *bandwidth);
+int csxb_rcm_edges(const int32_t *eu, const int32_t *ev, int64_t nedges, int64_t n, int64_t start, int32_t *perm,
+                   int64_t *bandwidth);
 /* The permutation is kept with the tuned matrix and stored by csxb_save (matvec.c:298, 422, 445).  get returns the
  * length (0 = none) and copies when perm is not NULL. */
 int csxb_set_perm(csxb_matrix_t *m, const int32_t *perm, int64_t n);

@@ -7,7 +7,8 @@
 // this file restates the published BGL code — boost/graph/cuthill_mckee_ordering.hpp and
 // boost/graph/detail/sparse_ordering.hpp — keeping its structure: an adjacency list filled by add_edge, a
 // breadth_first_visit with visitor hooks, the rcm_queue of pseudo_peripheral_pair, the sparse_ordering_queue and the
-// bfs_rcm_visitor of the ordering itself.  PARITY UNPINNED: it cannot be checked against Boost here.
+// bfs_rcm_visitor of the ordering itself.  Boost cannot be run here; the pin is the sample output the BGL documentation
+// prints for Boost's own example program (three orderings of a 10-vertex graph), reproduced in tests/test_cpu_rcm.py.
 #include <algorithm>
 #include <cstdint>
 #include <deque>
@@ -142,21 +143,18 @@ void dfs_mark(const Graph &G, int s, std::vector<Color> &color) {   // depth_fir
 
 }  // namespace
 
-// rowptr/colind zero-based, n x n.  perm[old] = new.  Returns 0, or 1 when no edge exists (Rcm.hpp:275-279).
-extern "C" int rcm_oracle_csr(const int32_t *rowptr, const int32_t *colind, int64_t n, int symmetric, int32_t *perm) {
-  Graph graph((size_t)n);
-  size_t edges = 0;
-  for (int64_t r = 0; r < n; r++)
-    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++)
-      if (symmetric ? r < colind[k] : r != colind[k]) { graph.add_edge((int)r, colind[k]); edges++; }
-  if (!edges) return 1;
-
-  // cuthill_mckee_ordering(G, permutation, color, degree)
+static int order_graph(Graph &graph, int64_t n, int32_t *perm, int start = -1) {
   std::vector<Color> color((size_t)n, WHITE);
   std::deque<int> vertex_queue;
-  for (int64_t v = 0; v < n; v++)
-    if (color[v] == WHITE) { dfs_mark(graph, (int)v, color); vertex_queue.push_back((int)v); }
-  for (int &s : vertex_queue) s = find_starting_node(graph, s, color);
+  if (start >= 0) {
+    // cuthill_mckee_ordering(G, s, permutation, color, degree): the caller names the starting vertex (connected graphs)
+    vertex_queue.push_front(start);
+  } else {
+    // cuthill_mckee_ordering(G, permutation, color, degree)
+    for (int64_t v = 0; v < n; v++)
+      if (color[v] == WHITE) { dfs_mark(graph, (int)v, color); vertex_queue.push_back((int)v); }
+    for (int &s : vertex_queue) s = find_starting_node(graph, s, color);
+  }
   // cuthill_mckee_ordering(G, vertex_queue, permutation, color, degree)
   std::vector<int> visit_order;
   OrderingQueue Q;
@@ -172,4 +170,23 @@ extern "C" int rcm_oracle_csr(const int32_t *rowptr, const int32_t *colind, int6
   for (int64_t k = 0; k < n; k++) inv_perm[(size_t)(n - 1 - k)] = visit_order[(size_t)k];
   for (int64_t i = 0; i < n; i++) perm[inv_perm[(size_t)i]] = (int32_t)i;
   return 0;
+}
+
+// rowptr/colind zero-based, n x n.  perm[old] = new.  Returns 0, or 1 when no edge exists (Rcm.hpp:275-279).
+extern "C" int rcm_oracle_csr(const int32_t *rowptr, const int32_t *colind, int64_t n, int symmetric, int32_t *perm) {
+  Graph graph((size_t)n);
+  size_t edges = 0;
+  for (int64_t r = 0; r < n; r++)
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++)
+      if (symmetric ? r < colind[k] : r != colind[k]) { graph.add_edge((int)r, colind[k]); edges++; }
+  if (!edges) return 1;
+  return order_graph(graph, n, perm);
+}
+
+// The same for an explicit edge list, added in the given order (known-answer graphs).
+extern "C" int rcm_oracle_edges(const int32_t *eu, const int32_t *ev, int64_t ne, int64_t n, int start, int32_t *perm) {
+  Graph graph((size_t)n);
+  for (int64_t e = 0; e < ne; e++) graph.add_edge(eu[e], ev[e]);
+  if (!ne) return 1;
+  return order_graph(graph, n, perm, start);
 }

@@ -99,7 +99,7 @@ std::string read_mmf(const char *path, CooHost &out);
 
 // rcm.cpp — reference: include/sparsex/internals/Rcm.hpp:116-340 (Boost Graph Library's cuthill_mckee_ordering restated)
 bool rcm_find_perm(int64_t n, const std::vector<int32_t> &eu, const std::vector<int32_t> &ev, std::vector<int32_t> &perm,
-                   std::vector<int32_t> &inv_perm, int64_t *bandwidth);
+                   std::vector<int32_t> &inv_perm, int64_t *bandwidth, int64_t start = -1);
 void rcm_edges_csr(const int32_t *rowptr, const int32_t *colind, int64_t nrows, bool symmetric, std::vector<int32_t> &eu,
                    std::vector<int32_t> &ev);
 void rcm_edges_coo(const CooHost &coo, std::vector<int32_t> &eu, std::vector<int32_t> &ev);

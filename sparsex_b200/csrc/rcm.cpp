@@ -18,9 +18,12 @@
 //               (the same call on the same sequence here, so ties fall the same way under the same libstdc++);
 //   reversal    the output iterator is inv_perm.rbegin(); perm[inv_perm[i]] = i (Rcm.hpp:131-142).
 //
-// Parity of this file against Boost itself is UNPINNED (Boost cannot be run here); tests/test_cpu_rcm.py pins it to a
-// literal Python transcription of the same published algorithm and checks the properties the reference relies on
-// (perm is a bijection, B = P A P^T, SpMV results agree after spx_vec_reorder / spx_vec_inv_reorder).
+// Boost cannot be run here.  The pin against it is the sample output the BGL documentation prints for Boost's own example
+// program (libs/graph/example/cuthill_mckee_ordering.cpp: 10 vertices, 14 edges; the orderings from vertex 6, from vertex 0
+// and without a starting vertex, bandwidth 8 -> 4), which this file reproduces (tests/test_cpu_rcm.py:
+// test_boost_documentation_example); beyond that it equals the structural restatement in oracle/rcm_oracle.cpp on seeded
+// graphs, and the properties the reference relies on hold (perm is a bijection, B = P A P^T, SpMV results agree after
+// spx_vec_reorder / spx_vec_inv_reorder).
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -112,7 +115,7 @@ int64_t bandwidth_of(const std::vector<int32_t> &eu, const std::vector<int32_t> 
 // FindPerm (Rcm.hpp:116-153).  perm: old index -> new index; inv_perm: new -> old.  bandwidth[0/1]: before / after
 // (what the reference logs).  Returns false when there is no edge ("no reordering available for this matrix").
 bool rcm_find_perm(int64_t n, const std::vector<int32_t> &eu, const std::vector<int32_t> &ev, std::vector<int32_t> &perm,
-                   std::vector<int32_t> &inv_perm, int64_t *bandwidth) {
+                   std::vector<int32_t> &inv_perm, int64_t *bandwidth, int64_t start) {
   if (eu.empty() || n <= 0) return false;
   Graph g;
   build_graph(n, eu, ev, g);
@@ -121,9 +124,11 @@ bool rcm_find_perm(int64_t n, const std::vector<int32_t> &eu, const std::vector<
   std::vector<int32_t> queue;
   queue.reserve(n);
 
-  // one representative per component, lowest vertex first
+  // one representative per component, lowest vertex first (or the one starting vertex the caller names:
+  // cuthill_mckee_ordering(G, s, ...), for connected graphs)
   std::vector<int32_t> starts;
-  {
+  if (start >= 0) starts.push_back((int32_t)start);
+  else {
     std::vector<int32_t> stack;
     ++stamp;
     for (int64_t v = 0; v < n; v++) {
@@ -139,8 +144,9 @@ bool rcm_find_perm(int64_t n, const std::vector<int32_t> &eu, const std::vector<
       }
     }
   }
-  for (int32_t &s : starts)
-    if (g.degree(s) > 0) s = find_starting_node(g, s, mark, stamp, queue);   // an isolated vertex is its own start
+  if (start < 0)
+    for (int32_t &s : starts)
+      if (g.degree(s) > 0) s = find_starting_node(g, s, mark, stamp, queue);   // an isolated vertex is its own start
 
   // Cuthill-McKee: BFS per component, each vertex's newly discovered neighbours sorted by degree
   std::vector<int32_t> order;
@@ -163,6 +169,7 @@ bool rcm_find_perm(int64_t n, const std::vector<int32_t> &eu, const std::vector<
       std::sort(queue.begin() + index_begin, queue.end(), by_degree);   // finish_vertex
     }
   }
+  if ((int64_t)order.size() != n) return false;   // a named starting vertex only reaches its own component
   // written through inv_perm.rbegin(): reversed
   inv_perm.assign(n, 0);
   perm.assign(n, 0);
@@ -227,6 +234,19 @@ int csxb_rcm_csr(const int32_t *rowptr, const int32_t *colind, int64_t nrows, in
   spxb::rcm_edges_csr(rowptr, colind, nrows, false, eu, ev);
   if (!spxb::rcm_find_perm(nrows, eu, ev, p, ip, bandwidth)) return 1;
   std::memcpy(perm, p.data(), sizeof(int32_t) * (size_t)nrows);
+  return 0;
+}
+
+// The ordering of an explicit undirected edge list (edges added in the given order): what csxb_rcm_csr runs after it
+// has listed the off-diagonal elements.  For callers that hold a graph rather than a matrix, and for known-answer tests.
+int csxb_rcm_edges(const int32_t *eu, const int32_t *ev, int64_t nedges, int64_t n, int64_t start, int32_t *perm,
+                   int64_t *bandwidth) {
+  if (!eu || !ev || !perm || n <= 0 || nedges < 0 || start >= n) return -1;
+  for (int64_t e = 0; e < nedges; e++)
+    if (eu[e] < 0 || eu[e] >= n || ev[e] < 0 || ev[e] >= n || eu[e] == ev[e]) return -1;
+  std::vector<int32_t> u(eu, eu + nedges), v(ev, ev + nedges), p, ip;
+  if (!spxb::rcm_find_perm(n, u, v, p, ip, bandwidth, start)) return 1;
+  std::memcpy(perm, p.data(), sizeof(int32_t) * (size_t)n);
   return 0;
 }
 

@@ -1,6 +1,7 @@
 """Reverse Cuthill-McKee (spx_mat_tune(..., SPX_MAT_REORDER); reference Rcm.hpp:116-340 on boost::cuthill_mckee_ordering).
 
-Boost is not available here, so parity against it is UNPINNED; what is checked:
+Boost is not available here; the pin against it is the sample output Boost publishes for its own example program
+(test_boost_documentation_example).  Further checks:
 * the product (flat arrays, sparsex_b200/csrc/rcm.cpp) equals the oracle (oracle/rcm_oracle.cpp, a structural
   restatement of the published BGL code) on seeded matrices: connected, disconnected, with isolated vertices,
   structurally non-symmetric, with long degree ties (std::sort on > 16 elements);
@@ -119,6 +120,35 @@ def test_known_answer():
     assert perm.tolist() == [3, 1, 2, 4, 0]
     assert oracle_rcm(rp, ci, 5).tolist() == [3, 1, 2, 4, 0]
     assert bw == (3, 1)
+
+
+def test_boost_documentation_example():
+    """The graph and the sample output of Boost's own example, libs/graph/example/cuthill_mckee_ordering.cpp as printed in
+    the BGL documentation (doc/cuthill_mckee_ordering.html, "Sample Output"): original bandwidth 8; reverse Cuthill-McKee
+    ordering starting at 6: 8 3 0 9 2 5 1 4 7 6; starting at 0: 9 1 4 6 7 2 8 5 3 0; without a starting vertex (the call
+    Rcm.hpp:136 makes): 0 8 5 7 3 6 4 2 1 9; bandwidth 4 each time.  The printed sequence is inv_perm (new position -> old
+    vertex).  Product and oracle must both reproduce it."""
+    edges = [(0, 3), (0, 5), (1, 2), (1, 4), (1, 6), (1, 9), (2, 3), (2, 4), (3, 5), (3, 8), (4, 6), (5, 6), (5, 7), (6, 7)]
+    eu = np.array([e[0] for e in edges], np.int32)
+    ev = np.array([e[1] for e in edges], np.int32)
+    O = C.CDLL(pyoracle.build())
+    O.rcm_oracle_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+    L = engine.lib()
+    L.csxb_rcm_edges.restype = C.c_int
+    L.csxb_rcm_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    published = {6: [8, 3, 0, 9, 2, 5, 1, 4, 7, 6], 0: [9, 1, 4, 6, 7, 2, 8, 5, 3, 0], -1: [0, 8, 5, 7, 3, 6, 4, 2, 1, 9]}
+    for start, want in published.items():
+        perm = np.zeros(10, np.int32)
+        assert O.rcm_oracle_edges(eu.ctypes.data, ev.ctypes.data, len(edges), 10, start, perm.ctypes.data) == 0
+        assert np.argsort(perm).tolist() == want
+        perm2 = np.zeros(10, np.int32)
+        bw = np.zeros(2, np.int64)
+        assert L.csxb_rcm_edges(eu.ctypes.data, ev.ctypes.data, len(edges), 10, start, perm2.ctypes.data, bw.ctypes.data) == 0
+        assert np.argsort(perm2).tolist() == want and bw.tolist() == [8, 4]
+    # a named starting vertex only orders a connected graph
+    eu2 = np.array([0, 2], np.int32); ev2 = np.array([1, 3], np.int32)
+    assert L.csxb_rcm_edges(eu2.ctypes.data, ev2.ctypes.data, 2, 4, 0, perm2.ctypes.data, None) == 1
+    assert L.csxb_rcm_edges(eu2.ctypes.data, ev2.ctypes.data, 2, 4, -1, perm2.ctypes.data, None) == 0
 
 
 def test_no_offdiagonal_and_bad_arguments():
